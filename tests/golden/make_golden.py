@@ -1,0 +1,188 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures under tests/golden/ by running the UNMODIFIED reference.
+
+Run here (the container that has /root/reference); the fixtures are committed so that the GPU box
+(which has no reference) can check both the oracle and the CUDA path against real reference output.
+
+    python tests/golden/make_golden.py [name ...]
+
+Each fixture is an .npz holding (a) the flattened problem -- the exact arrays the reference's own
+setup code produced (oracle/refharness/extract.py) -- and (b) what the reference's Context computed
+from them: dJ/dPops history and J, I, Gamma, n at selected iterations of the test.py loop.
+
+Fixtures
+  c1_falc_ca        test.py's problem: CaII active, H passive, FALC, 5 rays (BASELINE configs 0/1); run to convergence
+  c2_falc_cah       CaII + H active, FALC, 5 rays (C2 of SURVEY 8); 12 iterations + iteration count to convergence
+  c1v_jitter_ca3    CaII active, 3 rays, config-4 jitter recipe column 0 (T, ne, non-zero vlos): phi differs up/down
+  rf_k40p, rf_k10m  response_fn.py columns: T[k] +/- 25 K, warm-started from the converged c1 populations
+  units             formal-solver / w2 / planck / uv known answers
+"""
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle.refharness import load_reference, build_falc_setup  # noqa: E402
+from oracle.refharness.extract import problem_from_reference_context  # noqa: E402
+
+
+def jitter_modifier(col, ref):
+    """SURVEY.md 8(d) item 4 jitter recipe."""
+    u = sys.modules['astropy.units']
+
+    def smooth(g):
+        return np.convolve(np.pad(g, 2, 'edge'), np.ones(5) / 5, 'valid')
+
+    def mod(ac):
+        rng = np.random.default_rng(20260000 + col)
+        n = ac.temperature.shape[0]
+        g1, g2, g3 = (smooth(rng.standard_normal(n)) for _ in range(3))
+        ac.temperature = (ac.temperature.value * np.exp(0.01 * g1)) << u.K
+        ac.ne = (ac.ne.value * np.exp(0.05 * g2)) << (u.m ** -3)
+        ac.vlos = (2000.0 * g3) << (u.m / u.s)
+        return ac
+    return mod
+
+
+def run(ctx, max_iter, keep_full, keep_small):
+    """test.py:20-29 loop with snapshots.  Returns dict of arrays."""
+    out = {}
+    hist = []
+    dJ, dPops, i = 1.0, 1.0, 0
+    while (dJ > 2e-3 or dPops > 1e-3) and i < max_iter:
+        i += 1
+        dJ = ctx.formal_sol_gamma_matrices()
+        if i in keep_small or i in keep_full:
+            # Gamma as left by formal_sol_gamma_matrices (before stat_equil touches n)
+            out['it%d_Gamma' % i] = np.concatenate(
+                [a.Gamma.reshape(a.Nlevel * a.Nlevel, -1) for a in ctx.activeAtoms], axis=0)
+        if i > 3:
+            dPops = ctx.stat_equil()
+        hist.append((dJ, dPops))
+        if i in keep_small or i in keep_full:
+            out['it%d_I' % i] = np.array(ctx.I)
+            out['it%d_n' % i] = np.concatenate([a.n for a in ctx.activeAtoms], axis=0)
+            out['it%d_Jsum' % i] = np.array([ctx.J.sum(), np.abs(ctx.J).max()])
+        if i in keep_full:
+            out['it%d_J' % i] = np.array(ctx.J)
+    out['hist'] = np.array(hist)
+    out['niter'] = np.array(i)
+    out['converged'] = np.array(not (dJ > 2e-3 or dPops > 1e-3))
+    out['final_I'] = np.array(ctx.I)
+    out['final_J'] = np.array(ctx.J)
+    out['final_n'] = np.concatenate([a.n for a in ctx.activeAtoms], axis=0)
+    return out
+
+
+def save(name, problem, results, extra=None):
+    d = {'p_' + k: v for k, v in problem.items()}
+    d.update({'r_' + k: v for k, v in results.items()})
+    if extra:
+        d.update(extra)
+    path = os.path.join(HERE, name + '.npz')
+    np.savez_compressed(path, **d)
+    print('%-18s %8.2f MB  niter=%s converged=%s' % (name, os.path.getsize(path) / 1e6, results.get('niter'),
+                                                   results.get('converged')))
+
+
+def make_c1(ref):
+    atmos, spect, eqPops, bg = build_falc_setup(active=('Ca',), nrays=5)
+    ctx = ref['rh_method'].Context(atmos, spect, eqPops, bg)
+    p = problem_from_reference_context(ctx)
+    r = run(ctx, 1000, keep_full={1, 4, 5}, keep_small={2, 3, 6, 10, 20, 30, 46})
+    save('c1_falc_ca', p, r)
+    return r['final_n']
+
+
+def make_c2(ref):
+    atmos, spect, eqPops, bg = build_falc_setup(active=('Ca', 'H'), nrays=5)
+    ctx = ref['rh_method'].Context(atmos, spect, eqPops, bg)
+    p = problem_from_reference_context(ctx)
+    r = run(ctx, 12, keep_full={1, 5}, keep_small={4, 6, 8, 12})
+    save('c2_falc_cah', p, r)
+
+
+def make_c1v(ref):
+    atmos, spect, eqPops, bg = build_falc_setup(active=('Ca',), nrays=3, modify_constructor=jitter_modifier(0, ref))
+    ctx = ref['rh_method'].Context(atmos, spect, eqPops, bg)
+    p = problem_from_reference_context(ctx)
+    r = run(ctx, 10, keep_full={1, 5}, keep_small={4, 6, 10})
+    save('c1v_jitter_ca3', p, r)
+
+
+def make_rf(ref, start_n, k, pert, name):
+    u = sys.modules['astropy.units']
+
+    def mod(ac):
+        ac.temperature[k] += pert << u.K     # response_fn.py:26
+        return ac
+    atmos, spect, eqPops, bg = build_falc_setup(active=('Ca',), nrays=5, modify_constructor=mod,
+                                                start_pops={'Ca': start_n})
+    ctx = ref['rh_method'].Context(atmos, spect, eqPops, bg)
+    p = problem_from_reference_context(ctx)
+    r = run(ctx, 1000, keep_full={1}, keep_small={2, 4})
+    save(name, p, r)
+
+
+def make_units(ref):
+    fs = ref['formal_solver']
+    rng = np.random.default_rng(12345)
+    out = {}
+    # w2 at its three branches (formal_solver.py:34-43)
+    dt = np.array([1e-9, 1e-6, 4.9999e-4, 5e-4, 5.0001e-4, 1e-3, 0.1, 1.0, 7.3, 49.9, 50.0, 50.0001, 80.0, 1e4])
+    out['w2_dtau'] = dt
+    out['w2_w'] = np.array([fs.w2(x) for x in dt])
+    # planck
+    T = np.array([4170.0, 5000.0, 6520.0, 9400.0, 1.0e5])
+    wav = np.array([30.0, 91.17, 121.567, 393.366, 500.0, 854.209, 2000.0])
+    out['planck_T'] = T
+    out['planck_wav'] = wav
+    out['planck_B'] = np.array([[ref['utils'].planck(np.array([t]), w)[0] for w in wav] for t in T])
+
+    # piecewise_linear_1d on synthetic atmospheres covering all w2 branches
+    class A:
+        pass
+    cases = []
+    for N, scale in ((82, 1e-7), (82, 1e-4), (33, 1e-2), (7, 1.0), (3, 1e-6), (200, 1e-5)):
+        a = A()
+        a.Nspace = N
+        a.height = np.sort(rng.uniform(0, 2.0e6, N))[::-1].copy()
+        a.temperature = rng.uniform(4000, 9000, N)
+        a.muz = np.array([0.0469100770306680, 0.5, 0.9530899229693319])
+        chi = scale * np.exp(rng.normal(0, 2.0, N)) * np.exp(np.linspace(-6, 6, N))
+        S = rng.uniform(1e-9, 5e-8, N)
+        for mu in range(3):
+            for toFrom in (0, 1):
+                wv = float(rng.uniform(100, 900))
+                r = fs.piecewise_linear_1d(a, mu, toFrom, wv, chi, S)
+                cases.append((a.height, a.temperature, a.muz[mu], toFrom, wv, chi, S, r.I, r.PsiStar))
+    out['fs_ncase'] = np.array(len(cases))
+    for i, c in enumerate(cases):
+        for nm, v in zip(('z', 'T', 'mu', 'toFrom', 'wav', 'chi', 'S', 'I', 'Psi'), c):
+            out['fs%d_%s' % (i, nm)] = np.asarray(v)
+    np.savez_compressed(os.path.join(HERE, 'units.npz'), **out)
+    print('units              %8.2f MB' % (os.path.getsize(os.path.join(HERE, 'units.npz')) / 1e6))
+
+
+if __name__ == '__main__':
+    which = set(sys.argv[1:])
+    ref = load_reference()
+    t0 = time.time()
+    if not which or 'units' in which:
+        make_units(ref)
+    final_n = None
+    if not which or which & {'c1', 'rf'}:
+        final_n = make_c1(ref)
+    if not which or 'rf' in which:
+        make_rf(ref, final_n, 40, +25.0, 'rf_k40p')
+        make_rf(ref, final_n, 10, -25.0, 'rf_k10m')
+    if not which or 'c2' in which:
+        make_c2(ref)
+    if not which or 'c1v' in which:
+        make_c1v(ref)
+    print('done in %.0f s' % (time.time() - t0))
