@@ -1,0 +1,149 @@
+/*
+ * mali_b200.h -- C ABI of the B200-native MALI hot path (libmali_b200.so).
+ *
+ * The Lightspinner reference is pure Python and has no FFI layer; the boundary it offers is
+ * the Python API of rh_method.Context.  Every entry point below is therefore the C-level twin of one
+ * reference method, and lightspinner_b200/context.py binds them with ctypes behind the reference's own
+ * call signatures (INTEGRATION.md shows the stub a maintainer would add to the reference).
+ *
+ *   reference (file:line)                                   entry point
+ *   ------------------------------------------------------  ---------------------------------
+ *   Context.__init__            rh_method.py:531-563        mali_model_create, mali_upload_columns
+ *   ComputationalAtom.setup_wavelength  rh_method.py:425-455 (tables built once by mali_upload_columns)
+ *   Context.formal_sol_gamma_matrices   rh_method.py:565-708 mali_formal_sol_gamma
+ *   ComputationalTransition.uv  rh_method.py:245-288        (fused into mali_formal_sol_gamma); mali_uv = test hook
+ *   piecewise_linear_1d         formal_solver.py:144-212    (fused into mali_formal_sol_gamma); mali_piecewise_linear_1d = test hook
+ *   planck                      utils.py:17-22              mali_planck_bc (host helper for the lower boundary)
+ *   Context.stat_equil          rh_method.py:710-745        mali_stat_equil
+ *   test.py:20-29 / response_fn.py:11-21 (the MALI loop)    mali_iterate (device-resident loop, per-column convergence)
+ *
+ * Conventions
+ *   - plain C, no exceptions; every function returns 0 on success, a negative MALI_E* code on argument
+ *     errors, or a positive cudaError_t; mali_last_error() gives the message for the calling thread.
+ *   - all `*_dev` / mali_buffers pointers are DEVICE pointers owned by the caller (the Python layer carries
+ *     them in torch tensors); the library owns only the model descriptors it uploads in mali_model_create.
+ *   - everything is IEEE fp64; the kernels are compiled with --fmad=false and evaluate every expression in
+ *     the reference's order.
+ *   - all launches are asynchronous on the given stream (a cudaStream_t passed as void*).
+ *   - column batches: every per-column array is [ncol][...]; a launch works on columns [col0, col0+ncol).
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef MALI_B200_H
+#define MALI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MALI_OK 0
+#define MALI_EINVAL (-1)   /* bad argument */
+#define MALI_ENOMEM (-2)
+#define MALI_ELIMIT (-3)   /* problem exceeds a compiled-in limit (Nrays > 32, Nlevel > 16, Nspace < 3, ...) */
+
+#define MALI_TRANS_STRIDE 6 /* atom, i, j, isLine, Nblue, Nlambda */
+
+typedef struct mali_model mali_model; /* opaque */
+
+/* Host-side description of the radiative model shared by all columns of a batch.
+ * trans rows are in the reference's order: atoms as in Context.activeAtoms, within an atom lines then
+ * continua (rh_method.py:398-405).  A transition is active on wavelengths [Nblue, Nblue+Nlambda).
+ * The per-wavelength tables are concatenated over transitions (offset = running sum of Nlambda). */
+typedef struct {
+    int32_t Nspace, Nrays, Nspect, Natom, Ntrans;
+    const int32_t *Nlevel;     /* [Natom] */
+    const int32_t *trans;      /* [Ntrans][MALI_TRANS_STRIDE] */
+    const double *wavelength;  /* [Nspect] nm */
+    const double *muz, *wmu;   /* [Nrays] */
+    const double *lineconst;   /* [Ntrans][3]: hc/4pi*Bij, Aji/Bji, Bji/Bij (lines) */
+    const double *wlambda;     /* concat: rh_method.py:157-196 */
+    const double *alpha;       /* concat: continuum cross-sections */
+    const double *twohc_l3;    /* concat: 2hc/(NM_TO_M lambda)^3 (continua) */
+    const double *wlacont;     /* concat: wlambda/lambda/h (continua) */
+} mali_model_desc;
+
+/* Sizes (in doubles, per column) of every caller-owned array, and the offsets of the reference-layout
+ * arrays inside one column's host staging block ("host pack": plain concatenation, no transposition). */
+typedef struct {
+    int64_t hostpack;  /* staging block: what mali_upload_columns copies host->device */
+    int64_t colconst;  /* packed iteration-invariant device block (depth-major, wavelength-contiguous) */
+    int64_t pops;      /* sumNlevel * Nspace        n[level][k]            (in/out) */
+    int64_t J;         /* Nspace * Nspect           J[k][la]  (depth-major) (in/out) */
+    int64_t I;         /* Nspect * Nrays            I[la][mu]               (out) */
+    int64_t Gamma;     /* sum Nlevel^2 * Nspace     Gamma[i][j][k] per atom (out) */
+    int64_t scratch;   /* library scratch per column */
+    /* offsets inside the host pack (reference layouts): */
+    int64_t hp_height;   /* [Nspace] */
+    int64_t hp_bbc;      /* [Nspect][2]  planck(T[-2:], wav)  (formal_solver.py:206) */
+    int64_t hp_bg_chi, hp_bg_eta, hp_bg_sca; /* [Nspect][Nspace] */
+    int64_t hp_C;        /* concat atoms [Nlevel][Nlevel][Nspace] */
+    int64_t hp_nTotal;   /* [Natom][Nspace] */
+    int64_t hp_phi;      /* concat lines, each [Nlambda][Nrays][2][Nspace] (rh_method.py:224) */
+    int64_t hp_wphi;     /* [Ntrans][Nspace] */
+    int64_t hp_gijcont;  /* concat [offset+lt][Nspace], continua rows only (rh_method.py:453-454) */
+    int64_t hp_n;        /* [sumNlevel][Nspace] starting populations */
+    int32_t sumNlevel, sumNlevel2, ntile, lambda_per_warp;
+} mali_layout;
+
+/* Caller-owned device buffers for a batch of `ncol` columns. */
+typedef struct {
+    int32_t ncol;
+    double *colconst;  /* [ncol][layout.colconst] */
+    double *pops;      /* [ncol][layout.pops]     */
+    double *J;         /* [ncol][layout.J]        */
+    double *I;         /* [ncol][layout.I]        */
+    double *Gamma;     /* [ncol][layout.Gamma]    */
+    double *scratch;   /* [ncol][layout.scratch]  */
+    double *dJ;        /* [ncol] max |1 - Jold/Jnew| of the last formal solution (NaN-propagating) */
+    double *dPops;     /* [ncol] max |1 - nold/nnew| of the last stat_equil */
+    int32_t *status;   /* [ncol] bit 0: a singular / non-finite statistical-equilibrium system was met */
+    int32_t *iter;     /* [ncol] iterations done by mali_iterate */
+    int32_t *done;     /* [ncol] non-zero: column is skipped by the compute entry points (converged) */
+} mali_buffers;
+
+const char *mali_last_error(void);
+int mali_device_count(void);
+
+int mali_model_create(const mali_model_desc *desc, int device, mali_model **out);
+void mali_model_destroy(mali_model *m);
+int mali_model_layout(const mali_model *m, mali_layout *out);
+
+/* Host helper: out[la][0..1] = planck(T[Nspace-2]), planck(T[Nspace-1]) at wavelength[la]  (utils.py:17-22, glibc exp). */
+int mali_planck_bc(const double *wavelength, int32_t Nspect, double Tm2, double Tm1, double *out);
+
+/* Copies ncol host-pack blocks host->device (cudaMemcpyAsync; pin the host memory) into staging_dev
+ * ([ncol][layout.hostpack] doubles) and packs them into bufs->colconst / pops for columns [col0, col0+ncol).
+ * host_pack may be NULL when staging_dev already holds the blocks.  Also zeroes J for those columns. */
+int mali_upload_columns(const mali_model *m, const mali_buffers *bufs, int32_t col0, int32_t ncol,
+                        const double *host_pack, double *staging_dev, void *stream);
+
+/* Context.formal_sol_gamma_matrices for columns [col0, col0+ncol): updates J (J-dagger is read from the
+ * same buffer), I, Gamma and dJ. */
+int mali_formal_sol_gamma(const mali_model *m, const mali_buffers *bufs, int32_t col0, int32_t ncol, void *stream);
+
+/* Context.stat_equil for columns [col0, col0+ncol): updates pops in place, writes dPops and status. */
+int mali_stat_equil(const mali_model *m, const mali_buffers *bufs, int32_t col0, int32_t ncol, void *stream);
+
+/* The loop of test.py:20-29 kept on the device: up to max_iter iterations of formal solution (+ stat_equil once
+ * a column's own iteration counter exceeds 3); a column whose (dJ, dPops) satisfy dJ <= tolJ && dPops <= tolPops
+ * is flagged done and no longer touched.  tolJ < 0 disables the convergence test (fixed iteration count).
+ * Captured into a CUDA graph per (model, ncol) internally.  bufs->iter / done must be zeroed by the caller first. */
+int mali_iterate(const mali_model *m, const mali_buffers *bufs, int32_t col0, int32_t ncol, int32_t max_iter,
+                 double tolJ, double tolPops, void *stream);
+
+/* Test hooks ---------------------------------------------------------------------------------------------- */
+/* piecewise_linear_1d for nray independent rays: chi, S, I, Psi are [nray][Nspace]; muz, bbc0/bbc1 (planck at
+ * T[-2], T[-1]) and toFrom are per ray; z is [Nspace] (shared). */
+int mali_piecewise_linear_1d(int32_t Nspace, int32_t nray, const double *z_dev, const double *muz_dev,
+                             const int32_t *toFrom_dev, const double *bbc0_dev, const double *bbc1_dev,
+                             const double *chi_dev, const double *S_dev, double *I_dev, double *Psi_dev,
+                             void *stream);
+/* ComputationalTransition.uv(la, mu, toFrom) for transition t of column col: writes Uji, Vij, Vji [Nspace]. */
+int mali_uv(const mali_model *m, const mali_buffers *bufs, int32_t col, int32_t t, int32_t la, int32_t mu,
+            int32_t toFrom, double *Uji_dev, double *Vij_dev, double *Vji_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MALI_B200_H */

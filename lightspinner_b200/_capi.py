@@ -1,0 +1,78 @@
+"""ctypes binding of libmali_b200.so (include/mali_b200.h).  Thin on purpose: plain pointers and sizes.
+
+There is no CPU fallback: if the library is missing or was not built, importing the compute layer fails loudly.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, '_lib', 'libmali_b200.so')
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+
+
+class MaliError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__('libmali_b200 error %d: %s' % (code, msg))
+        self.code = code
+
+
+class ModelDesc(C.Structure):
+    _fields_ = [('Nspace', C.c_int32), ('Nrays', C.c_int32), ('Nspect', C.c_int32), ('Natom', C.c_int32),
+                ('Ntrans', C.c_int32), ('Nlevel', _ip), ('trans', _ip), ('wavelength', _dp), ('muz', _dp),
+                ('wmu', _dp), ('lineconst', _dp), ('wlambda', _dp), ('alpha', _dp), ('twohc_l3', _dp),
+                ('wlacont', _dp)]
+
+
+class Layout(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in (
+        'hostpack', 'colconst', 'pops', 'J', 'I', 'Gamma', 'scratch', 'hp_height', 'hp_bbc', 'hp_bg_chi',
+        'hp_bg_eta', 'hp_bg_sca', 'hp_C', 'hp_nTotal', 'hp_phi', 'hp_wphi', 'hp_gijcont', 'hp_n')] + \
+        [(n, C.c_int32) for n in ('sumNlevel', 'sumNlevel2', 'ntile', 'lambda_per_warp')]
+
+
+class Buffers(C.Structure):
+    _fields_ = [('ncol', C.c_int32), ('colconst', C.c_void_p), ('pops', C.c_void_p), ('J', C.c_void_p),
+                ('I', C.c_void_p), ('Gamma', C.c_void_p), ('scratch', C.c_void_p), ('dJ', C.c_void_p),
+                ('dPops', C.c_void_p), ('status', C.c_void_p), ('iter', C.c_void_p), ('done', C.c_void_p)]
+
+
+EXPORTS = ['mali_last_error', 'mali_device_count', 'mali_model_create', 'mali_model_destroy', 'mali_model_layout',
+           'mali_planck_bc', 'mali_upload_columns', 'mali_formal_sol_gamma', 'mali_stat_equil', 'mali_iterate',
+           'mali_piecewise_linear_1d', 'mali_uv']
+
+_lib = None
+
+
+def load():
+    """Load the shared library (building it is the job of lightspinner_b200.build / __graft_entry__.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise ImportError('%s is missing: run `python -m lightspinner_b200.build` (nvcc, sm_100a). '
+                          'There is no CPU fallback for the MALI hot path.' % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    L.mali_last_error.restype = C.c_char_p
+    L.mali_device_count.restype = C.c_int
+    L.mali_model_create.argtypes = [C.POINTER(ModelDesc), C.c_int, C.POINTER(C.c_void_p)]
+    L.mali_model_destroy.argtypes = [C.c_void_p]
+    L.mali_model_destroy.restype = None
+    L.mali_model_layout.argtypes = [C.c_void_p, C.POINTER(Layout)]
+    L.mali_planck_bc.argtypes = [_dp, C.c_int32, C.c_double, C.c_double, _dp]
+    L.mali_upload_columns.argtypes = [C.c_void_p, C.POINTER(Buffers), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                      C.c_void_p]
+    for name in ('mali_formal_sol_gamma', 'mali_stat_equil'):
+        getattr(L, name).argtypes = [C.c_void_p, C.POINTER(Buffers), C.c_int32, C.c_int32, C.c_void_p]
+    L.mali_iterate.argtypes = [C.c_void_p, C.POINTER(Buffers), C.c_int32, C.c_int32, C.c_int32, C.c_double,
+                               C.c_double, C.c_void_p]
+    L.mali_piecewise_linear_1d.argtypes = [C.c_int32, C.c_int32] + [C.c_void_p] * 10
+    L.mali_uv.argtypes = [C.c_void_p, C.POINTER(Buffers)] + [C.c_int32] * 5 + [C.c_void_p] * 4
+    _lib = L
+    return L
+
+
+def check(code):
+    if code != 0:
+        raise MaliError(code, load().mali_last_error().decode('utf-8', 'replace'))

@@ -1,0 +1,616 @@
+// mali_api.cu -- host side of libmali_b200.so: model flattening (tiles / slots / layouts) and the C ABI
+// declared in include/mali_b200.h.  No torch types, no exceptions across the boundary.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/mali_b200.h"
+#include "mali_kernels.cuh"
+
+using namespace mali;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) return fail((int)e_, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+template <class T>
+cudaError_t to_device(const std::vector<T> &h, T **d)
+{
+    *d = nullptr;
+    const size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
+    cudaError_t e = cudaMalloc((void **)d, bytes);
+    if (e != cudaSuccess) return e;
+    if (!h.empty()) e = cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+    return e;
+}
+
+__global__ void col_zero_bits_kernel(unsigned long long *bits, const int32_t *done, const int32_t *iter, int iterMin,
+                                     int col0, int ncol)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncol) return;
+    const int col = col0 + c;
+    if (done != nullptr && done[col] != 0) return;
+    if (iter != nullptr && iter[col] < iterMin) return;
+    bits[col] = 0ull;
+}
+
+// Per-column loop control of mali_iterate (test.py:23-28): phase 0 = after the formal solution: ++iter;
+// phase 1 = after stat_equil: convergence test.
+__global__ void iterate_ctl_kernel(int phase, double *dJ, double *dPops, int32_t *iter, int32_t *done, double tolJ,
+                                   double tolPops, int col0, int ncol)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncol) return;
+    const int col = col0 + c;
+    if (done[col] != 0) return;
+    if (phase == 0) {
+        iter[col] += 1;
+    } else if (tolJ >= 0.0) {
+        const double a = dJ[col], b = dPops[col];
+        if (!(a > tolJ || b > tolPops)) done[col] = 1;  // `while dJ > 2e-3 or dPops > 1e-3` (NaN keeps iterating... never)
+        if (a != a || b != b) done[col] = 2;            // NaN: stop touching the column, flag it
+    }
+}
+
+}  // namespace
+
+struct mali_model {
+    int device = 0;
+    int N = 0, Nrays = 0, Nspect = 0, Natom = 0, Ntrans = 0, Lw = 0, ntile = 0, Dmax = 0, Tmax = 0;
+    int sumNlevel = 0, sumNlevel2 = 0, maxNlevel = 0, nPartRows = 0;
+    std::vector<int32_t> Nlevel, lvlOff, g2Off, trans, toff;
+    std::vector<SlotDesc> slots;
+    std::vector<TileDesc> tiles;
+    std::vector<SlotDesc> transSlot;  // one descriptor per transition (for the uv hook)
+    mali_layout lay{};
+    int64_t off_z = 0, off_bbc = 0, off_bgchi = 0, off_bgeta = 0, off_bgsca = 0, off_C = 0, off_nTotal = 0;
+    int64_t off_jpart = 0, off_part = 0;
+    std::vector<TransposeJob> tjobs;
+    std::vector<CopyJob> cjobs;
+    std::vector<WlaJob> wjobs;
+    int transposeTiles = 0;
+    // device copies
+    TileDesc *d_tiles = nullptr;
+    SlotDesc *d_slots = nullptr;
+    double *d_alpha = nullptr, *d_twohc = nullptr, *d_wlacont = nullptr, *d_wlambda = nullptr, *d_zmu = nullptr,
+           *d_hw = nullptr;
+    int32_t *d_Nlevel = nullptr, *d_lvlOff = nullptr, *d_g2Off = nullptr, *d_trans = nullptr, *d_trPartOff = nullptr,
+            *d_trPartRows = nullptr;
+    TransposeJob *d_tjobs = nullptr;
+    CopyJob *d_cjobs = nullptr;
+    WlaJob *d_wjobs = nullptr;
+};
+
+extern "C" {
+
+const char *mali_last_error(void) { return g_err.c_str(); }
+
+int mali_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int mali_planck_bc(const double *wavelength, int32_t Nspect, double Tm2, double Tm1, double *out)
+{
+    if (!wavelength || !out || Nspect < 0) return fail(MALI_EINVAL, "mali_planck_bc: bad argument");
+    // utils.py:17-22 as numba compiles it: cube by repeated multiplication, libm exp
+    for (int la = 0; la < Nspect; ++la) {
+        const double wav = wavelength[la];
+        const double y = kNmToM * wav;
+        const double twohnu3_c2 = (2.0 * kHC) / (y * y * y);
+        const double T[2] = {Tm2, Tm1};
+        for (int q = 0; q < 2; ++q) {
+            const double hc_Tkla = kHC / (kKBoltzmann * kNmToM * wav) / T[q];
+            out[2 * la + q] = twohnu3_c2 / (std::exp(hc_Tkla) - 1.0);
+        }
+    }
+    return MALI_OK;
+}
+
+int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
+{
+    if (!d || !out) return fail(MALI_EINVAL, "mali_model_create: null argument");
+    *out = nullptr;
+    if (d->Nspace < 3) return fail(MALI_ELIMIT, "Nspace=%d: the short-characteristic sweep needs >= 3 depth points", d->Nspace);
+    if (d->Nrays < 1 || d->Nrays > 32) return fail(MALI_ELIMIT, "Nrays=%d not in [1, 32]", d->Nrays);
+    if (d->Nspect < 1 || d->Natom < 1 || d->Ntrans < 0) return fail(MALI_EINVAL, "bad model sizes");
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(MALI_EINVAL, "device %d out of range (%d devices)", device, ndev);
+    CU(cudaSetDevice(device));
+
+    auto *m = new mali_model();
+    m->device = device;
+    m->N = d->Nspace;
+    m->Nrays = d->Nrays;
+    m->Nspect = d->Nspect;
+    m->Natom = d->Natom;
+    m->Ntrans = d->Ntrans;
+    m->Lw = 32 / d->Nrays;
+    m->ntile = (d->Nspect + m->Lw - 1) / m->Lw;
+    const int N = m->N;
+
+    m->Nlevel.assign(d->Nlevel, d->Nlevel + d->Natom);
+    m->lvlOff.assign(d->Natom + 1, 0);
+    m->g2Off.assign(d->Natom + 1, 0);
+    for (int a = 0; a < d->Natom; ++a) {
+        if (m->Nlevel[a] < 1 || m->Nlevel[a] > 16) {
+            delete m;
+            return fail(MALI_ELIMIT, "atom %d: Nlevel=%d not in [1, 16]", a, d->Nlevel[a]);
+        }
+        m->lvlOff[a + 1] = m->lvlOff[a] + m->Nlevel[a];
+        m->g2Off[a + 1] = m->g2Off[a] + m->Nlevel[a] * m->Nlevel[a];
+        m->maxNlevel = std::max(m->maxNlevel, m->Nlevel[a]);
+    }
+    m->sumNlevel = m->lvlOff[d->Natom];
+    m->sumNlevel2 = m->g2Off[d->Natom];
+    m->trans.assign(d->trans, d->trans + (size_t)d->Ntrans * MALI_TRANS_STRIDE);
+    m->toff.assign(d->Ntrans + 1, 0);
+    for (int t = 0; t < d->Ntrans; ++t) {
+        const int32_t *tr = &m->trans[(size_t)t * 6];
+        const bool bad = tr[0] < 0 || tr[0] >= d->Natom || tr[1] < 0 || tr[2] < 0 || tr[1] >= m->Nlevel[tr[0]] ||
+                         tr[2] >= m->Nlevel[tr[0]] || tr[1] == tr[2] || tr[4] < 0 || tr[5] < 2 ||
+                         tr[4] + tr[5] > d->Nspect;
+        if (bad) {
+            delete m;
+            return fail(MALI_EINVAL, "transition %d: inconsistent descriptor", t);
+        }
+        m->toff[t + 1] = m->toff[t] + tr[5];
+    }
+    const int ntab = m->toff[d->Ntrans];
+
+    // ---- layouts.  colconst: every table depth-major with the wavelength (and angle) index contiguous.
+    int64_t o = 0;
+    auto take = [&](int64_t n) { int64_t r = o; o = align_up(o + n, 16); return r; };
+    m->off_z = take(N);
+    m->off_bbc = take(2 * (int64_t)d->Nspect);
+    m->off_bgchi = take((int64_t)N * d->Nspect);
+    m->off_bgeta = take((int64_t)N * d->Nspect);
+    m->off_bgsca = take((int64_t)N * d->Nspect);
+    m->off_C = take((int64_t)m->sumNlevel2 * N);
+    m->off_nTotal = take((int64_t)d->Natom * N);
+    std::vector<int64_t> tabOff(d->Ntrans), wlaOff(d->Ntrans, 0);
+    for (int t = 0; t < d->Ntrans; ++t) {
+        const int32_t *tr = &m->trans[(size_t)t * 6];
+        if (tr[3]) {
+            tabOff[t] = take(2 * (int64_t)N * tr[5] * d->Nrays);
+            wlaOff[t] = take((int64_t)N * tr[5]);
+        } else {
+            tabOff[t] = take((int64_t)N * tr[5]);
+        }
+    }
+    mali_layout &L = m->lay;
+    L.colconst = o;
+    L.pops = (int64_t)m->sumNlevel * N;
+    L.J = (int64_t)N * d->Nspect;
+    L.I = (int64_t)d->Nspect * d->Nrays;
+    L.Gamma = (int64_t)m->sumNlevel2 * N;
+    L.sumNlevel = m->sumNlevel;
+    L.sumNlevel2 = m->sumNlevel2;
+    L.ntile = m->ntile;
+    L.lambda_per_warp = m->Lw;
+
+    // host pack: reference layouts, plain concatenation
+    int64_t h = 0;
+    auto htake = [&](int64_t n) { int64_t r = h; h += n; return r; };
+    L.hp_height = htake(N);
+    L.hp_bbc = htake(2 * (int64_t)d->Nspect);
+    L.hp_bg_chi = htake((int64_t)d->Nspect * N);
+    L.hp_bg_eta = htake((int64_t)d->Nspect * N);
+    L.hp_bg_sca = htake((int64_t)d->Nspect * N);
+    L.hp_C = htake((int64_t)m->sumNlevel2 * N);
+    L.hp_nTotal = htake((int64_t)d->Natom * N);
+    L.hp_phi = h;
+    std::vector<int64_t> hpPhi(d->Ntrans, 0), hpGij(d->Ntrans, 0);
+    for (int t = 0; t < d->Ntrans; ++t)
+        if (m->trans[(size_t)t * 6 + 3]) hpPhi[t] = htake((int64_t)m->trans[(size_t)t * 6 + 5] * d->Nrays * 2 * N);
+    L.hp_wphi = htake((int64_t)d->Ntrans * N);
+    L.hp_gijcont = h;
+    for (int t = 0; t < d->Ntrans; ++t)
+        if (!m->trans[(size_t)t * 6 + 3]) hpGij[t] = htake((int64_t)m->trans[(size_t)t * 6 + 5] * N);
+    L.hp_n = htake((int64_t)m->sumNlevel * N);
+    L.hostpack = h;
+
+    // ---- per-transition descriptors, tiles and slots
+    m->transSlot.resize(d->Ntrans);
+    for (int t = 0; t < d->Ntrans; ++t) {
+        const int32_t *tr = &m->trans[(size_t)t * 6];
+        SlotDesc s{};
+        s.t = t;
+        s.isLine = tr[3];
+        s.Nblue = tr[4];
+        s.Nlam = tr[5];
+        s.atom = tr[0];
+        s.rowI = m->lvlOff[tr[0]] + tr[1];
+        s.rowJ = m->lvlOff[tr[0]] + tr[2];
+        s.toff = m->toff[t];
+        s.tabOff = tabOff[t];
+        s.wlaOff = wlaOff[t];
+        s.c0 = d->lineconst[3 * t + 0];
+        s.c1 = d->lineconst[3 * t + 1];
+        s.c2 = d->lineconst[3 * t + 2];
+        m->transSlot[t] = s;
+    }
+    std::vector<std::vector<int32_t>> trRows(d->Ntrans);
+    int partRow = 0;
+    for (int ti = 0; ti < m->ntile; ++ti) {
+        const int la0 = ti * m->Lw, la1 = std::min(d->Nspect, la0 + m->Lw);
+        TileDesc td{};
+        td.la0 = la0;
+        td.slot0 = (int)m->slots.size();
+        td.partRow0 = partRow;
+        std::map<std::pair<int, int>, int> lev;
+        for (int t = 0; t < d->Ntrans; ++t) {
+            const int32_t *tr = &m->trans[(size_t)t * 6];
+            if (!(tr[4] < la1 && tr[4] + tr[5] > la0)) continue;
+            SlotDesc s = m->transSlot[t];
+            auto slot_of = [&](int level) {
+                auto key = std::make_pair((int)tr[0], level);
+                auto it = lev.find(key);
+                if (it != lev.end()) return it->second;
+                const int id = (int)lev.size();
+                lev[key] = id;
+                return id;
+            };
+            s.lsI = slot_of(tr[1]);
+            s.lsJ = slot_of(tr[2]);
+            trRows[t].push_back(partRow);
+            partRow += 2;
+            m->slots.push_back(s);
+            td.nslot++;
+        }
+        td.nlevslot = (int)lev.size();
+        m->Dmax = std::max(m->Dmax, td.nlevslot);
+        m->Tmax = std::max(m->Tmax, td.nslot);
+        m->tiles.push_back(td);
+    }
+    m->nPartRows = partRow;
+    std::vector<int32_t> trPartOff(d->Ntrans + 1, 0), trPartRows;
+    for (int t = 0; t < d->Ntrans; ++t) {
+        trPartOff[t + 1] = trPartOff[t] + (int)trRows[t].size();
+        trPartRows.insert(trPartRows.end(), trRows[t].begin(), trRows[t].end());
+    }
+    int64_t so = 0;
+    m->off_jpart = so;
+    so = align_up(so + L.J, 16);
+    m->off_part = so;
+    so = align_up(so + (int64_t)std::max(partRow, 1) * N, 16);
+    L.scratch = so;
+
+    // ---- upload jobs
+    auto add_transpose = [&](int64_t src, int64_t dst, int R, int C) {
+        TransposeJob j{};
+        j.srcOff = src;
+        j.dstOff = dst;
+        j.R = R;
+        j.C = C;
+        j.tile0 = m->transposeTiles;
+        j.tilesC = (C + 31) / 32;
+        m->transposeTiles += ((R + 31) / 32) * j.tilesC;
+        m->tjobs.push_back(j);
+    };
+    add_transpose(L.hp_bg_chi, m->off_bgchi, d->Nspect, N);
+    add_transpose(L.hp_bg_eta, m->off_bgeta, d->Nspect, N);
+    add_transpose(L.hp_bg_sca, m->off_bgsca, d->Nspect, N);
+    for (int t = 0; t < d->Ntrans; ++t) {
+        const int32_t *tr = &m->trans[(size_t)t * 6];
+        if (tr[3]) {
+            add_transpose(hpPhi[t], tabOff[t], tr[5] * d->Nrays, 2 * N);
+            WlaJob w{};
+            w.wphiOff = L.hp_wphi + (int64_t)t * N;
+            w.dstOff = wlaOff[t];
+            w.toff = m->toff[t];
+            w.Nlam = tr[5];
+            m->wjobs.push_back(w);
+        } else {
+            add_transpose(hpGij[t], tabOff[t], tr[5], N);
+        }
+    }
+    auto add_copy = [&](int64_t src, int64_t dst, int64_t len, int toPops) {
+        CopyJob c{};
+        c.srcOff = src;
+        c.dstOff = dst;
+        c.len = len;
+        c.toPops = toPops;
+        m->cjobs.push_back(c);
+    };
+    add_copy(L.hp_height, m->off_z, N, 0);
+    add_copy(L.hp_bbc, m->off_bbc, 2 * (int64_t)d->Nspect, 0);
+    add_copy(L.hp_C, m->off_C, (int64_t)m->sumNlevel2 * N, 0);
+    add_copy(L.hp_nTotal, m->off_nTotal, (int64_t)d->Natom * N, 0);
+    add_copy(L.hp_n, 0, (int64_t)m->sumNlevel * N, 1);
+
+    // ---- device copies of the model tables
+    std::vector<double> zmu(d->Nrays), hw(d->Nrays);
+    for (int q = 0; q < d->Nrays; ++q) {
+        zmu[q] = 1.0 / d->muz[q];  // formal_solver.py:92
+        hw[q] = 0.5 * d->wmu[q];   // rh_method.py:640,661
+    }
+    std::vector<double> alpha(d->alpha, d->alpha + ntab), twohc(d->twohc_l3, d->twohc_l3 + ntab),
+        wlacont(d->wlacont, d->wlacont + ntab), wlambda(d->wlambda, d->wlambda + ntab);
+    cudaError_t e = cudaSuccess;
+    auto up = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+    up(to_device(m->tiles, &m->d_tiles));
+    up(to_device(m->slots, &m->d_slots));
+    up(to_device(alpha, &m->d_alpha));
+    up(to_device(twohc, &m->d_twohc));
+    up(to_device(wlacont, &m->d_wlacont));
+    up(to_device(wlambda, &m->d_wlambda));
+    up(to_device(zmu, &m->d_zmu));
+    up(to_device(hw, &m->d_hw));
+    up(to_device(m->Nlevel, &m->d_Nlevel));
+    up(to_device(m->lvlOff, &m->d_lvlOff));
+    up(to_device(m->g2Off, &m->d_g2Off));
+    up(to_device(m->trans, &m->d_trans));
+    up(to_device(trPartOff, &m->d_trPartOff));
+    up(to_device(trPartRows, &m->d_trPartRows));
+    up(to_device(m->tjobs, &m->d_tjobs));
+    up(to_device(m->cjobs, &m->d_cjobs));
+    up(to_device(m->wjobs, &m->d_wjobs));
+    if (e != cudaSuccess) {
+        mali_model_destroy(m);
+        return fail((int)e, "mali_model_create: %s", cudaGetErrorString(e));
+    }
+    *out = m;
+    return MALI_OK;
+}
+
+void mali_model_destroy(mali_model *m)
+{
+    if (!m) return;
+    cudaSetDevice(m->device);
+    void *ptrs[] = {m->d_tiles, m->d_slots, m->d_alpha, m->d_twohc, m->d_wlacont, m->d_wlambda, m->d_zmu, m->d_hw,
+                    m->d_Nlevel, m->d_lvlOff, m->d_g2Off, m->d_trans, m->d_trPartOff, m->d_trPartRows, m->d_tjobs,
+                    m->d_cjobs, m->d_wjobs};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    delete m;
+}
+
+int mali_model_layout(const mali_model *m, mali_layout *out)
+{
+    if (!m || !out) return fail(MALI_EINVAL, "mali_model_layout: null argument");
+    *out = m->lay;
+    return MALI_OK;
+}
+
+static int check_range(const mali_model *m, const mali_buffers *b, int col0, int ncol, const char *who)
+{
+    if (!m || !b) return fail(MALI_EINVAL, "%s: null argument", who);
+    if (col0 < 0 || ncol < 1 || col0 + ncol > b->ncol) return fail(MALI_EINVAL, "%s: columns [%d, %d) outside the batch of %d", who, col0, col0 + ncol, b->ncol);
+    return MALI_OK;
+}
+
+int mali_upload_columns(const mali_model *m, const mali_buffers *b, int32_t col0, int32_t ncol, const double *host_pack,
+                        double *staging_dev, void *stream)
+{
+    if (int r = check_range(m, b, col0, ncol, "mali_upload_columns")) return r;
+    if (!staging_dev || !b->colconst || !b->pops || !b->J) return fail(MALI_EINVAL, "mali_upload_columns: null buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const mali_layout &L = m->lay;
+    if (host_pack)
+        CU(cudaMemcpyAsync(staging_dev, host_pack, (size_t)ncol * L.hostpack * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (m->transposeTiles > 0) {
+        dim3 grid(m->transposeTiles, ncol), block(32, 8);
+        pack_transpose_kernel<<<grid, block, 0, st>>>(m->d_tjobs, (int)m->tjobs.size(), staging_dev, L.hostpack,
+                                                      b->colconst, L.colconst, col0);
+    }
+    {
+        dim3 grid(32, ncol);
+        pack_misc_kernel<<<grid, 256, 0, st>>>(m->d_cjobs, (int)m->cjobs.size(), m->d_wjobs, (int)m->wjobs.size(),
+                                               m->d_wlambda, m->N, staging_dev, L.hostpack, b->colconst, L.colconst,
+                                               b->pops, L.pops, b->J, L.J, col0);
+    }
+    CU(cudaGetLastError());
+    return MALI_OK;
+}
+
+static FsParams make_fs_params(const mali_model *m, const mali_buffers *b, int col0, int ncol, int wpb)
+{
+    FsParams p{};
+    p.N = m->N;
+    p.Nrays = m->Nrays;
+    p.Nspect = m->Nspect;
+    p.Natom = m->Natom;
+    p.Ntrans = m->Ntrans;
+    p.Lw = m->Lw;
+    p.ntile = m->ntile;
+    p.Dmax = std::max(m->Dmax, 1);
+    p.col0 = col0;
+    p.ncol = ncol;
+    p.warpsPerBlock = wpb;
+    p.blocksPerCol = (m->ntile + wpb - 1) / wpb;
+    p.smemPerWarp = (2 * p.Dmax + m->Natom) * 32;
+    p.colStride = m->lay.colconst;
+    p.popStride = m->lay.pops;
+    p.JStride = m->lay.J;
+    p.IStride = m->lay.I;
+    p.scratchStride = m->lay.scratch;
+    p.off_z = m->off_z;
+    p.off_bbc = m->off_bbc;
+    p.off_bgchi = m->off_bgchi;
+    p.off_bgeta = m->off_bgeta;
+    p.off_bgsca = m->off_bgsca;
+    p.off_jpart = m->off_jpart;
+    p.off_part = m->off_part;
+    p.tiles = m->d_tiles;
+    p.slots = m->d_slots;
+    p.alpha = m->d_alpha;
+    p.twohc = m->d_twohc;
+    p.wlacont = m->d_wlacont;
+    p.zmu = m->d_zmu;
+    p.hw = m->d_hw;
+    p.colconst = b->colconst;
+    p.pops = b->pops;
+    p.J = b->J;
+    p.I = b->I;
+    p.scratch = b->scratch;
+    p.dJbits = reinterpret_cast<unsigned long long *>(b->dJ);
+    p.done = b->done;
+    return p;
+}
+
+static FinishParams make_finish_params(const mali_model *m, const mali_buffers *b, int col0, int ncol)
+{
+    FinishParams p{};
+    p.N = m->N;
+    p.Natom = m->Natom;
+    p.Ntrans = m->Ntrans;
+    p.col0 = col0;
+    p.ncol = ncol;
+    p.sumNlevel = m->sumNlevel;
+    p.sumNlevel2 = m->sumNlevel2;
+    p.colStride = m->lay.colconst;
+    p.popStride = m->lay.pops;
+    p.gammaStride = m->lay.Gamma;
+    p.scratchStride = m->lay.scratch;
+    p.off_C = m->off_C;
+    p.off_nTotal = m->off_nTotal;
+    p.off_part = m->off_part;
+    p.Nlevel = m->d_Nlevel;
+    p.lvlOff = m->d_lvlOff;
+    p.g2Off = m->d_g2Off;
+    p.trans = m->d_trans;
+    p.trPartOff = m->d_trPartOff;
+    p.trPartRows = m->d_trPartRows;
+    p.colconst = b->colconst;
+    p.pops = b->pops;
+    p.Gamma = b->Gamma;
+    p.scratch = b->scratch;
+    p.dPopsBits = reinterpret_cast<unsigned long long *>(b->dPops);
+    p.status = b->status;
+    p.done = b->done;
+    return p;
+}
+
+static int launch_fs(const mali_model *m, const mali_buffers *b, int col0, int ncol, cudaStream_t st)
+{
+    // Few (column, tile) pairs: one warp per block so that the tiles spread over all 148 SMs; otherwise 4.
+    const int wpb = ((int64_t)ncol * m->ntile >= 148 * 16) ? 4 : 1;
+    FsParams p = make_fs_params(m, b, col0, ncol, wpb);
+    const size_t smem = (size_t)p.smemPerWarp * wpb * sizeof(double);
+    if (smem > 48 * 1024) {
+        if (smem > 227 * 1024) return fail(MALI_ELIMIT, "tile needs %zu B of shared memory", smem);
+        CU(cudaFuncSetAttribute(fs_gamma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    col_zero_bits_kernel<<<(ncol + 127) / 128, 128, 0, st>>>(p.dJbits, b->done, nullptr, 0, col0, ncol);
+    fs_gamma_kernel<<<(unsigned)(p.blocksPerCol * ncol), 32 * wpb, smem, st>>>(p);
+    FinishParams f = make_finish_params(m, b, col0, ncol);
+    dim3 grid((m->N + 63) / 64, m->Natom, ncol);
+    gamma_finish_kernel<<<grid, 64, 0, st>>>(f);
+    CU(cudaGetLastError());
+    return MALI_OK;
+}
+
+static int launch_se(const mali_model *m, const mali_buffers *b, int col0, int ncol, const int32_t *iter, int iterMin,
+                     cudaStream_t st)
+{
+    FinishParams f = make_finish_params(m, b, col0, ncol);
+    // inside mali_iterate, columns whose own iteration counter is still <= 3 only iterate J (test.py:27)
+    f.iter = iter;
+    f.iterMin = iterMin;
+    col_zero_bits_kernel<<<(ncol + 127) / 128, 128, 0, st>>>(f.dPopsBits, b->done, iter, iterMin, col0, ncol);
+    dim3 grid((m->N + 63) / 64, m->Natom, ncol);
+    if (m->maxNlevel <= 8)
+        stat_equil_kernel<8><<<grid, 64, 0, st>>>(f);
+    else
+        stat_equil_kernel<16><<<grid, 64, 0, st>>>(f);
+    CU(cudaGetLastError());
+    return MALI_OK;
+}
+
+int mali_formal_sol_gamma(const mali_model *m, const mali_buffers *b, int32_t col0, int32_t ncol, void *stream)
+{
+    if (int r = check_range(m, b, col0, ncol, "mali_formal_sol_gamma")) return r;
+    if (!b->colconst || !b->pops || !b->J || !b->I || !b->Gamma || !b->scratch || !b->dJ)
+        return fail(MALI_EINVAL, "mali_formal_sol_gamma: null buffer");
+    return launch_fs(m, b, col0, ncol, (cudaStream_t)stream);
+}
+
+int mali_stat_equil(const mali_model *m, const mali_buffers *b, int32_t col0, int32_t ncol, void *stream)
+{
+    if (int r = check_range(m, b, col0, ncol, "mali_stat_equil")) return r;
+    if (!b->colconst || !b->pops || !b->Gamma || !b->dPops || !b->status)
+        return fail(MALI_EINVAL, "mali_stat_equil: null buffer");
+    return launch_se(m, b, col0, ncol, nullptr, 0, (cudaStream_t)stream);
+}
+
+int mali_iterate(const mali_model *m, const mali_buffers *b, int32_t col0, int32_t ncol, int32_t max_iter, double tolJ,
+                 double tolPops, void *stream)
+{
+    if (int r = check_range(m, b, col0, ncol, "mali_iterate")) return r;
+    if (!b->colconst || !b->pops || !b->J || !b->I || !b->Gamma || !b->scratch || !b->dJ || !b->dPops || !b->status ||
+        !b->iter || !b->done)
+        return fail(MALI_EINVAL, "mali_iterate: null buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nb = (ncol + 127) / 128;
+    for (int it = 0; it < max_iter; ++it) {
+        if (int r = launch_fs(m, b, col0, ncol, st)) return r;
+        iterate_ctl_kernel<<<nb, 128, 0, st>>>(0, b->dJ, b->dPops, b->iter, b->done, tolJ, tolPops, col0, ncol);
+        if (int r = launch_se(m, b, col0, ncol, b->iter, 4, st)) return r;
+        iterate_ctl_kernel<<<nb, 128, 0, st>>>(1, b->dJ, b->dPops, b->iter, b->done, tolJ, tolPops, col0, ncol);
+    }
+    CU(cudaGetLastError());
+    return MALI_OK;
+}
+
+int mali_piecewise_linear_1d(int32_t Nspace, int32_t nray, const double *z, const double *muz, const int32_t *toFrom,
+                             const double *bbc0, const double *bbc1, const double *chi, const double *S, double *I,
+                             double *Psi, void *stream)
+{
+    if (Nspace < 3) return fail(MALI_ELIMIT, "Nspace=%d: need >= 3 depth points", Nspace);
+    if (nray < 1 || !z || !muz || !toFrom || !bbc0 || !bbc1 || !chi || !S || !I || !Psi)
+        return fail(MALI_EINVAL, "mali_piecewise_linear_1d: bad argument");
+    sweep_hook_kernel<<<(nray + 63) / 64, 64, 0, (cudaStream_t)stream>>>(Nspace, nray, z, muz, toFrom, bbc0, bbc1, chi, S,
+                                                                         I, Psi);
+    CU(cudaGetLastError());
+    return MALI_OK;
+}
+
+int mali_uv(const mali_model *m, const mali_buffers *b, int32_t col, int32_t t, int32_t la, int32_t mu, int32_t toFrom,
+            double *Uji, double *Vij, double *Vji, void *stream)
+{
+    if (int r = check_range(m, b, col, 1, "mali_uv")) return r;
+    if (t < 0 || t >= m->Ntrans || mu < 0 || mu >= m->Nrays || !Uji || !Vij || !Vji)
+        return fail(MALI_EINVAL, "mali_uv: bad argument");
+    const SlotDesc sd = m->transSlot[t];
+    if (la < sd.Nblue || la >= sd.Nblue + sd.Nlam) return fail(MALI_EINVAL, "mali_uv: transition %d is not active at wavelength %d", t, la);
+    FsParams p = make_fs_params(m, b, col, 1, 1);
+    uv_hook_kernel<<<(m->N + 63) / 64, 64, 0, (cudaStream_t)stream>>>(p, col, sd, la, mu, toFrom ? 1 : 0, Uji, Vij, Vji);
+    CU(cudaGetLastError());
+    return MALI_OK;
+}
+
+}  // extern "C"

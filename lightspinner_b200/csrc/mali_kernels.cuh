@@ -1,0 +1,623 @@
+// mali_kernels.cuh -- hand-written sm_100a kernels of the MALI hot path (fp64, CUDA cores, no tensor cores:
+// nothing on this path is a dense contraction; the largest "matrix" is Nlevel x Nlevel).
+//
+// Compile with --fmad=false: the reference arithmetic (numpy, numba without fastmath) never contracts
+// a*b+c, and every expression below is written in the reference's evaluation order so that
+// the only sources of difference are exp() in w2 (CUDA libdevice vs glibc) and the order of the J / Gamma sums.
+#pragma once
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+
+#include "mali_types.cuh"
+
+namespace mali {
+
+// --------------------------------------------------------------------------------------------------------
+// formal_solver.py:14-44
+__device__ __forceinline__ void w2(double dtau, double &w0, double &w1)
+{
+    if (dtau < 5e-4) {
+        w0 = dtau * (1.0 - 0.5 * dtau);
+        w1 = (dtau * dtau) * (0.5 - dtau / 3.0);
+    } else if (dtau > 50.0) {
+        w0 = 1.0;
+        w1 = 1.0;
+    } else {
+        const double expdt = exp(-dtau);
+        w0 = 1.0 - expdt;
+        w1 = w0 - dtau * expdt;
+    }
+}
+
+// One ray's short-characteristic recurrence, one depth point per step() (formal_solver.py:46-142,191-211).
+// The caller supplies chi, S at the current point in sweep order; step() returns I and PsiStar = LambdaStar/chi there.
+struct Sweep {
+    double Iupw, chiPrev, SPrev, zPrev, w0, w1;
+
+    // first point of the sweep (k = kStart).  chiNext = chi[kStart+dk] is only needed for the upgoing boundary.
+    __device__ __forceinline__ void first(bool up, double zmu, double chi, double S, double z, double chiNext,
+                                          double zNext, double bbc0, double bbc1, double &I, double &Psi)
+    {
+        if (up) {
+            // formal_solver.py:205-207
+            const double dtau_uw = zmu * (chi + chiNext) * 0.5 * fabs(z - zNext);
+            Iupw = bbc1 - (bbc0 - bbc1) / dtau_uw;
+        } else {
+            Iupw = 0.0;
+        }
+        chiPrev = chi;
+        SPrev = S;
+        zPrev = z;
+        w0 = 0.0;
+        w1 = 0.0;
+        I = Iupw;
+        Psi = 0.0 / chi;  // LambdaStar[kStart] = 0
+    }
+
+    // interior point (formal_solver.py:120-135) or, with last = true, the final point with the reference's
+    // stale-w / S[kEnd-dk] behaviour (formal_solver.py:137-139).
+    __device__ __forceinline__ void step(bool last, double zmu, double chi, double S, double z, double &I, double &Psi)
+    {
+        const double dtau = 0.5 * (chiPrev + chi) * zmu * fabs(zPrev - z);
+        const double dS = (SPrev - S) / dtau;
+        double Ik, Lam;
+        if (!last) {
+            w2(dtau, w0, w1);
+            Ik = Iupw * (1.0 - w0) + w0 * S + w1 * dS;
+        } else {
+            Ik = (1.0 - w0) * Iupw + w0 * SPrev + w1 * dS;
+        }
+        Lam = w0 - w1 / dtau;
+        Iupw = Ik;
+        chiPrev = chi;
+        SPrev = S;
+        zPrev = z;
+        I = Ik;
+        Psi = Lam / chi;
+    }
+};
+
+// --------------------------------------------------------------------------------------------------------
+// Deterministic warp reduce-scatter of 8 values per lane: after the call the lane holds, in the return value,
+// the sum over all 32 lanes of v[lane >> 2].  9 shuffle-adds instead of 40; fixed summation tree.
+__device__ __forceinline__ double reduce_scatter8(double (&v)[8], int lane)
+{
+    const unsigned full = 0xffffffffu;
+    {
+        const bool up = lane & 16;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double send = up ? v[j] : v[j + 4];
+            const double keep = up ? v[j + 4] : v[j];
+            v[j] = keep + __shfl_xor_sync(full, send, 16);
+        }
+    }
+    {
+        const bool up = lane & 8;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const double send = up ? v[j] : v[j + 2];
+            const double keep = up ? v[j + 2] : v[j];
+            v[j] = keep + __shfl_xor_sync(full, send, 8);
+        }
+    }
+    {
+        const bool up = lane & 4;
+        const double send = up ? v[0] : v[1];
+        const double keep = up ? v[1] : v[0];
+        v[0] = keep + __shfl_xor_sync(full, send, 4);
+    }
+    v[0] = v[0] + __shfl_xor_sync(full, v[0], 2);
+    v[0] = v[0] + __shfl_xor_sync(full, v[0], 1);
+    return v[0];
+}
+
+__device__ __forceinline__ unsigned long long absbits(double x)
+{
+    // |x| as an unsigned integer: ordering of non-negative doubles == ordering of their bit patterns, and any
+    // NaN compares above +inf, so an integer max is a NaN-propagating max like numpy's.
+    return (unsigned long long)__double_as_longlong(fabs(x));
+}
+
+// --------------------------------------------------------------------------------------------------------
+// Context.formal_sol_gamma_matrices, rh_method.py:595-692, for one (column, tile) per warp.
+//
+// lane -> (ls = lane / Nrays, mu = lane % Nrays): wavelength la = tile.la0 + ls, angle mu.  Each lane runs the
+// downward then the upward recurrence of its ray, one depth point per step; at every point it (1) builds the
+// total opacity / source function from the active transitions (uv, rh_method.py:245-288), (2) advances the short
+// characteristic, (3) adds its share of J (segmented sum over the Nrays lanes of a wavelength), (4) forms the
+// Gamma integrands and reduces them over the 32 lanes.  Per-warp partial sums go to a per-column scratch
+// (down sweep: store, up sweep: add) and are combined in fixed order by gamma_finish_kernel -> deterministic.
+__global__ void __launch_bounds__(128) fs_gamma_kernel(const FsParams p)
+{
+    extern __shared__ double smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = (blockIdx.x % p.blocksPerCol) * p.warpsPerBlock + warp;
+    const int col = p.col0 + blockIdx.x / p.blocksPerCol;
+    if (tile >= p.ntile) return;
+    if (p.done != nullptr && p.done[col] != 0) return;
+
+    const TileDesc td = p.tiles[tile];
+    const int N = p.N, Nrays = p.Nrays, Nspect = p.Nspect;
+    const int ls = lane / Nrays, mu = lane - ls * Nrays;
+    const int la = td.la0 + ls;
+    const bool valid = (ls < p.Lw) && (la < Nspect);
+    const int laC = valid ? la : td.la0;
+    const int muC = valid ? mu : 0;
+    const bool leader = valid && (mu == 0);
+
+    // per-lane level accumulators (the reference's atom.chi / atom.U / atom.eta scratch, rh_method.py:464-466)
+    double *lvl = smem + (size_t)warp * p.smemPerWarp;
+#define CHI_L(d) lvl[((d) * 2 + 0) * 32 + lane]
+#define U_L(d) lvl[((d) * 2 + 1) * 32 + lane]
+#define ETA_A(a) lvl[(2 * p.Dmax + (a)) * 32 + lane]
+
+    const double *cc = p.colconst + (size_t)col * p.colStride;
+    const double *zz = cc + p.off_z;
+    const double *bgchi = cc + p.off_bgchi, *bgeta = cc + p.off_bgeta, *bgsca = cc + p.off_bgsca;
+    const double *npop = p.pops + (size_t)col * p.popStride;
+    double *Jcol = p.J + (size_t)col * p.JStride;
+    double *scr = p.scratch + (size_t)col * p.scratchStride;
+    double *Jpart = scr + p.off_jpart;
+    double *part = scr + p.off_part;
+    const SlotDesc *slots = p.slots + td.slot0;
+    const int nslot = td.nslot;
+
+    const double zmu = p.zmu[muC], hw = p.hw[muC];
+    const double bbc0 = cc[p.off_bbc + 2 * laC], bbc1 = cc[p.off_bbc + 2 * laC + 1];
+    const double fourPi = 4.0 * kPi;  // (x*4)*pi == x*(4*pi) exactly: scaling by 4 commutes with rounding
+
+    unsigned long long dJb = 0ull;
+
+    for (int d = 0; d < 2; ++d) {
+        const int dk = d ? -1 : 1;
+        const int kS = d ? N - 1 : 0;
+        Sweep sw;
+        double chiProbe = 0.0;
+        // s = -1 (upgoing only): evaluate chi at kS+dk first, needed by the thermalised lower boundary
+        for (int s = (d ? -1 : 0); s < N; ++s) {
+            const bool probe = s < 0;
+            const int k = probe ? (kS + dk) : (kS + s * dk);
+
+            // ---- (1) opacity and emissivity at depth k: rh_method.py:601-632
+            double chiTot = 0.0, etaTot = 0.0;
+            if (!probe) {
+                for (int q = 0; q < td.nlevslot; ++q) {
+                    CHI_L(q) = 0.0;
+                    U_L(q) = 0.0;
+                }
+                for (int a = 0; a < p.Natom; ++a) ETA_A(a) = 0.0;
+            }
+            for (int tt = 0; tt < nslot; ++tt) {
+                const SlotDesc &sd = slots[tt];
+                const int lt = laC - sd.Nblue;
+                const bool act = valid && lt >= 0 && lt < sd.Nlam;
+                const int ltC = act ? lt : 0;
+                double Vij, Vji, Uji;
+                if (sd.isLine) {
+                    const double phi =
+                        act ? __ldg(cc + sd.tabOff + ((size_t)(d * N + k) * sd.Nlam + ltC) * Nrays + muC) : 0.0;
+                    Vij = sd.c0 * phi;
+                    Vji = sd.c2 * Vij;
+                    Uji = sd.c1 * Vji;
+                } else {
+                    const double a = act ? __ldg(p.alpha + sd.toff + ltC) : 0.0;
+                    const double g = act ? __ldg(cc + sd.tabOff + (size_t)k * sd.Nlam + ltC) : 0.0;
+                    Vij = a;
+                    Vji = g * Vij;
+                    Uji = __ldg(p.twohc + sd.toff + ltC) * Vji;
+                }
+                const double ni = npop[(size_t)sd.rowI * N + k], nj = npop[(size_t)sd.rowJ * N + k];
+                const double chi_t = ni * Vij - nj * Vji;
+                const double eta_t = nj * Uji;
+                if (!probe) {
+                    CHI_L(sd.lsI) += chi_t;
+                    CHI_L(sd.lsJ) -= chi_t;
+                    U_L(sd.lsJ) += Uji;
+                    ETA_A(sd.atom) += eta_t;
+                }
+                chiTot += chi_t;
+                etaTot += eta_t;
+            }
+            const size_t kl = (size_t)k * Nspect + laC;
+            chiTot += __ldg(bgchi + kl);
+            if (probe) {
+                chiProbe = chiTot;
+                continue;
+            }
+            const double Jdag = Jcol[kl];
+            const double S = (etaTot + __ldg(bgeta + kl) + __ldg(bgsca + kl) * Jdag) / chiTot;
+
+            // ---- (2) short characteristic: formal_solver.py
+            const double zk = zz[k];
+            double Ik, Psi;
+            if (s == 0)
+                sw.first(d != 0, zmu, chiTot, S, zk, chiProbe, zz[kS + dk], bbc0, bbc1, Ik, Psi);
+            else
+                sw.step(s == N - 1, zmu, chiTot, S, zk, Ik, Psi);
+
+            // ---- (3) J: rh_method.py:640.  Sum over the Nrays lanes of this wavelength in mu order.
+            {
+                const double x = valid ? hw * Ik : 0.0;
+                double sum = x;
+                for (int m = 1; m < Nrays; ++m) sum += __shfl_down_sync(0xffffffffu, x, m);
+                if (leader) {
+                    if (d == 0) {
+                        __stcg(Jpart + kl, sum);
+                    } else {
+                        const double Jn = __ldcg(Jpart + kl) + sum;
+                        Jcol[kl] = Jn;
+                        const unsigned long long b = absbits(1.0 - Jdag / Jn);
+                        dJb = b > dJb ? b : dJb;
+                    }
+                }
+            }
+
+            // ---- (4) Gamma integrands: rh_method.py:643-681
+            for (int c0 = 0; c0 < nslot; c0 += 4) {
+                double v[8];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int tt = c0 + q;
+                    v[2 * q] = 0.0;
+                    v[2 * q + 1] = 0.0;
+                    if (tt < nslot) {
+                        const SlotDesc &sd = slots[tt];
+                        const int lt = laC - sd.Nblue;
+                        const bool act = valid && lt >= 0 && lt < sd.Nlam;
+                        const int ltC = act ? lt : 0;
+                        double Vij, Vji, Uji, wla;
+                        if (sd.isLine) {
+                            const double phi =
+                                act ? __ldg(cc + sd.tabOff + ((size_t)(d * N + k) * sd.Nlam + ltC) * Nrays + muC) : 0.0;
+                            Vij = sd.c0 * phi;
+                            Vji = sd.c2 * Vij;
+                            Uji = sd.c1 * Vji;
+                            wla = act ? __ldg(cc + sd.wlaOff + (size_t)k * sd.Nlam + ltC) : 0.0;
+                        } else {
+                            const double a = act ? __ldg(p.alpha + sd.toff + ltC) : 0.0;
+                            const double g = act ? __ldg(cc + sd.tabOff + (size_t)k * sd.Nlam + ltC) : 0.0;
+                            Vij = a;
+                            Vji = g * Vij;
+                            Uji = __ldg(p.twohc + sd.toff + ltC) * Vji;
+                            wla = act ? __ldg(p.wlacont + sd.toff + ltC) : 0.0;
+                        }
+                        const double Ieff = Ik - Psi * ETA_A(sd.atom);
+                        const double wlamu = (wla * hw) * fourPi;
+                        const double g1 = (Uji + Vji * Ieff) - ((CHI_L(sd.lsI) * Psi) * U_L(sd.lsJ));
+                        const double g2 = (Vij * Ieff) - ((CHI_L(sd.lsJ) * Psi) * U_L(sd.lsI));
+                        v[2 * q] = act ? g1 * wlamu : 0.0;
+                        v[2 * q + 1] = act ? g2 * wlamu : 0.0;
+                    }
+                }
+                const double tot = reduce_scatter8(v, lane);
+                const int e = lane >> 2;  // value index owned by this lane group
+                const int tt = c0 + (e >> 1);
+                if ((lane & 3) == 0 && tt < nslot) {
+                    double *dst = part + (size_t)(td.partRow0 + 2 * tt + (e & 1)) * N + k;
+                    if (d == 0)
+                        __stcg(dst, tot);
+                    else
+                        __stcg(dst, __ldcg(dst) + tot);
+                }
+            }
+        }
+        // emergent intensity: rh_method.py:638 (the upgoing value survives)
+        if (d == 1 && valid) p.I[(size_t)col * p.IStride + (size_t)la * Nrays + mu] = sw.Iupw;
+    }
+
+    // dJ = max |1 - JDag/J| (rh_method.py:705-706)
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(0xffffffffu, dJb, off);
+        dJb = o > dJb ? o : dJb;
+    }
+    if (lane == 0) atomicMax(p.dJbits + col, dJb);
+#undef CHI_L
+#undef U_L
+#undef ETA_A
+}
+
+// --------------------------------------------------------------------------------------------------------
+// Gamma = C + sum of the per-tile partials in ascending tile order, then the diagonal (rh_method.py:587-590,
+// 698-703).  One thread per (column, atom, depth); coalesced over depth.
+__global__ void gamma_finish_kernel(const FinishParams p)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int a = blockIdx.y;
+    const int col = p.col0 + blockIdx.z;
+    if (k >= p.N) return;
+    if (p.done != nullptr && p.done[col] != 0) return;
+    const int N = p.N;
+    const int NL = p.Nlevel[a];
+    const double *C = p.colconst + (size_t)col * p.colStride + p.off_C + (size_t)p.g2Off[a] * N;
+    double *G = p.Gamma + (size_t)col * p.gammaStride + (size_t)p.g2Off[a] * N;
+    const double *part = p.scratch + (size_t)col * p.scratchStride + p.off_part;
+
+    for (int e = 0; e < NL * NL; ++e) G[(size_t)e * N + k] = 0.0 + C[(size_t)e * N + k];
+    for (int t = 0; t < p.Ntrans; ++t) {
+        const int32_t *tr = p.trans + 6 * t;
+        if (tr[0] != a) continue;
+        const int i = tr[1], j = tr[2];
+        double sij = 0.0, sji = 0.0;
+        for (int r = p.trPartOff[t]; r < p.trPartOff[t + 1]; ++r) {
+            const int row = p.trPartRows[r];
+            sij += part[(size_t)row * N + k];
+            sji += part[(size_t)(row + 1) * N + k];
+        }
+        G[((size_t)i * NL + j) * N + k] += sij;
+        G[((size_t)j * NL + i) * N + k] += sji;
+    }
+    for (int i = 0; i < NL; ++i) G[((size_t)i * NL + i) * N + k] = 0.0;
+    for (int i = 0; i < NL; ++i) {
+        double GamDiag = 0.0;
+        for (int l = 0; l < NL; ++l) GamDiag += G[((size_t)l * NL + i) * N + k];
+        G[((size_t)i * NL + i) * N + k] = -GamDiag;
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------
+// Context.stat_equil (rh_method.py:710-745): one thread per (column, atom, depth) solves the Nlevel x Nlevel
+// system Gamma' n = nTotal e_iEliminate by LU with partial pivoting, then two rounds of iterative refinement
+// with the residual accumulated in double-double (the systems have cond ~ 1e6..1e9, SURVEY.md 7.3-1: the aim is
+// to sit closer to the exact solution than LAPACK does, not to clone its rounding).
+__device__ __forceinline__ void two_sum(double a, double b, double &s, double &e)
+{
+    s = a + b;
+    const double bb = s - a;
+    e = (a - (s - bb)) + (b - bb);
+}
+
+template <int NLMAX>
+__global__ void stat_equil_kernel(const FinishParams p)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int a = blockIdx.y;
+    const int col = p.col0 + blockIdx.z;
+    if (k >= p.N) return;
+    if (p.done != nullptr && p.done[col] != 0) return;
+    if (p.iter != nullptr && p.iter[col] < p.iterMin) return;
+    const int N = p.N;
+    const int NL = p.Nlevel[a];
+    const double *G = p.Gamma + (size_t)col * p.gammaStride + (size_t)p.g2Off[a] * N;
+    double *n = p.pops + (size_t)col * p.popStride + (size_t)p.lvlOff[a] * N;
+    const double nTot = p.colconst[(size_t)col * p.colStride + p.off_nTotal + (size_t)a * N + k];
+
+    double A[NLMAX * NLMAX], LU[NLMAX * NLMAX], x[NLMAX], r[NLMAX];
+    int piv[NLMAX];
+
+    // iEliminate = argmax(n[:, k]) (first maximum)
+    int iEl = 0;
+    double nmax = n[k];
+    for (int l = 1; l < NL; ++l) {
+        const double v = n[(size_t)l * N + k];
+        if (v > nmax) {
+            nmax = v;
+            iEl = l;
+        }
+    }
+    for (int i = 0; i < NL; ++i)
+        for (int j = 0; j < NL; ++j) {
+            const double v = (i == iEl) ? 1.0 : G[((size_t)i * NL + j) * N + k];
+            A[i * NLMAX + j] = v;
+            LU[i * NLMAX + j] = v;
+        }
+
+    bool singular = false;
+    for (int j = 0; j < NL; ++j) {
+        int pr = j;
+        double best = fabs(LU[j * NLMAX + j]);
+        for (int i = j + 1; i < NL; ++i) {
+            const double v = fabs(LU[i * NLMAX + j]);
+            if (v > best) {
+                best = v;
+                pr = i;
+            }
+        }
+        piv[j] = pr;
+        if (!(best > 0.0) || !(best <= DBL_MAX)) {
+            singular = true;
+            break;
+        }
+        if (pr != j)
+            for (int q = 0; q < NL; ++q) {
+                const double tmp = LU[j * NLMAX + q];
+                LU[j * NLMAX + q] = LU[pr * NLMAX + q];
+                LU[pr * NLMAX + q] = tmp;
+            }
+        const double pv = LU[j * NLMAX + j];
+        for (int i = j + 1; i < NL; ++i) {
+            const double l = LU[i * NLMAX + j] / pv;
+            LU[i * NLMAX + j] = l;
+            for (int q = j + 1; q < NL; ++q) LU[i * NLMAX + q] -= l * LU[j * NLMAX + q];
+        }
+    }
+    if (singular) {
+        atomicOr(p.status + col, 1);
+        return;
+    }
+
+    auto lu_solve = [&](double *b) {
+        for (int j = 0; j < NL; ++j) {
+            const int pr = piv[j];
+            if (pr != j) {
+                const double tmp = b[j];
+                b[j] = b[pr];
+                b[pr] = tmp;
+            }
+            for (int i = j + 1; i < NL; ++i) b[i] -= LU[i * NLMAX + j] * b[j];
+        }
+        for (int i = NL - 1; i >= 0; --i) {
+            double acc = b[i];
+            for (int q = i + 1; q < NL; ++q) acc -= LU[i * NLMAX + q] * b[q];
+            b[i] = acc / LU[i * NLMAX + i];
+        }
+    };
+
+    for (int i = 0; i < NL; ++i) x[i] = 0.0;
+    x[iEl] = nTot;
+    lu_solve(x);
+    for (int it = 0; it < 2; ++it) {
+        // r = b - A x in double-double
+        for (int i = 0; i < NL; ++i) {
+            double hi = (i == iEl) ? nTot : 0.0, lo = 0.0;
+            for (int j = 0; j < NL; ++j) {
+                const double aij = A[i * NLMAX + j];
+                const double ph = -(aij * x[j]);
+                const double pl = -__fma_rn(aij, x[j], ph);  // exact product error (ph = -(a*x) rounded)
+                double s, e;
+                two_sum(hi, ph, s, e);
+                hi = s;
+                lo += e + pl;
+            }
+            r[i] = hi + lo;
+        }
+        lu_solve(r);
+        for (int i = 0; i < NL; ++i) x[i] += r[i];
+    }
+
+    bool ok = true;
+    for (int i = 0; i < NL; ++i) ok = ok && (fabs(x[i]) <= DBL_MAX);
+    if (!ok) {
+        atomicOr(p.status + col, 1);
+        return;
+    }
+    unsigned long long db = 0ull;
+    for (int l = 0; l < NL; ++l) {
+        const double nOld = n[(size_t)l * N + k];
+        const unsigned long long b = absbits(1.0 - nOld / x[l]);
+        db = b > db ? b : db;
+        n[(size_t)l * N + k] = x[l];
+    }
+    atomicMax(p.dPopsBits + col, db);
+}
+
+// --------------------------------------------------------------------------------------------------------
+// Test hook: piecewise_linear_1d for independent rays, one thread per ray, same Sweep code as the fused kernel.
+__global__ void sweep_hook_kernel(int N, int nray, const double *z, const double *muz, const int32_t *toFrom,
+                                  const double *bbc0, const double *bbc1, const double *chi, const double *S,
+                                  double *I, double *Psi)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nray) return;
+    const bool up = toFrom[r] != 0;
+    const double zmu = 1.0 / muz[r];
+    const int dk = up ? -1 : 1, kS = up ? N - 1 : 0;
+    const double *c = chi + (size_t)r * N, *s = S + (size_t)r * N;
+    Sweep sw;
+    double Ik, Pk;
+    sw.first(up, zmu, c[kS], s[kS], z[kS], c[kS + dk], z[kS + dk], bbc0[r], bbc1[r], Ik, Pk);
+    I[(size_t)r * N + kS] = Ik;
+    Psi[(size_t)r * N + kS] = Pk;
+    for (int q = 1; q < N; ++q) {
+        const int k = kS + q * dk;
+        sw.step(q == N - 1, zmu, c[k], s[k], z[k], Ik, Pk);
+        I[(size_t)r * N + k] = Ik;
+        Psi[(size_t)r * N + k] = Pk;
+    }
+}
+
+// Test hook: ComputationalTransition.uv from the packed device tables of one column.
+__global__ void uv_hook_kernel(const FsParams p, int col, SlotDesc sd, int la, int mu, int d, double *Uji,
+                               double *Vij, double *Vji)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= p.N) return;
+    const double *cc = p.colconst + (size_t)col * p.colStride;
+    const int lt = la - sd.Nblue;
+    double vij, vji, uji;
+    if (sd.isLine) {
+        const double phi = cc[sd.tabOff + ((size_t)(d * p.N + k) * sd.Nlam + lt) * p.Nrays + mu];
+        vij = sd.c0 * phi;
+        vji = sd.c2 * vij;
+        uji = sd.c1 * vji;
+    } else {
+        vij = p.alpha[sd.toff + lt];
+        vji = cc[sd.tabOff + (size_t)k * sd.Nlam + lt] * vij;
+        uji = p.twohc[sd.toff + lt] * vji;
+    }
+    Uji[k] = uji;
+    Vij[k] = vij;
+    Vji[k] = vji;
+}
+
+// --------------------------------------------------------------------------------------------------------
+// Upload path: the host pack is a plain concatenation of the reference's depth-contiguous arrays; these kernels
+// turn it into the depth-major, wavelength-contiguous device layout.
+struct TransposeJob {
+    int64_t srcOff, dstOff;  // doubles, inside hostpack / colconst
+    int32_t R, C;            // src is [R][C], dst is [C][R]
+    int32_t tile0;           // first 32x32 tile of this job in the flat tile list
+    int32_t tilesC;          // tiles along C
+};
+
+__global__ void pack_transpose_kernel(const TransposeJob *jobs, int njobs, const double *staging, int64_t hpStride,
+                                      double *colconst, int64_t colStride, int col0)
+{
+    __shared__ double tile[32][33];
+    const int flat = blockIdx.x;
+    int lo = 0, hi = njobs - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (jobs[mid].tile0 <= flat)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    const TransposeJob jb = jobs[lo];
+    const int tl = flat - jb.tile0;
+    const int tr = tl / jb.tilesC, tc = tl - tr * jb.tilesC;
+    const double *src = staging + (size_t)blockIdx.y * hpStride + jb.srcOff;
+    double *dst = colconst + (size_t)(col0 + blockIdx.y) * colStride + jb.dstOff;
+    const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+    for (int q = ty; q < 32; q += 8) {
+        const int r = tr * 32 + q, c = tc * 32 + tx;
+        if (r < jb.R && c < jb.C) tile[q][tx] = src[(size_t)r * jb.C + c];
+    }
+    __syncthreads();
+    for (int q = ty; q < 32; q += 8) {
+        const int c = tc * 32 + q, r = tr * 32 + tx;
+        if (r < jb.R && c < jb.C) dst[(size_t)c * jb.R + r] = tile[tx][q];
+    }
+}
+
+struct CopyJob {
+    int64_t srcOff, dstOff, len;
+    int32_t toPops;  // destination is the pops buffer instead of colconst
+    int32_t pad;
+};
+struct WlaJob {
+    int64_t wphiOff;  // hostpack offset of wphi[t][N]
+    int64_t dstOff;   // colconst offset of wla[N][Nlam]
+    int32_t toff, Nlam;
+};
+
+__global__ void pack_misc_kernel(const CopyJob *copies, int ncopies, const WlaJob *wlas, int nwla,
+                                 const double *wlambda, int N, const double *staging, int64_t hpStride,
+                                 double *colconst, int64_t colStride, double *pops, int64_t popStride, double *J,
+                                 int64_t JStride, int col0)
+{
+    const int col = col0 + blockIdx.y;
+    const double *src = staging + (size_t)blockIdx.y * hpStride;
+    double *cc = colconst + (size_t)col * colStride;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    for (int c = 0; c < ncopies; ++c) {
+        const CopyJob cj = copies[c];
+        double *dst = cj.toPops ? pops + (size_t)col * popStride + cj.dstOff : cc + cj.dstOff;
+        for (int64_t q = tid; q < cj.len; q += nth) dst[q] = src[cj.srcOff + q];
+    }
+    // wla[k][lt] = wlambda(lt) * wphi[k] / HC   (rh_method.py:451)
+    for (int w = 0; w < nwla; ++w) {
+        const WlaJob wj = wlas[w];
+        const int64_t tot = (int64_t)N * wj.Nlam;
+        for (int64_t q = tid; q < tot; q += nth) {
+            const int k = (int)(q / wj.Nlam), lt = (int)(q - (int64_t)k * wj.Nlam);
+            cc[wj.dstOff + q] = wlambda[wj.toff + lt] * src[wj.wphiOff + k] / kHC;
+        }
+    }
+    double *Jc = J + (size_t)col * JStride;
+    for (int64_t q = tid; q < JStride; q += nth) Jc[q] = 0.0;
+}
+
+}  // namespace mali

@@ -1,0 +1,88 @@
+// mali_types.cuh -- device-side descriptors of the B200 MALI hot path.
+//
+// Layout vocabulary: a *column* is one 1D atmosphere; a *ray* is one
+// (wavelength la, angle mu) pair of a column, swept down (toFrom=0) then up (toFrom=1) over the
+// Nspace depth points; a *tile* is the group of Lw = 32 / Nrays consecutive wavelengths (all angles)
+// one warp owns; a *slot* is one radiative transition overlapping a tile's wavelength range.
+#pragma once
+#include <cstdint>
+
+namespace mali {
+
+// constants.py:1-4,17 -- digit for digit
+constexpr double kCLight = 2.99792458E+08;
+constexpr double kHPlanck = 6.6260755E-34;
+constexpr double kHC = kHPlanck * kCLight;
+constexpr double kKBoltzmann = 1.380658E-23;
+constexpr double kNmToM = 1.0E-09;
+constexpr double kPi = 3.141592653589793;  // == numpy.pi
+
+struct SlotDesc {
+    int32_t t;        // transition index (reference order)
+    int32_t isLine;
+    int32_t Nblue, Nlam;
+    int32_t rowI, rowJ;  // rows of the lower / upper level in n[sumNlevel][Nspace]
+    int32_t atom;
+    int32_t lsI, lsJ;    // level-slot of the lower / upper level inside the tile
+    int32_t toff;        // offset of this transition in the per-wavelength tables (alpha, twohc, wlacont)
+    int64_t tabOff;      // colconst offset: lines phi[2][N][Nlam][Nrays]; continua gij[N][Nlam]
+    int64_t wlaOff;      // colconst offset: lines wla[N][Nlam] = wlambda*wphi/HC   (rh_method.py:451)
+    double c0, c1, c2;   // lines: hc/4pi*Bij, Aji/Bji, Bji/Bij  (rh_method.py:279-281,450)
+};
+
+struct TileDesc {
+    int32_t la0;       // first wavelength of the tile
+    int32_t nslot;     // transitions overlapping [la0, la0+Lw)
+    int32_t slot0;     // first SlotDesc of the tile
+    int32_t nlevslot;  // distinct (atom, level) pairs touched by the tile's slots
+    int32_t partRow0;  // first row of the tile's Gamma partials (2 rows per slot: [i,j] then [j,i])
+    int32_t pad[3];
+};
+
+// Kernel parameters (passed by value -> constant bank).
+struct FsParams {
+    // sizes
+    int32_t N, Nrays, Nspect, Natom, Ntrans, Lw, ntile, Dmax;
+    int32_t col0, ncol, blocksPerCol, warpsPerBlock;
+    int32_t smemPerWarp;  // doubles
+    // strides (doubles per column)
+    int64_t colStride, popStride, JStride, IStride, scratchStride;
+    // offsets inside one column's colconst block
+    int64_t off_z, off_bbc, off_bgchi, off_bgeta, off_bgsca;
+    // offsets inside one column's scratch block
+    int64_t off_jpart, off_part;
+    // model tables (device)
+    const TileDesc *tiles;
+    const SlotDesc *slots;
+    const double *alpha, *twohc, *wlacont;  // concatenated per-wavelength tables
+    const double *zmu, *hw;                 // [Nrays]: 1/muz, 0.5*wmu
+    // batch buffers (device)
+    const double *colconst;
+    const double *pops;
+    double *J, *I, *scratch;
+    unsigned long long *dJbits;
+    const int32_t *done;  // may be null
+};
+
+struct FinishParams {
+    int32_t N, Natom, Ntrans, col0, ncol;
+    int32_t sumNlevel, sumNlevel2;
+    int64_t colStride, popStride, gammaStride, scratchStride;
+    int64_t off_C, off_nTotal, off_part;
+    const int32_t *Nlevel;     // [Natom]
+    const int32_t *lvlOff;     // [Natom+1]
+    const int32_t *g2Off;      // [Natom+1]
+    const int32_t *trans;      // [Ntrans][6]
+    const int32_t *trPartOff;  // [Ntrans+1] CSR into trPartRows
+    const int32_t *trPartRows; // partial row of the [i,j] entry (the [j,i] entry is row+1), ascending tile order
+    const double *colconst;
+    double *pops, *Gamma;
+    const double *scratch;
+    unsigned long long *dPopsBits;
+    int32_t *status;
+    const int32_t *done;
+    const int32_t *iter;  // may be null; with iter: only columns with iter[col] >= iterMin are solved
+    int32_t iterMin;
+};
+
+}  // namespace mali

@@ -1,0 +1,207 @@
+"""Batched MALI engine: owns the device buffers (torch tensors as carriers) of a batch of columns that share one
+radiative model, and drives libmali_b200.so through its C ABI.
+
+    eng = MaliEngine(problem_or_ModelTables, ncol)       # Context.__init__ for ncol columns
+    eng.upload([problem0, problem1, ...])                 # host pack -> H2D -> device re-layout
+    dJ = eng.formal_sol_gamma_matrices()                  # [ncol] numpy   (rh_method.py:565-708)
+    dP = eng.stat_equil()                                 # [ncol] numpy   (rh_method.py:710-745)
+    eng.J(col), eng.I(col), eng.Gamma(col), eng.n(col)    # numpy, reference shapes
+
+Columns are independent (no cross-column arithmetic anywhere), which is what makes the path data-parallel:
+ranks of a multi-GPU job each own a contiguous slice of columns (see lightspinner_b200/sharding.py).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _capi
+from .tables import ModelTables, pack_column
+
+
+class MaliEngine:
+    def __init__(self, model, ncol, device=None, max_upload_chunk=64):
+        if not torch.cuda.is_available():
+            raise RuntimeError('lightspinner_b200 needs a CUDA device: the MALI hot path has no CPU fallback')
+        self.mt = model if isinstance(model, ModelTables) else ModelTables(model)
+        self.ncol = int(ncol)
+        self.device = torch.device('cuda', torch.cuda.current_device() if device is None else device)
+        self.lib = _capi.load()
+        self._handle = C.c_void_p()
+        desc = self.mt.desc()
+        _capi.check(self.lib.mali_model_create(C.byref(desc), self.device.index, C.byref(self._handle)))
+        self.lay = _capi.Layout()
+        _capi.check(self.lib.mali_model_layout(self._handle, C.byref(self.lay)))
+        L = self.lay
+        f64 = dict(dtype=torch.float64, device=self.device)
+        i32 = dict(dtype=torch.int32, device=self.device)
+        n = self.ncol
+        self.t_colconst = torch.empty(n * L.colconst, **f64)
+        self.t_pops = torch.zeros(n * L.pops, **f64)
+        self.t_J = torch.zeros(n * L.J, **f64)
+        self.t_I = torch.zeros(n * L.I, **f64)
+        self.t_Gamma = torch.zeros(n * L.Gamma, **f64)
+        self.t_scratch = torch.zeros(n * L.scratch, **f64)
+        self.t_dJ = torch.zeros(n, **f64)
+        self.t_dPops = torch.ones(n, **f64)
+        self.t_status = torch.zeros(n, **i32)
+        self.t_iter = torch.zeros(n, **i32)
+        self.t_done = torch.zeros(n, **i32)
+        self.bufs = _capi.Buffers(n, *(t.data_ptr() for t in (
+            self.t_colconst, self.t_pops, self.t_J, self.t_I, self.t_Gamma, self.t_scratch, self.t_dJ,
+            self.t_dPops, self.t_status, self.t_iter, self.t_done)))
+        self.chunk = max(1, min(int(max_upload_chunk), n))
+        self._staging = None
+        self._pinned = None
+
+    def close(self):
+        if self._handle:
+            self.lib.mali_model_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _staging_bufs(self):
+        if self._staging is None:
+            self._staging = torch.empty(self.chunk * self.lay.hostpack, dtype=torch.float64, device=self.device)
+            self._pinned = torch.empty(self.chunk * self.lay.hostpack, dtype=torch.float64, pin_memory=True)
+        return self._staging, self._pinned
+
+    def hostpack_size(self):
+        return int(self.lay.hostpack)
+
+    # ------------------------------------------------------------------ upload
+    def upload(self, problems, col0=0):
+        """Pack and upload a list of problem dicts into columns [col0, col0+len(problems))."""
+        staging, pinned = self._staging_bufs()
+        hp = self.lay.hostpack
+        pin_np = pinned.numpy()
+        for c0 in range(0, len(problems), self.chunk):
+            chunk = problems[c0:c0 + self.chunk]
+            torch.cuda.current_stream(self.device).synchronize()  # pinned buffer reuse
+            for q, p in enumerate(chunk):
+                pack_column(self.mt, self.lay, p, out=pin_np[q * hp:(q + 1) * hp])
+            self.upload_packed(pinned, col0 + c0, len(chunk))
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def upload_packed(self, host_pinned, col0, ncol, staging=None):
+        """H2D copy of `ncol` host-pack blocks (a pinned torch tensor) + device re-layout; asynchronous."""
+        if staging is None:
+            staging, _ = self._staging_bufs()
+        if ncol * self.lay.hostpack > staging.numel():
+            raise ValueError('staging buffer too small for %d columns' % ncol)
+        with torch.cuda.device(self.device):
+            _capi.check(self.lib.mali_upload_columns(self._handle, C.byref(self.bufs), col0, ncol,
+                                                     C.c_void_p(host_pinned.data_ptr()),
+                                                     C.c_void_p(staging.data_ptr()), self._stream()))
+
+    def repack_from_staging(self, staging, col0, ncol):
+        """Device re-layout only (the staging tensor already holds host-pack blocks on the device)."""
+        with torch.cuda.device(self.device):
+            _capi.check(self.lib.mali_upload_columns(self._handle, C.byref(self.bufs), col0, ncol, None,
+                                                     C.c_void_p(staging.data_ptr()), self._stream()))
+
+    # ------------------------------------------------------------------ the hot path
+    def formal_sol_gamma_async(self, col0=0, ncol=None):
+        ncol = self.ncol - col0 if ncol is None else ncol
+        with torch.cuda.device(self.device):
+            _capi.check(self.lib.mali_formal_sol_gamma(self._handle, C.byref(self.bufs), col0, ncol, self._stream()))
+
+    def stat_equil_async(self, col0=0, ncol=None):
+        ncol = self.ncol - col0 if ncol is None else ncol
+        with torch.cuda.device(self.device):
+            _capi.check(self.lib.mali_stat_equil(self._handle, C.byref(self.bufs), col0, ncol, self._stream()))
+
+    def formal_sol_gamma_matrices(self):
+        """One Lambda iteration for every column; returns dJ per column (device->host read of ncol doubles)."""
+        self.formal_sol_gamma_async()
+        return self.t_dJ.cpu().numpy()
+
+    def stat_equil(self):
+        self.stat_equil_async()
+        dP = self.t_dPops.cpu().numpy()
+        status = self.t_status.cpu().numpy()
+        if (status & 1).any():
+            bad = np.nonzero(status & 1)[0]
+            self.t_status.zero_()
+            raise np.linalg.LinAlgError('singular statistical-equilibrium system in column(s) %s' % bad[:8].tolist())
+        return dP
+
+    def iterate_async(self, max_iter, tolJ=2e-3, tolPops=1e-3, col0=0, ncol=None):
+        """The loop of test.py:20-29 on the device with per-column convergence (tolJ < 0: fixed iteration count)."""
+        ncol = self.ncol - col0 if ncol is None else ncol
+        with torch.cuda.device(self.device):
+            _capi.check(self.lib.mali_iterate(self._handle, C.byref(self.bufs), col0, ncol, int(max_iter),
+                                              float(tolJ), float(tolPops), self._stream()))
+
+    def reset_iteration_state(self):
+        self.t_iter.zero_()
+        self.t_done.zero_()
+        self.t_dPops.fill_(1.0)
+        self.t_dJ.fill_(1.0)
+        self.t_status.zero_()
+
+    # ------------------------------------------------------------------ results, reference shapes
+    def J(self, col=0):
+        N, S = self.mt.Nspace, self.mt.Nspect
+        return self.t_J[col * self.lay.J:(col + 1) * self.lay.J].view(N, S).t().contiguous().cpu().numpy()
+
+    def I(self, col=0):
+        return self.t_I[col * self.lay.I:(col + 1) * self.lay.I].view(self.mt.Nspect, self.mt.Nrays).cpu().numpy()
+
+    def Gamma(self, col=0):
+        return self.t_Gamma[col * self.lay.Gamma:(col + 1) * self.lay.Gamma].view(-1, self.mt.Nspace).cpu().numpy()
+
+    def n(self, col=0):
+        return self.t_pops[col * self.lay.pops:(col + 1) * self.lay.pops].view(-1, self.mt.Nspace).cpu().numpy()
+
+    def set_n(self, col, n):
+        t = torch.from_numpy(np.ascontiguousarray(n, dtype=np.float64).reshape(-1))
+        self.t_pops[col * self.lay.pops:(col + 1) * self.lay.pops].copy_(t)
+
+    def atom_Gamma(self, col, a):
+        NL = int(self.mt.Nlevel[a])
+        g = self.Gamma(col)
+        return g[self.mt.g2off[a]:self.mt.g2off[a + 1]].reshape(NL, NL, self.mt.Nspace)
+
+    def atom_n(self, col, a):
+        return self.n(col)[self.mt.lvloff[a]:self.mt.lvloff[a + 1]]
+
+    # ------------------------------------------------------------------ test hooks
+    def uv(self, col, t, la, mu, toFrom):
+        N = self.mt.Nspace
+        out = torch.empty(3, N, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _capi.check(self.lib.mali_uv(self._handle, C.byref(self.bufs), col, t, la, mu, int(bool(toFrom)),
+                                         C.c_void_p(out[0].data_ptr()), C.c_void_p(out[1].data_ptr()),
+                                         C.c_void_p(out[2].data_ptr()), self._stream()))
+        o = out.cpu().numpy()
+        return o[0], o[1], o[2]   # Uji, Vij, Vji
+
+
+def piecewise_linear_1d_batch(z, muz, toFrom, bbc0, bbc1, chi, S, device=None):
+    """formal_solver.piecewise_linear_1d for nray independent rays on the GPU (test hook of the fused sweep)."""
+    if not torch.cuda.is_available():
+        raise RuntimeError('lightspinner_b200 needs a CUDA device: the MALI hot path has no CPU fallback')
+    dev = torch.device('cuda', torch.cuda.current_device() if device is None else device)
+    lib = _capi.load()
+    chi = np.ascontiguousarray(chi, dtype=np.float64)
+    nray, N = chi.shape
+    td = lambda a, dt=torch.float64: torch.as_tensor(np.ascontiguousarray(a), dtype=dt).to(dev)
+    tz, tmu, ttf = td(z), td(muz), td(np.asarray(toFrom, dtype=np.int32), torch.int32)
+    tb0, tb1, tchi, tS = td(bbc0), td(bbc1), td(chi), td(S)
+    tI = torch.empty(nray, N, dtype=torch.float64, device=dev)
+    tP = torch.empty(nray, N, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _capi.check(lib.mali_piecewise_linear_1d(N, nray, *(C.c_void_p(t.data_ptr()) for t in
+                                                           (tz, tmu, ttf, tb0, tb1, tchi, tS, tI, tP)),
+                                                 C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    return tI.cpu().numpy(), tP.cpu().numpy()
