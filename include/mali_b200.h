@@ -139,6 +139,9 @@ int mali_piecewise_linear_1d(int32_t Nspace, int32_t nray, const double *z_dev, 
                              const int32_t *toFrom_dev, const double *bbc0_dev, const double *bbc1_dev,
                              const double *chi_dev, const double *S_dev, double *I_dev, double *Psi_dev,
                              void *stream);
+/* y[i] = exp(x[i]) with the kernel's own exp (valid for 2^-54 <= |x| < 512): must equal libm's exp bit for bit,
+ * which is what numba calls in formal_solver.py:41. */
+int mali_exp_hook(int32_t n, const double *x_dev, double *y_dev, void *stream);
 /* ComputationalTransition.uv(la, mu, toFrom) for transition t of column col: writes Uji, Vij, Vji [Nspace]. */
 int mali_uv(const mali_model *m, const mali_buffers *bufs, int32_t col, int32_t t, int32_t la, int32_t mu,
             int32_t toFrom, double *Uji_dev, double *Vij_dev, double *Vji_dev, void *stream);

@@ -599,6 +599,14 @@ int mali_piecewise_linear_1d(int32_t Nspace, int32_t nray, const double *z, cons
     return MALI_OK;
 }
 
+int mali_exp_hook(int32_t n, const double *x_dev, double *y_dev, void *stream)
+{
+    if (n < 1 || !x_dev || !y_dev) return fail(MALI_EINVAL, "mali_exp_hook: bad argument");
+    exp_hook_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, x_dev, y_dev);
+    CU(cudaGetLastError());
+    return MALI_OK;
+}
+
 int mali_uv(const mali_model *m, const mali_buffers *b, int32_t col, int32_t t, int32_t la, int32_t mu, int32_t toFrom,
             double *Uji, double *Vij, double *Vji, void *stream)
 {

@@ -205,3 +205,14 @@ def piecewise_linear_1d_batch(z, muz, toFrom, bbc0, bbc1, chi, S, device=None):
                                                            (tz, tmu, ttf, tb0, tb1, tchi, tS, tI, tP)),
                                                  C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
     return tI.cpu().numpy(), tP.cpu().numpy()
+
+
+def exp_hook(x, device=None):
+    """The kernel's exp() on the GPU (test hook): must be bit-identical to libm's exp for 2^-54 <= |x| < 512."""
+    dev = torch.device('cuda', torch.cuda.current_device() if device is None else device)
+    tx = torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64)).to(dev)
+    ty = torch.empty_like(tx)
+    with torch.cuda.device(dev):
+        _capi.check(_capi.load().mali_exp_hook(tx.numel(), C.c_void_p(tx.data_ptr()), C.c_void_p(ty.data_ptr()),
+                                               C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    return ty.cpu().numpy()
