@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdint>
 
+#include "mali_solve.h"
 #include "mali_types.cuh"
 
 namespace mali {
@@ -402,13 +403,6 @@ __global__ void gamma_finish_kernel(const FinishParams p)
 // system Gamma' n = nTotal e_iEliminate by LU with partial pivoting, then two rounds of iterative refinement
 // with the residual accumulated in double-double (the systems have cond ~ 1e6..1e9, SURVEY.md 7.3-1: the aim is
 // to sit closer to the exact solution than LAPACK does, not to clone its rounding).
-__device__ __forceinline__ void two_sum(double a, double b, double &s, double &e)
-{
-    s = a + b;
-    const double bb = s - a;
-    e = (a - (s - bb)) + (b - bb);
-}
-
 template <int NLMAX>
 __global__ void stat_equil_kernel(const FinishParams p)
 {
@@ -420,14 +414,11 @@ __global__ void stat_equil_kernel(const FinishParams p)
     if (p.iter != nullptr && p.iter[col] < p.iterMin) return;
     const int N = p.N;
     const int NL = p.Nlevel[a];
-    const double *G = p.Gamma + (size_t)col * p.gammaStride + (size_t)p.g2Off[a] * N;
+    const double *G = p.Gamma + (size_t)col * p.gammaStride + (size_t)p.g2Off[a] * N + k;
     double *n = p.pops + (size_t)col * p.popStride + (size_t)p.lvlOff[a] * N;
     const double nTot = p.colconst[(size_t)col * p.colStride + p.off_nTotal + (size_t)a * N + k];
 
-    double A[NLMAX * NLMAX], LU[NLMAX * NLMAX], x[NLMAX], r[NLMAX];
-    int piv[NLMAX];
-
-    // iEliminate = argmax(n[:, k]) (first maximum)
+    // iEliminate = argmax(n[:, k]) (first maximum, rh_method.py:727)
     int iEl = 0;
     double nmax = n[k];
     for (int l = 1; l < NL; ++l) {
@@ -437,90 +428,9 @@ __global__ void stat_equil_kernel(const FinishParams p)
             iEl = l;
         }
     }
-    for (int i = 0; i < NL; ++i)
-        for (int j = 0; j < NL; ++j) {
-            const double v = (i == iEl) ? 1.0 : G[((size_t)i * NL + j) * N + k];
-            A[i * NLMAX + j] = v;
-            LU[i * NLMAX + j] = v;
-        }
-
-    bool singular = false;
-    for (int j = 0; j < NL; ++j) {
-        int pr = j;
-        double best = fabs(LU[j * NLMAX + j]);
-        for (int i = j + 1; i < NL; ++i) {
-            const double v = fabs(LU[i * NLMAX + j]);
-            if (v > best) {
-                best = v;
-                pr = i;
-            }
-        }
-        piv[j] = pr;
-        if (!(best > 0.0) || !(best <= DBL_MAX)) {
-            singular = true;
-            break;
-        }
-        if (pr != j)
-            for (int q = 0; q < NL; ++q) {
-                const double tmp = LU[j * NLMAX + q];
-                LU[j * NLMAX + q] = LU[pr * NLMAX + q];
-                LU[pr * NLMAX + q] = tmp;
-            }
-        const double pv = LU[j * NLMAX + j];
-        for (int i = j + 1; i < NL; ++i) {
-            const double l = LU[i * NLMAX + j] / pv;
-            LU[i * NLMAX + j] = l;
-            for (int q = j + 1; q < NL; ++q) LU[i * NLMAX + q] -= l * LU[j * NLMAX + q];
-        }
-    }
-    if (singular) {
-        atomicOr(p.status + col, 1);
-        return;
-    }
-
-    auto lu_solve = [&](double *b) {
-        for (int j = 0; j < NL; ++j) {
-            const int pr = piv[j];
-            if (pr != j) {
-                const double tmp = b[j];
-                b[j] = b[pr];
-                b[pr] = tmp;
-            }
-            for (int i = j + 1; i < NL; ++i) b[i] -= LU[i * NLMAX + j] * b[j];
-        }
-        for (int i = NL - 1; i >= 0; --i) {
-            double acc = b[i];
-            for (int q = i + 1; q < NL; ++q) acc -= LU[i * NLMAX + q] * b[q];
-            b[i] = acc / LU[i * NLMAX + i];
-        }
-    };
-
-    for (int i = 0; i < NL; ++i) x[i] = 0.0;
-    x[iEl] = nTot;
-    lu_solve(x);
-    for (int it = 0; it < 2; ++it) {
-        // r = b - A x in double-double
-        for (int i = 0; i < NL; ++i) {
-            double hi = (i == iEl) ? nTot : 0.0, lo = 0.0;
-            for (int j = 0; j < NL; ++j) {
-                const double aij = A[i * NLMAX + j];
-                const double ph = -(aij * x[j]);
-                const double pl = -__fma_rn(aij, x[j], ph);  // exact product error (ph = -(a*x) rounded)
-                double s, e;
-                two_sum(hi, ph, s, e);
-                hi = s;
-                lo += e + pl;
-            }
-            r[i] = hi + lo;
-        }
-        lu_solve(r);
-        for (int i = 0; i < NL; ++i) x[i] += r[i];
-    }
-
-    bool ok = true;
-    for (int i = 0; i < NL; ++i) ok = ok && (fabs(x[i]) <= DBL_MAX);
-    if (!ok) {
-        atomicOr(p.status + col, 1);
+    double x[NLMAX];
+    if (!solve_stat_equil<NLMAX>(G, N, NL, iEl, nTot, x)) {
+        atomicOr(p.status + col, 1);  // the reference would raise LinAlgError here
         return;
     }
     unsigned long long db = 0ull;
