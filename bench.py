@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py -- MALI ray-depth updates/s on B200 (BASELINE.json metric), one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--ncol C] [--iters I]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Workload (config.workload): BASELINE config 4's per-GPU share -- a synthetic 1.5D batch of `ncol` perturbed FALC
+columns per GPU (default 1024; 8 GPUs = the config's 8192), CaII + H 6-level both active (Nspect 777, 5 rays, 82 depths,
+25 overlapping transitions), derived from the committed reference fixture tests/golden/c2_falc_cah.npz by
+lightspinner_b200/synth.py.  Columns shard across ranks with no data-path collective (weak scaling); the only
+exchange is the final gather of the emergent intensities, done inside the e2e region when N > 1.
+
+A *step* is one fixed-length MALI solve of the whole batch: `iters` iterations, each = formal solution + Gamma
+(fs_gamma_kernel, gamma_finish_kernel) + statistical equilibrium (stat_equil_kernel).
+  value : units / s with the inputs already resident in HBM (units = ncol_total * Nspect * Nrays * Nspace * iters)
+  e2e   : the same solve through the public API from pinned HOST buffers: every step copies every column's
+          inputs host->device (chunked, double-buffered against the compute), re-lays them out on the device,
+          iterates, and reads I, n, dJ, dPops back to the host.
+  roofline : fs_gamma_kernel only: algorithmic bytes per launch (SURVEY.md 8d formula) / its mean device time
+             measured with CUDA events around every launch inside the timed region, vs MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline : the oracle's C restatement (OpenMP over columns, all host cores) on a bounded sample of the same
+                 columns and the same `iters` (rank 0, N = 1 only).  --impl reference prints that arm alone.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+METRIC = 'MALI ray-depth updates/s'
+UNIT = 'updates/s'
+
+
+def load_base(name):
+    from helpers import load_golden
+    return load_golden(name)[0]
+
+
+def algorithmic_bytes_per_column(p):
+    """every distinct input read once and every output written once per iteration, fp64."""
+    N, S, R = int(p['Nspace']), int(p['Nspect']), int(p['Nrays'])
+    tr = np.asarray(p['trans'])
+    line_nl = int(tr[tr[:, 3] == 1, 5].sum())
+    nl = np.asarray(p['Nlevel'], dtype=np.int64)
+    return 8 * (2 * line_nl * R * N + 5 * S * N + int(((2 * nl * nl + 2 * nl + 1) * N).sum()) + S * R)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.isfile(path):
+        try:
+            return float(json.load(open(path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+        except Exception:
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, pw = [], [], set(), []
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                smax.append(float(r[1]))
+                pw.append(float(r[2]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith('active'):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(smax) if smax else None,
+                'power_w_max': max(pw) if pw else None, 'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def cpu_oracle_rate(base, ncol_cpu, iters, col0=0):
+    """Times the oracle's C restatement (OpenMP over columns) on synthetic columns [col0, col0+ncol_cpu)."""
+    from oracle import mali_oracle as mo
+    from lightspinner_b200 import synth
+    mo.build()
+    ctxs = [mo.OracleContext(synth.jitter_problem(base, col0 + c)) for c in range(ncol_cpu)]
+    t0 = time.perf_counter()
+    mo.iterate_batch(ctxs, iters, start_iter=3)     # start_iter=3: every iteration does formal solution + stat-eq
+    dt = time.perf_counter() - t0
+    units = ncol_cpu * int(base['Nspect']) * int(base['Nrays']) * int(base['Nspace']) * iters
+    return units / dt, dt, mo.max_threads(), ctxs
+
+
+def run_reference(args, base):
+    """--impl reference: the reference's algorithm on the host cores (the oracle port; the reference itself is
+    pure Python and is not present on the GPU box).  Rank 0 only."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    ncol_cpu = max(threads, min(4 * threads, 256))
+    for _ in range(args.warmup and 1):
+        cpu_oracle_rate(base, min(ncol_cpu, threads), 1)
+    rates, times = [], []
+    for _ in range(args.steps):
+        r, dt, th, _ = cpu_oracle_rate(base, ncol_cpu, args.iters)
+        rates.append(r)
+        times.append(dt)
+    units = ncol_cpu * int(base['Nspect']) * int(base['Nrays']) * int(base['Nspace']) * args.iters
+    value = units * len(times) / sum(times)
+    sample = '%d synthetic columns x %d MALI iterations per step (of the %d-column batch)' % (
+        ncol_cpu, args.iters, args.ncol * args.gpus)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * sum(times) / len(times),
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': workload_config(args, base),
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': th, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, base):
+    return {
+        'workload': 'synthetic 1.5D batch of perturbed FALC columns, CaII + H 6-level active '
+                    '(BASELINE config 4 per-GPU share), fixed-length MALI solve',
+        'fixture': args.fixture, 'columns_per_gpu': args.ncol, 'columns_total': args.ncol * args.gpus,
+        'iters_per_solve': args.iters, 'Nspace': int(base['Nspace']), 'Nrays': int(base['Nrays']),
+        'Nspect': int(base['Nspect']), 'Ntrans': int(np.asarray(base['trans']).shape[0]),
+        'parallelism': 'columns sharded over %d GPU(s), no data-path collective' % args.gpus,
+        'l2_policy': 'inputs larger than L2 (%.1f GB of per-column tables per GPU)' % (
+            args.ncol * algorithmic_bytes_per_column(base) / 1e9),
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--ncol', type=int, default=1024, help='columns per GPU')
+    ap.add_argument('--iters', type=int, default=16, help='MALI iterations per solve (= per step)')
+    ap.add_argument('--fixture', default='c2_falc_cah')
+    ap.add_argument('--chunk', type=int, default=128, help='columns per upload chunk in the e2e path')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cpu', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    base = load_base(args.fixture)
+
+    if args.impl == 'reference':
+        run_reference(args, base)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from lightspinner_b200 import synth
+    from lightspinner_b200.engine import MaliEngine
+    from lightspinner_b200.tables import pack_column
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world != args.gpus and world > 1:
+        raise SystemExit('--gpus %d but WORLD_SIZE=%d' % (args.gpus, world))
+    if args.gpus > 1 and world == 1:
+        raise SystemExit('launch with torch.distributed.run --nproc-per-node %d for --gpus %d' % (args.gpus, args.gpus))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ncol, iters = args.ncol, args.iters
+    N, S, R = int(base['Nspace']), int(base['Nspect']), int(base['Nrays'])
+    units_per_col_iter = S * R * N
+    eng = MaliEngine(base, ncol, device=local, max_upload_chunk=args.chunk)
+    lay, mt = eng.lay, eng.mt
+    hp = int(lay.hostpack)
+    chunk = min(args.chunk, ncol)
+    col_global0 = rank * ncol        # this rank's slice of the global batch
+
+    # ---- build the resident batch: base host pack -> device, jitter on the device, re-layout
+    base_pack = torch.from_numpy(pack_column(mt, lay, base)).to(dev)
+    staging = [torch.empty(chunk * hp, dtype=torch.float64, device=dev) for _ in range(2)]
+    want_e2e = not args.no_e2e
+    host_in = torch.empty(ncol * hp, dtype=torch.float64, pin_memory=True) if want_e2e else None
+    for c0 in range(0, ncol, chunk):
+        nc = min(chunk, ncol - c0)
+        synth.jitter_staging(staging[0], lay, mt, base_pack, [col_global0 + c for c in range(c0, c0 + nc)])
+        eng.repack_from_staging(staging[0], c0, nc)
+        if want_e2e:
+            host_in[c0 * hp:(c0 + nc) * hp].copy_(staging[0][:nc * hp])
+    torch.cuda.synchronize(dev)
+
+    def solve_resident():
+        for _ in range(iters):
+            eng.formal_sol_gamma_async()
+            eng.stat_equil_async()
+
+    # ---- value: inputs resident in HBM
+    for _ in range(args.warmup):
+        solve_resident()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches0 = eng.launch_count()
+    eng.profile_begin(args.steps * iters)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        solve_resident()
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    fs_ms, fs_n = eng.profile_end()
+    launches = eng.launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    finite = bool(torch.isfinite(eng.t_pops).all().item() and torch.isfinite(eng.t_I).all().item())
+    total_units = world * ncol * units_per_col_iter * iters * args.steps
+    value = total_units / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel
+    peak, peak_src = measured_peaks()
+    fs_ms_mean = fs_ms / max(fs_n, 1)
+    alg_bytes = algorithmic_bytes_per_column(base) * ncol
+    achieved = alg_bytes / (fs_ms_mean * 1e-3) / 1e9
+    roofline = {'kernel': 'fs_gamma_kernel', 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                'algorithmic_bytes_per_launch': alg_bytes, 'mean_launch_ms': fs_ms_mean, 'launches_timed': fs_n,
+                'share_of_step': fs_ms / ms if ms > 0 else None,
+                'note': 'fp64 CUDA-core work binds before HBM on this path (SURVEY.md 7.3-2); see DESIGN.md'}
+
+    # ---- e2e: host buffers -> H2D -> re-layout -> iterate -> D2H, double-buffered over column chunks
+    e2e = None
+    if want_e2e:
+        streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+        out_I = torch.empty(ncol * lay.I, dtype=torch.float64, pin_memory=True)
+        out_n = torch.empty(ncol * lay.pops, dtype=torch.float64, pin_memory=True)
+        out_d = torch.empty(2 * ncol, dtype=torch.float64, pin_memory=True)
+        gathered = torch.empty(world * ncol * lay.I, dtype=torch.float64, device=dev) if world > 1 else None
+
+        def solve_from_host():
+            for ci, c0 in enumerate(range(0, ncol, chunk)):
+                nc = min(chunk, ncol - c0)
+                st = streams[ci & 1]
+                with torch.cuda.stream(st):
+                    eng.upload_packed(host_in[c0 * hp:(c0 + nc) * hp], c0, nc, staging=staging[ci & 1])
+                    for _ in range(iters):
+                        eng.formal_sol_gamma_async(c0, nc)
+                        eng.stat_equil_async(c0, nc)
+                    out_I[c0 * lay.I:(c0 + nc) * lay.I].copy_(eng.t_I[c0 * lay.I:(c0 + nc) * lay.I], non_blocking=True)
+                    out_n[c0 * lay.pops:(c0 + nc) * lay.pops].copy_(eng.t_pops[c0 * lay.pops:(c0 + nc) * lay.pops],
+                                                                  non_blocking=True)
+                    out_d[c0:c0 + nc].copy_(eng.t_dJ[c0:c0 + nc], non_blocking=True)
+                    out_d[ncol + c0:ncol + c0 + nc].copy_(eng.t_dPops[c0:c0 + nc], non_blocking=True)
+            for st in streams:
+                torch.cuda.current_stream(dev).wait_stream(st)
+            if world > 1:     # the path's only exchange: final gather of the emergent intensities
+                dist.all_gather_into_tensor(gathered, eng.t_I)
+
+        solve_from_host()
+        barrier()
+        l0 = eng.launch_count()
+        k_e2e = max(1, min(args.steps, 3))
+        e0.record()
+        for _ in range(k_e2e):
+            solve_from_host()
+        e1.record()
+        barrier()
+        ms_e = max_over_ranks(e0.elapsed_time(e1))
+        launches_e2e = eng.launch_count() - l0
+        e_units = world * ncol * units_per_col_iter * iters * k_e2e
+        e2e = {'value': e_units / (ms_e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': world * ncol * hp * 8,
+               'd2h_bytes_per_step': world * (ncol * (lay.I + lay.pops) + 2 * ncol) * 8, 'steps': k_e2e,
+               'ms_per_step': ms_e / k_e2e, 'gpu_launches': launches_e2e,
+               'finite': bool(np.isfinite(out_I.numpy()).all() and np.isfinite(out_n.numpy()).all()),
+               'pipeline': '%d-column chunks, 2 streams (H2D of chunk c+1 overlaps the iterations of chunk c)' % chunk}
+        if world > 1:
+            e2e['gather_bytes_per_step'] = world * ncol * lay.I * 8
+
+    # ---- CPU baseline on the host cores (rank 0, N = 1)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        ncol_cpu = max(1, min(ncol, max(threads, min(4 * threads, 256))))
+        rate, dt, th, ctxs = cpu_oracle_rate(base, ncol_cpu, iters, col0=col_global0)
+        cpu = {'value': rate, 'unit': UNIT, 'cores': th, 'kind': 'port',
+               'sample': '%d of the %d synthetic columns x %d MALI iterations, oracle C restatement with OpenMP '
+                         'over columns, %.1f s' % (ncol_cpu, ncol, iters, dt)}
+
+    if rank == 0:
+        cfg = workload_config(args, base)
+        line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+                'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+                'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': cfg, 'clocks': clocks,
+                'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu,
+                'results_finite': finite}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -132,6 +132,13 @@ int mali_stat_equil(const mali_model *m, const mali_buffers *bufs, int32_t col0,
 int mali_iterate(const mali_model *m, const mali_buffers *bufs, int32_t col0, int32_t ncol, int32_t max_iter,
                  double tolJ, double tolPops, void *stream);
 
+/* Measurement: between begin and end every fs_gamma_kernel launch made through this model is bracketed by CUDA
+ * events on its stream; end() returns their summed device time and the launch count (bench.py's roofline).
+ * mali_launch_count: kernels launched through this model since creation (bench.py's gpu_launches). */
+int mali_profile_begin(const mali_model *m, int32_t max_launches);
+int mali_profile_end(const mali_model *m, double *fs_ms_total, int32_t *fs_launches);
+long long mali_launch_count(const mali_model *m);
+
 /* Test hooks ---------------------------------------------------------------------------------------------- */
 /* piecewise_linear_1d for nray independent rays: chi, S, I, Psi are [nray][Nspace]; muz, bbc0/bbc1 (planck at
  * T[-2], T[-1]) and toFrom are per ray; z is [Nspace] (shared). */

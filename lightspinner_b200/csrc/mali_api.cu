@@ -106,6 +106,11 @@ struct mali_model {
     TransposeJob *d_tjobs = nullptr;
     CopyJob *d_cjobs = nullptr;
     WlaJob *d_wjobs = nullptr;
+    // optional per-launch timing of fs_gamma_kernel (mali_profile_begin / mali_profile_end)
+    mutable std::vector<cudaEvent_t> profEvents;
+    mutable int profUsed = 0;
+    mutable bool profOn = false;
+    mutable long long launches = 0;  // kernels launched through this model since creation
 };
 
 extern "C" {
@@ -396,6 +401,7 @@ void mali_model_destroy(mali_model *m)
                     m->d_cjobs, m->d_wjobs};
     for (void *p : ptrs)
         if (p) cudaFree(p);
+    for (cudaEvent_t e : m->profEvents) cudaEventDestroy(e);
     delete m;
 }
 
@@ -526,7 +532,14 @@ static int launch_fs(const mali_model *m, const mali_buffers *b, int col0, int n
         CU(cudaFuncSetAttribute(fs_gamma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     col_zero_bits_kernel<<<(ncol + 127) / 128, 128, 0, st>>>(p.dJbits, b->done, nullptr, 0, col0, ncol);
+    const bool rec = m->profOn && m->profUsed + 2 <= (int)m->profEvents.size();
+    if (rec) cudaEventRecord(m->profEvents[m->profUsed], st);
     fs_gamma_kernel<<<(unsigned)(p.blocksPerCol * ncol), 32 * wpb, smem, st>>>(p);
+    if (rec) {
+        cudaEventRecord(m->profEvents[m->profUsed + 1], st);
+        m->profUsed += 2;
+    }
+    m->launches += 3;
     FinishParams f = make_finish_params(m, b, col0, ncol);
     dim3 grid((m->N + 63) / 64, m->Natom, ncol);
     gamma_finish_kernel<<<grid, 64, 0, st>>>(f);
@@ -547,6 +560,7 @@ static int launch_se(const mali_model *m, const mali_buffers *b, int col0, int n
         stat_equil_kernel<8><<<grid, 64, 0, st>>>(f);
     else
         stat_equil_kernel<16><<<grid, 64, 0, st>>>(f);
+    m->launches += 2;
     CU(cudaGetLastError());
     return MALI_OK;
 }
@@ -581,6 +595,7 @@ int mali_iterate(const mali_model *m, const mali_buffers *b, int32_t col0, int32
         iterate_ctl_kernel<<<nb, 128, 0, st>>>(0, b->dJ, b->dPops, b->iter, b->done, tolJ, tolPops, col0, ncol);
         if (int r = launch_se(m, b, col0, ncol, b->iter, 4, st)) return r;
         iterate_ctl_kernel<<<nb, 128, 0, st>>>(1, b->dJ, b->dPops, b->iter, b->done, tolJ, tolPops, col0, ncol);
+        m->launches += 2;
     }
     CU(cudaGetLastError());
     return MALI_OK;
@@ -598,6 +613,39 @@ int mali_piecewise_linear_1d(int32_t Nspace, int32_t nray, const double *z, cons
     CU(cudaGetLastError());
     return MALI_OK;
 }
+
+int mali_profile_begin(const mali_model *m, int32_t max_launches)
+{
+    if (!m || max_launches < 1) return fail(MALI_EINVAL, "mali_profile_begin: bad argument");
+    CU(cudaSetDevice(m->device));
+    while ((int)m->profEvents.size() < 2 * max_launches) {
+        cudaEvent_t e;
+        CU(cudaEventCreate(&e));
+        m->profEvents.push_back(e);
+    }
+    m->profUsed = 0;
+    m->profOn = true;
+    return MALI_OK;
+}
+
+int mali_profile_end(const mali_model *m, double *fs_ms_total, int32_t *fs_launches)
+{
+    if (!m || !fs_ms_total || !fs_launches) return fail(MALI_EINVAL, "mali_profile_end: bad argument");
+    m->profOn = false;
+    double tot = 0.0;
+    for (int q = 0; q + 1 < m->profUsed; q += 2) {
+        CU(cudaEventSynchronize(m->profEvents[q + 1]));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, m->profEvents[q], m->profEvents[q + 1]));
+        tot += ms;
+    }
+    *fs_ms_total = tot;
+    *fs_launches = m->profUsed / 2;
+    m->profUsed = 0;
+    return MALI_OK;
+}
+
+long long mali_launch_count(const mali_model *m) { return m ? m->launches : 0; }
 
 int mali_exp_hook(int32_t n, const double *x_dev, double *y_dev, void *stream)
 {

@@ -149,6 +149,19 @@ class MaliEngine:
         self.t_dJ.fill_(1.0)
         self.t_status.zero_()
 
+    # ------------------------------------------------------------------ measurement
+    def profile_begin(self, max_launches):
+        _capi.check(self.lib.mali_profile_begin(self._handle, int(max_launches)))
+
+    def profile_end(self):
+        """(summed device ms of the fs_gamma_kernel launches since profile_begin, number of launches)"""
+        ms, n = C.c_double(0.0), C.c_int32(0)
+        _capi.check(self.lib.mali_profile_end(self._handle, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def launch_count(self):
+        return int(self.lib.mali_launch_count(self._handle))
+
     # ------------------------------------------------------------------ results, reference shapes
     def J(self, col=0):
         N, S = self.mt.Nspace, self.mt.Nspect
