@@ -12,7 +12,7 @@
 #include <vector>
 
 #include "../../include/mali_b200.h"
-#include "mali_kernels.cuh"
+#include "mali_fs_kernel.cuh"
 
 using namespace mali;
 
@@ -89,6 +89,8 @@ struct mali_model {
     std::vector<SlotDesc> slots;
     std::vector<TileDesc> tiles;
     std::vector<SlotDesc> transSlot;  // one descriptor per transition (for the uv hook)
+    std::vector<int32_t> classTiles[3];  // tiles with <= 4, 5..8, > 8 transitions
+    int32_t *d_classTiles[3] = {nullptr, nullptr, nullptr};
     mali_layout lay{};
     int64_t off_z = 0, off_bbc = 0, off_bgchi = 0, off_bgeta = 0, off_bgsca = 0, off_C = 0, off_nTotal = 0;
     int64_t off_jpart = 0, off_part = 0;
@@ -112,6 +114,17 @@ struct mali_model {
     mutable bool profOn = false;
     mutable long long launches = 0;  // kernels launched through this model since creation
 };
+
+template <int TMAX>
+static void launch_fs_class(const FsParams &p, int natom, unsigned grid, int threads, size_t smem, cudaStream_t st)
+{
+    if (natom == 1)
+        fs_gamma_kernel_t<TMAX, 1><<<grid, threads, smem, st>>>(p);
+    else if (natom == 2)
+        fs_gamma_kernel_t<TMAX, 2><<<grid, threads, smem, st>>>(p);
+    else
+        fs_gamma_kernel_t<TMAX, 4><<<grid, threads, smem, st>>>(p);
+}
 
 extern "C" {
 
@@ -281,16 +294,18 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
             const int32_t *tr = &m->trans[(size_t)t * 6];
             if (!(tr[4] < la1 && tr[4] + tr[5] > la0)) continue;
             SlotDesc s = m->transSlot[t];
-            auto slot_of = [&](int level) {
+            auto slot_of = [&](int level, int bit) {
                 auto key = std::make_pair((int)tr[0], level);
                 auto it = lev.find(key);
                 if (it != lev.end()) return it->second;
                 const int id = (int)lev.size();
                 lev[key] = id;
+                s.flags |= bit;  // first slot of the tile to touch this level: store instead of accumulate
                 return id;
             };
-            s.lsI = slot_of(tr[1]);
-            s.lsJ = slot_of(tr[2]);
+            s.flags = 0;
+            s.lsI = slot_of(tr[1], 1);
+            s.lsJ = slot_of(tr[2], 2);
             trRows[t].push_back(partRow);
             partRow += 2;
             m->slots.push_back(s);
@@ -302,6 +317,15 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
         m->tiles.push_back(td);
     }
     m->nPartRows = partRow;
+    if (m->Dmax > 255 || L.colconst >= (int64_t)1 << 31) {
+        delete m;
+        return fail(MALI_ELIMIT, "tile touches %d levels / column block of %lld doubles: beyond the 32-bit offsets of the kernel", m->Dmax, (long long)L.colconst);
+    }
+    for (int ti = 0; ti < m->ntile; ++ti) {
+        const int T = m->tiles[ti].nslot;
+        const int cls = (d->Natom > 4 || T > 8) ? 2 : (T > 4 ? 1 : 0);
+        m->classTiles[cls].push_back(ti);
+    }
     std::vector<int32_t> trPartOff(d->Ntrans + 1, 0), trPartRows;
     for (int t = 0; t < d->Ntrans; ++t) {
         trPartOff[t + 1] = trPartOff[t] + (int)trRows[t].size();
@@ -315,8 +339,9 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
     L.scratch = so;
 
     // ---- upload jobs
-    auto add_transpose = [&](int64_t src, int64_t dst, int R, int C) {
+    auto add_transpose = [&](int64_t src, int64_t dst, int R, int C, double scale = 1.0) {
         TransposeJob j{};
+        j.scale = scale;
         j.srcOff = src;
         j.dstOff = dst;
         j.R = R;
@@ -332,7 +357,7 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
     for (int t = 0; t < d->Ntrans; ++t) {
         const int32_t *tr = &m->trans[(size_t)t * 6];
         if (tr[3]) {
-            add_transpose(hpPhi[t], tabOff[t], tr[5] * d->Nrays, 2 * N);
+            add_transpose(hpPhi[t], tabOff[t], tr[5] * d->Nrays, 2 * N, d->lineconst[3 * t + 0]);
             WlaJob w{};
             w.wphiOff = L.hp_wphi + (int64_t)t * N;
             w.dstOff = wlaOff[t];
@@ -381,6 +406,7 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
     up(to_device(m->trans, &m->d_trans));
     up(to_device(trPartOff, &m->d_trPartOff));
     up(to_device(trPartRows, &m->d_trPartRows));
+    for (int c = 0; c < 3; ++c) up(to_device(m->classTiles[c], &m->d_classTiles[c]));
     up(to_device(m->tjobs, &m->d_tjobs));
     up(to_device(m->cjobs, &m->d_cjobs));
     up(to_device(m->wjobs, &m->d_wjobs));
@@ -398,7 +424,7 @@ void mali_model_destroy(mali_model *m)
     cudaSetDevice(m->device);
     void *ptrs[] = {m->d_tiles, m->d_slots, m->d_alpha, m->d_twohc, m->d_wlacont, m->d_wlambda, m->d_zmu, m->d_hw,
                     m->d_Nlevel, m->d_lvlOff, m->d_g2Off, m->d_trans, m->d_trPartOff, m->d_trPartRows, m->d_tjobs,
-                    m->d_cjobs, m->d_wjobs};
+                    m->d_cjobs, m->d_wjobs, m->d_classTiles[0], m->d_classTiles[1], m->d_classTiles[2]};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (cudaEvent_t e : m->profEvents) cudaEventDestroy(e);
@@ -527,22 +553,40 @@ static int launch_fs(const mali_model *m, const mali_buffers *b, int col0, int n
     const int wpb = ((int64_t)ncol * m->ntile >= 148 * 16) ? 4 : 1;
     FsParams p = make_fs_params(m, b, col0, ncol, wpb);
     const size_t smem = (size_t)p.smemPerWarp * wpb * sizeof(double);
-    if (smem > 48 * 1024) {
-        if (smem > 227 * 1024) return fail(MALI_ELIMIT, "tile needs %zu B of shared memory", smem);
-        CU(cudaFuncSetAttribute(fs_gamma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 227 * 1024) return fail(MALI_ELIMIT, "tile needs %zu B of shared memory", smem);
+    static bool attr_set = false;
+    if (smem > 48 * 1024 && !attr_set) {
+        CU(cudaFuncSetAttribute(fs_gamma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
     }
     col_zero_bits_kernel<<<(ncol + 127) / 128, 128, 0, st>>>(p.dJbits, b->done, nullptr, 0, col0, ncol);
+    m->launches += 1;
     const bool rec = m->profOn && m->profUsed + 2 <= (int)m->profEvents.size();
     if (rec) cudaEventRecord(m->profEvents[m->profUsed], st);
-    fs_gamma_kernel<<<(unsigned)(p.blocksPerCol * ncol), 32 * wpb, smem, st>>>(p);
+    // heaviest class first so that the light tiles fill the tail
+    for (int cls = 2; cls >= 0; --cls) {
+        const int nt = (int)m->classTiles[cls].size();
+        if (nt == 0) continue;
+        p.classTiles = m->d_classTiles[cls];
+        p.nClassTiles = nt;
+        p.blocksPerCol = (nt + wpb - 1) / wpb;
+        const unsigned grid = (unsigned)(p.blocksPerCol * ncol);
+        if (cls == 2)
+            fs_gamma_kernel<<<grid, 32 * wpb, smem, st>>>(p);
+        else if (cls == 1)
+            launch_fs_class<8>(p, m->Natom, grid, 32 * wpb, smem, st);
+        else
+            launch_fs_class<4>(p, m->Natom, grid, 32 * wpb, smem, st);
+        m->launches += 1;
+    }
     if (rec) {
         cudaEventRecord(m->profEvents[m->profUsed + 1], st);
         m->profUsed += 2;
     }
-    m->launches += 3;
     FinishParams f = make_finish_params(m, b, col0, ncol);
     dim3 grid((m->N + 63) / 64, m->Natom, ncol);
     gamma_finish_kernel<<<grid, 64, 0, st>>>(f);
+    m->launches += 1;
     CU(cudaGetLastError());
     return MALI_OK;
 }

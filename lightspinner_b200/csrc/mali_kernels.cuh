@@ -3,7 +3,9 @@
 //
 // Compile with --fmad=false: the reference arithmetic (numpy, numba without fastmath) never contracts
 // a*b+c, and every expression below is written in the reference's evaluation order so that
-// the only sources of difference are exp() in w2 (CUDA libdevice vs glibc) and the order of the J / Gamma sums.
+// the only source of difference is the order of the J / Gamma sums (exp_m below reproduces libm's exp).
+// This file holds the generic kernel (any number of transitions per tile; runtime loops) and the small kernels;
+// the production formal-solution kernel is the register-resident fs_gamma_kernel_t in mali_fs_kernel.cuh.
 #pragma once
 #include <cfloat>
 #include <cmath>
@@ -174,12 +176,12 @@ __global__ void __launch_bounds__(128) fs_gamma_kernel(const FsParams p)
 {
     extern __shared__ double smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile = (blockIdx.x % p.blocksPerCol) * p.warpsPerBlock + warp;
+    const int tslot = (blockIdx.x % p.blocksPerCol) * p.warpsPerBlock + warp;
     const int col = p.col0 + blockIdx.x / p.blocksPerCol;
-    if (tile >= p.ntile) return;
+    if (tslot >= p.nClassTiles) return;
     if (p.done != nullptr && p.done[col] != 0) return;
 
-    const TileDesc td = p.tiles[tile];
+    const TileDesc td = p.tiles[p.classTiles[tslot]];
     const int N = p.N, Nrays = p.Nrays, Nspect = p.Nspect;
     const int ls = lane / Nrays, mu = lane - ls * Nrays;
     const int la = td.la0 + ls;
@@ -239,7 +241,7 @@ __global__ void __launch_bounds__(128) fs_gamma_kernel(const FsParams p)
                 if (sd.isLine) {
                     const double phi =
                         act ? __ldg(cc + sd.tabOff + ((size_t)(d * N + k) * sd.Nlam + ltC) * Nrays + muC) : 0.0;
-                    Vij = sd.c0 * phi;
+                    Vij = phi;  // the table holds hc/4pi*Bij*phi (rh_method.py:279), folded in at upload
                     Vji = sd.c2 * Vij;
                     Uji = sd.c1 * Vji;
                 } else {
@@ -312,7 +314,7 @@ __global__ void __launch_bounds__(128) fs_gamma_kernel(const FsParams p)
                         if (sd.isLine) {
                             const double phi =
                                 act ? __ldg(cc + sd.tabOff + ((size_t)(d * N + k) * sd.Nlam + ltC) * Nrays + muC) : 0.0;
-                            Vij = sd.c0 * phi;
+                            Vij = phi;  // the table holds hc/4pi*Bij*phi (rh_method.py:279), folded in at upload
                             Vji = sd.c2 * Vij;
                             Uji = sd.c1 * Vji;
                             wla = act ? __ldg(cc + sd.wlaOff + (size_t)k * sd.Nlam + ltC) : 0.0;
@@ -478,8 +480,7 @@ __global__ void uv_hook_kernel(const FsParams p, int col, SlotDesc sd, int la, i
     const int lt = la - sd.Nblue;
     double vij, vji, uji;
     if (sd.isLine) {
-        const double phi = cc[sd.tabOff + ((size_t)(d * p.N + k) * sd.Nlam + lt) * p.Nrays + mu];
-        vij = sd.c0 * phi;
+        vij = cc[sd.tabOff + ((size_t)(d * p.N + k) * sd.Nlam + lt) * p.Nrays + mu];  // hc/4pi*Bij*phi
         vji = sd.c2 * vij;
         uji = sd.c1 * vji;
     } else {
@@ -500,6 +501,7 @@ struct TransposeJob {
     int32_t R, C;            // src is [R][C], dst is [C][R]
     int32_t tile0;           // first 32x32 tile of this job in the flat tile list
     int32_t tilesC;          // tiles along C
+    double scale;            // dst = scale * src (1.0, or hc/4pi*Bij for a line's phi -> Vij table)
 };
 
 __global__ void pack_transpose_kernel(const TransposeJob *jobs, int njobs, const double *staging, int64_t hpStride,
@@ -528,7 +530,7 @@ __global__ void pack_transpose_kernel(const TransposeJob *jobs, int njobs, const
     __syncthreads();
     for (int q = ty; q < 32; q += 8) {
         const int c = tc * 32 + q, r = tr * 32 + tx;
-        if (r < jb.R && c < jb.C) dst[(size_t)c * jb.R + r] = tile[tx][q];
+        if (r < jb.R && c < jb.C) dst[(size_t)c * jb.R + r] = jb.scale * tile[tx][q];
     }
 }
 

@@ -25,9 +25,11 @@ struct SlotDesc {
     int32_t atom;
     int32_t lsI, lsJ;    // level-slot of the lower / upper level inside the tile
     int32_t toff;        // offset of this transition in the per-wavelength tables (alpha, twohc, wlacont)
-    int64_t tabOff;      // colconst offset: lines phi[2][N][Nlam][Nrays]; continua gij[N][Nlam]
+    int32_t flags;       // bit 0 / 1: this slot is the first of its tile to touch level-slot lsI / lsJ
+    int32_t pad;
+    int64_t tabOff;      // colconst offset: lines Vij[2][N][Nlam][Nrays] (= hc/4pi*Bij*phi); continua gij[N][Nlam]
     int64_t wlaOff;      // colconst offset: lines wla[N][Nlam] = wlambda*wphi/HC   (rh_method.py:451)
-    double c0, c1, c2;   // lines: hc/4pi*Bij, Aji/Bji, Bji/Bij  (rh_method.py:279-281,450)
+    double c0, c1, c2;   // lines: hc/4pi*Bij (folded into the Vij table at upload), Aji/Bji, Bji/Bij  (rh_method.py:279-281,450)
 };
 
 struct TileDesc {
@@ -54,6 +56,8 @@ struct FsParams {
     // model tables (device)
     const TileDesc *tiles;
     const SlotDesc *slots;
+    const int32_t *classTiles;  // tile indices handled by this launch (tiles are grouped by slot count)
+    int32_t nClassTiles;
     const double *alpha, *twohc, *wlacont;  // concatenated per-wavelength tables
     const double *zmu, *hw;                 // [Nrays]: 1/muz, 0.5*wmu
     // batch buffers (device)
