@@ -91,6 +91,10 @@ struct mali_model {
     std::vector<SlotDesc> transSlot;  // one descriptor per transition (for the uv hook)
     std::vector<int32_t> classTiles[3];  // tiles with <= 4, 5..8, > 8 transitions
     int32_t *d_classTiles[3] = {nullptr, nullptr, nullptr};
+    std::vector<TileC<4>> tiles4;        // constant-bank descriptors of the class-0 / class-1 tiles
+    std::vector<TileC<8>> tiles8;
+    int64_t off_zero = 0;
+    int smemPopDoubles = 0, smemZOff = 0, smemLvlOff = 0, smemMbarOff = 0, smemBytesPerWarp = 0, useBulk = 0;
     mali_layout lay{};
     int64_t off_z = 0, off_bbc = 0, off_bgchi = 0, off_bgeta = 0, off_bgsca = 0, off_C = 0, off_nTotal = 0;
     int64_t off_jpart = 0, off_part = 0;
@@ -115,15 +119,79 @@ struct mali_model {
     mutable long long launches = 0;  // kernels launched through this model since creation
 };
 
-template <int TMAX>
-static void launch_fs_class(const FsParams &p, int natom, unsigned grid, int threads, size_t smem, cudaStream_t st)
+static FsCommon make_fs_common(const mali_model *m, const mali_buffers *b, int col0, int ncol, int wpb)
 {
-    if (natom == 1)
-        fs_gamma_kernel_t<TMAX, 1><<<grid, threads, smem, st>>>(p);
-    else if (natom == 2)
-        fs_gamma_kernel_t<TMAX, 2><<<grid, threads, smem, st>>>(p);
-    else
-        fs_gamma_kernel_t<TMAX, 4><<<grid, threads, smem, st>>>(p);
+    FsCommon c{};
+    c.N = m->N;
+    c.Nrays = m->Nrays;
+    c.Nspect = m->Nspect;
+    c.Lw = m->Lw;
+    c.col0 = col0;
+    c.ncol = ncol;
+    c.warpsPerBlock = wpb;
+    c.useBulk = m->useBulk;
+    c.smemBytesPerWarp = m->smemBytesPerWarp;
+    c.popDoubles = m->smemPopDoubles;
+    c.zOffDoubles = m->smemZOff;
+    c.lvlOffDoubles = m->smemLvlOff;
+    c.mbarOffBytes = m->smemMbarOff;
+    c.colStride = m->lay.colconst;
+    c.popStride = m->lay.pops;
+    c.JStride = m->lay.J;
+    c.IStride = m->lay.I;
+    c.scratchStride = m->lay.scratch;
+    c.off_z = m->off_z;
+    c.off_bbc = m->off_bbc;
+    c.off_bgchi = m->off_bgchi;
+    c.off_bgeta = m->off_bgeta;
+    c.off_bgsca = m->off_bgsca;
+    c.off_zero = m->off_zero;
+    c.off_jpart = m->off_jpart;
+    c.off_part = m->off_part;
+    c.alpha = m->d_alpha;
+    c.twohc = m->d_twohc;
+    c.wlacont = m->d_wlacont;
+    c.zmu = m->d_zmu;
+    c.hw = m->d_hw;
+    c.colconst = b->colconst;
+    c.pops = b->pops;
+    c.J = b->J;
+    c.I = b->I;
+    c.scratch = b->scratch;
+    c.dJbits = reinterpret_cast<unsigned long long *>(b->dJ);
+    c.done = b->done;
+    return c;
+}
+
+
+// Launches fs_gamma_kernel_c over one tile class, at most ClassParams<TMAX>::kMaxTiles tiles per launch
+// (the tile descriptors travel in the kernel parameters).
+template <int TMAX>
+static int launch_fs_class(const mali_model *m, const std::vector<TileC<TMAX>> &tiles, const FsCommon &c, int ncol,
+                           size_t smem, cudaStream_t st)
+{
+    using CP = ClassParams<TMAX>;
+    static thread_local CP *P = nullptr;  // 32 KB: keep it off the stack
+    if (!P) P = new CP();
+    void (*kern)(const CP) = m->Natom == 1 ? fs_gamma_kernel_c<TMAX, 1>
+                             : m->Natom == 2 ? fs_gamma_kernel_c<TMAX, 2> : fs_gamma_kernel_c<TMAX, 4>;
+    static thread_local const void *attr_done[3] = {nullptr, nullptr, nullptr};
+    const int ai = m->Natom == 1 ? 0 : (m->Natom == 2 ? 1 : 2);
+    if (smem > 48 * 1024 && attr_done[ai] != (const void *)kern) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        attr_done[ai] = (const void *)kern;
+    }
+    P->c = c;
+    const int nt = (int)tiles.size();
+    for (int t0 = 0; t0 < nt; t0 += CP::kMaxTiles) {
+        const int n = std::min(CP::kMaxTiles, nt - t0);
+        memcpy(P->tiles, tiles.data() + t0, sizeof(TileC<TMAX>) * n);
+        dim3 grid(n, (ncol + c.warpsPerBlock - 1) / c.warpsPerBlock);
+        kern<<<grid, 32 * c.warpsPerBlock, smem, st>>>(*P);
+        m->launches += 1;
+    }
+    return 0;
 }
 
 extern "C" {
@@ -219,6 +287,7 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
     m->off_bgsca = take((int64_t)N * d->Nspect);
     m->off_C = take((int64_t)m->sumNlevel2 * N);
     m->off_nTotal = take((int64_t)d->Natom * N);
+    m->off_zero = take(16);  // zeros: lanes on which a transition is inactive read here with stride 0
     std::vector<int64_t> tabOff(d->Ntrans), wlaOff(d->Ntrans, 0);
     for (int t = 0; t < d->Ntrans; ++t) {
         const int32_t *tr = &m->trans[(size_t)t * 6];
@@ -321,10 +390,52 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
         delete m;
         return fail(MALI_ELIMIT, "tile touches %d levels / column block of %lld doubles: beyond the 32-bit offsets of the kernel", m->Dmax, (long long)L.colconst);
     }
+    auto slotc = [&](const SlotDesc &sd) {
+        SlotC c{};
+        c.kind = (sd.isLine ? 1 : 0) | ((sd.flags & 1) ? 2 : 0) | ((sd.flags & 2) ? 4 : 0);
+        c.Nblue = sd.Nblue;
+        c.Nlam = sd.Nlam;
+        c.tabOff = (int32_t)sd.tabOff;
+        c.wlaOff = (int32_t)sd.wlaOff;
+        c.toff = sd.toff;
+        c.rowIN = sd.rowI * N;
+        c.rowJN = sd.rowJ * N;
+        c.lvI = sd.lsI * 32;
+        c.lvJ = sd.lsJ * 32;
+        c.atom = sd.atom;
+        c.cA = sd.c2;
+        c.cB = sd.c1;
+        return c;
+    };
     for (int ti = 0; ti < m->ntile; ++ti) {
-        const int T = m->tiles[ti].nslot;
+        const TileDesc &td = m->tiles[ti];
+        const int T = td.nslot;
         const int cls = (d->Natom > 4 || T > 8) ? 2 : (T > 4 ? 1 : 0);
         m->classTiles[cls].push_back(ti);
+        if (cls == 0) {
+            TileC<4> t{};
+            t.la0 = td.la0;
+            t.nslot = T;
+            t.partRow0 = td.partRow0;
+            for (int q = 0; q < T; ++q) t.s[q] = slotc(m->slots[td.slot0 + q]);
+            m->tiles4.push_back(t);
+        } else if (cls == 1) {
+            TileC<8> t{};
+            t.la0 = td.la0;
+            t.nslot = T;
+            t.partRow0 = td.partRow0;
+            for (int q = 0; q < T; ++q) t.s[q] = slotc(m->slots[td.slot0 + q]);
+            m->tiles8.push_back(t);
+        }
+    }
+    {   // per-warp shared memory of fs_gamma_kernel_c: populations | heights | level array | mbarrier
+        auto even = [](int x) { return (x + 1) & ~1; };
+        m->smemPopDoubles = m->sumNlevel * N;
+        m->smemZOff = even(m->smemPopDoubles);
+        m->smemLvlOff = m->smemZOff + even(N);
+        m->smemMbarOff = (m->smemLvlOff + std::max(m->Dmax, 1) * 64) * 8;
+        m->smemBytesPerWarp = (int)align_up(m->smemMbarOff + 16, 16);
+        m->useBulk = (N % 2 == 0 && m->smemPopDoubles % 2 == 0) ? 1 : 0;  // cp.async.bulk: 16-byte sizes / addresses
     }
     std::vector<int32_t> trPartOff(d->Ntrans + 1, 0), trPartRows;
     for (int t = 0; t < d->Ntrans; ++t) {
@@ -463,7 +574,7 @@ int mali_upload_columns(const mali_model *m, const mali_buffers *b, int32_t col0
         dim3 grid(32, ncol);
         pack_misc_kernel<<<grid, 256, 0, st>>>(m->d_cjobs, (int)m->cjobs.size(), m->d_wjobs, (int)m->wjobs.size(),
                                                m->d_wlambda, m->N, staging_dev, L.hostpack, b->colconst, L.colconst,
-                                               b->pops, L.pops, b->J, L.J, col0);
+                                               b->pops, L.pops, b->J, L.J, col0, m->off_zero);
     }
     CU(cudaGetLastError());
     return MALI_OK;
@@ -549,35 +660,38 @@ static FinishParams make_finish_params(const mali_model *m, const mali_buffers *
 
 static int launch_fs(const mali_model *m, const mali_buffers *b, int col0, int ncol, cudaStream_t st)
 {
-    // Few (column, tile) pairs: one warp per block so that the tiles spread over all 148 SMs; otherwise 4.
+    // Few (column, tile) pairs: one warp per block so that the work spreads over all 148 SMs; otherwise 4.
     const int wpb = ((int64_t)ncol * m->ntile >= 148 * 16) ? 4 : 1;
-    FsParams p = make_fs_params(m, b, col0, ncol, wpb);
-    const size_t smem = (size_t)p.smemPerWarp * wpb * sizeof(double);
-    if (smem > 227 * 1024) return fail(MALI_ELIMIT, "tile needs %zu B of shared memory", smem);
-    static bool attr_set = false;
-    if (smem > 48 * 1024 && !attr_set) {
-        CU(cudaFuncSetAttribute(fs_gamma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
-    }
-    col_zero_bits_kernel<<<(ncol + 127) / 128, 128, 0, st>>>(p.dJbits, b->done, nullptr, 0, col0, ncol);
+    col_zero_bits_kernel<<<(ncol + 127) / 128, 128, 0, st>>>(reinterpret_cast<unsigned long long *>(b->dJ), b->done,
+                                                           nullptr, 0, col0, ncol);
     m->launches += 1;
     const bool rec = m->profOn && m->profUsed + 2 <= (int)m->profEvents.size();
     if (rec) cudaEventRecord(m->profEvents[m->profUsed], st);
     // heaviest class first so that the light tiles fill the tail
-    for (int cls = 2; cls >= 0; --cls) {
-        const int nt = (int)m->classTiles[cls].size();
-        if (nt == 0) continue;
-        p.classTiles = m->d_classTiles[cls];
+    if (!m->classTiles[2].empty()) {  // generic kernel: any number of transitions per tile / atoms
+        FsParams p = make_fs_params(m, b, col0, ncol, wpb);
+        const size_t smem = (size_t)p.smemPerWarp * wpb * sizeof(double);
+        if (smem > 227 * 1024) return fail(MALI_ELIMIT, "tile needs %zu B of shared memory", smem);
+        static bool attr_set = false;
+        if (smem > 48 * 1024 && !attr_set) {
+            CU(cudaFuncSetAttribute(fs_gamma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            attr_set = true;
+        }
+        const int nt = (int)m->classTiles[2].size();
+        p.classTiles = m->d_classTiles[2];
         p.nClassTiles = nt;
         p.blocksPerCol = (nt + wpb - 1) / wpb;
-        const unsigned grid = (unsigned)(p.blocksPerCol * ncol);
-        if (cls == 2)
-            fs_gamma_kernel<<<grid, 32 * wpb, smem, st>>>(p);
-        else if (cls == 1)
-            launch_fs_class<8>(p, m->Natom, grid, 32 * wpb, smem, st);
-        else
-            launch_fs_class<4>(p, m->Natom, grid, 32 * wpb, smem, st);
+        fs_gamma_kernel<<<(unsigned)(p.blocksPerCol * ncol), 32 * wpb, smem, st>>>(p);
         m->launches += 1;
+    }
+    {
+        const FsCommon c = make_fs_common(m, b, col0, ncol, wpb);
+        const size_t smem = (size_t)m->smemBytesPerWarp * wpb;
+        if (smem > 227 * 1024) return fail(MALI_ELIMIT, "column needs %zu B of shared memory per block", smem);
+        if (!m->tiles8.empty())
+            if (int e = launch_fs_class<8>(m, m->tiles8, c, ncol, smem, st)) return fail(e, "fs_gamma_kernel_c<8>: %s", cudaGetErrorString((cudaError_t)e));
+        if (!m->tiles4.empty())
+            if (int e = launch_fs_class<4>(m, m->tiles4, c, ncol, smem, st)) return fail(e, "fs_gamma_kernel_c<4>: %s", cudaGetErrorString((cudaError_t)e));
     }
     if (rec) {
         cudaEventRecord(m->profEvents[m->profUsed + 1], st);

@@ -548,7 +548,7 @@ struct WlaJob {
 __global__ void pack_misc_kernel(const CopyJob *copies, int ncopies, const WlaJob *wlas, int nwla,
                                  const double *wlambda, int N, const double *staging, int64_t hpStride,
                                  double *colconst, int64_t colStride, double *pops, int64_t popStride, double *J,
-                                 int64_t JStride, int col0)
+                                 int64_t JStride, int col0, int64_t offZero)
 {
     const int col = col0 + blockIdx.y;
     const double *src = staging + (size_t)blockIdx.y * hpStride;
@@ -570,6 +570,7 @@ __global__ void pack_misc_kernel(const CopyJob *copies, int ncopies, const WlaJo
     }
     double *Jc = J + (size_t)col * JStride;
     for (int64_t q = tid; q < JStride; q += nth) Jc[q] = 0.0;
+    if (tid < 16) cc[offZero + tid] = 0.0;
 }
 
 }  // namespace mali
