@@ -1,0 +1,298 @@
+"""Drop-in for the MALI hot path of Lightspinner's rh_method.py, running on a B200 through libmali_b200.so.
+
+    from lightspinner_b200 import Context          # instead of: from rh_method import Context
+    ctx = Context(atmos, spect, eqPops, background)   # same objects the reference builds (test.py:8-18)
+    dJ = ctx.formal_sol_gamma_matrices()              # rh_method.py:565-708
+    dPops = ctx.stat_equil()                          # rh_method.py:710-745
+    ctx.I, ctx.J, ctx.activeAtoms[0].n, .Gamma        # same names, shapes and aliasing as the reference
+
+Only the hot path moves to the GPU.  Everything in this file is the host-side mirror of the reference's per-Context
+SET-UP (ComputationalTransition / ComputationalAtom construction: line profiles, wavelength weights, collisional
+rates -- rh_method.py:93-131,198-243,366-423,474-487): it calls the same methods on the same model objects
+(`line.damping`, `atom.v_broad`, `collision.compute_rates`) with the reference's own numpy expressions, flattens the
+result (lightspinner_b200/tables.py) and uploads it once.  The iteration itself never touches the host except for
+the two scalars the reference's loop reads (dJ, dPops) and the population write-back that keeps
+`eqPops[name].pops is atom.n` true.
+"""
+from dataclasses import dataclass
+
+import numpy as np
+from scipy import special
+
+from . import tables
+from .engine import MaliEngine, piecewise_linear_1d_batch
+
+CLight = tables.CLight
+HC = tables.HC
+
+
+@dataclass
+class UV:
+    """Container for the [RH92]/[U01] Uji, Vij and Vji terms (rh_method.py:17-23)."""
+    Uji: np.ndarray
+    Vij: np.ndarray
+    Vji: np.ndarray
+
+
+def voigt_H(a, v):
+    """utils.py:13-15"""
+    return special.wofz(v + 1j * a).real
+
+
+def _is_line(trans):
+    # reference: isinstance(trans, AtomicLine); lines carry Einstein coefficients, continua a cross-section
+    return hasattr(trans, 'Aji') and hasattr(trans, 'lambda0')
+
+
+class ComputationalTransition:
+    """Host mirror of rh_method.ComputationalTransition (state + set-up only; `uv` evaluates on the GPU tables)."""
+
+    def __init__(self, trans, compAtom, atmos, spect):
+        self.transModel = trans
+        self.atom = compAtom
+        self.wavelength = trans.wavelength
+        self.isLine = _is_line(trans)
+        if self.isLine:
+            self.Aji = trans.Aji
+            self.Bji = trans.Bji
+            self.Bij = trans.Bij
+            self.lambda0 = trans.lambda0
+        else:
+            self.alpha = trans.alpha
+        self.i = trans.i
+        self.j = trans.j
+        self.Nblue = int(np.searchsorted(spect.wavelength, self.wavelength[0]))     # rh_method.py:122
+        self.compute_phi(atmos)
+        self.active = np.zeros(spect.wavelength.shape[0], bool)
+        for i, s in enumerate(spect.activeSet):                                     # rh_method.py:125-127
+            if trans in s:
+                self.active[i] = True
+        self.gij = None
+        self.Rij = np.zeros(atmos.Nspace)    # dead outputs of the reference (never zeroed, never read): not maintained
+        self.Rji = np.zeros(atmos.Nspace)
+        self.index = None                    # position in the flattened transition table
+
+    def lt(self, la):
+        return la - self.Nblue
+
+    def wlambda(self, la=None):
+        """rh_method.py:157-196"""
+        dopplerWidth = CLight / self.lambda0 if self.isLine else 1.0
+        wl = self.wavelength
+        if la is not None:
+            if la == 0:
+                return 0.5 * (wl[1] - wl[0]) * dopplerWidth
+            elif la == wl.shape[0] - 1:
+                return 0.5 * (wl[-1] - wl[-2]) * dopplerWidth
+            return 0.5 * (wl[la + 1] - wl[la - 1]) * dopplerWidth
+        wla = np.zeros_like(wl)
+        wla[0] = 0.5 * (wl[1] - wl[0])
+        wla[-1] = 0.5 * (wl[-1] - wl[-2])
+        wla[1:-1] = 0.5 * (wl[2:] - wl[:-2])
+        return dopplerWidth * wla
+
+    def compute_phi(self, atmos):
+        """rh_method.py:198-243 (set-up; next-row candidate for a device Voigt kernel)."""
+        if not self.isLine:
+            return
+        sqrtPi = np.sqrt(np.pi)
+        aDamp, Qelast = self.transModel.damping(atmos, self.atom.vBroad, self.atom.hPops.n[0])
+        Nlambda = self.wavelength.shape[0]
+        phi = np.zeros((Nlambda, atmos.Nrays, 2, atmos.Nspace))
+        wPhi = np.zeros(atmos.Nspace)
+        wLambda = self.wlambda()
+        vlosDop = np.zeros((atmos.Nrays, atmos.Nspace))
+        for mu in range(atmos.Nrays):
+            vlosDop[mu, :] = atmos.muz[mu] * atmos.vlos / self.atom.vBroad
+        for la in range(Nlambda):
+            v = (self.wavelength[la] - self.lambda0) * CLight / (self.atom.vBroad * self.lambda0)
+            for mu in range(atmos.Nrays):
+                wlamu = wLambda * 0.5 * atmos.wmu[mu]
+                for toFrom, sign in enumerate([-1.0, 1.0]):
+                    vk = v + sign * vlosDop[mu]
+                    phi[la, mu, toFrom, :] = voigt_H(aDamp, vk) / (sqrtPi * self.atom.vBroad)
+                    wPhi[:] += phi[la, mu, toFrom, :] * wlamu[la]
+        self.wphi = 1.0 / wPhi
+        self.phi = phi
+
+    def uv(self, la, mu, toFrom):
+        """rh_method.py:245-288, evaluated by the GPU from the packed tables (mali_uv)."""
+        U, Vij, Vji = self.atom.ctx._engine.uv(0, self.index, int(la), int(mu), bool(toFrom))
+        return UV(Uji=U, Vij=Vij, Vji=Vji)
+
+
+class ComputationalAtom:
+    """Host mirror of rh_method.ComputationalAtom: state and set-up (rh_method.py:366-423, 474-487)."""
+
+    def __init__(self, atom, atmos, spect, eqPops, ctx):
+        self.ctx = ctx
+        self.atomicModel = atom
+        self.atomicTable = getattr(eqPops, 'atomicTable', None)
+        self.spect = spect
+        self.atmos = atmos
+        self.vBroad = atom.v_broad(atmos)
+        self.pops = eqPops[atom.name]
+        self.hPops = eqPops['H']
+        self.nTotal = self.pops.nTotal
+        self.trans = []
+        for l in atom.lines:
+            if l in spect.transitions:
+                self.trans.append(ComputationalTransition(l, self, atmos, spect))
+        for c in atom.continua:
+            if c in spect.transitions:
+                self.trans.append(ComputationalTransition(c, self, atmos, spect))
+        Nlevel = len(atom.levels)
+        self.C = np.zeros((Nlevel, Nlevel, atmos.Nspace))
+        self.nStar = self.pops.nStar
+        if self.pops.pops is not None:          # rh_method.py:411-416: alias, not copy
+            self.n = self.pops.pops
+        else:
+            self.n = np.copy(self.nStar)
+            self.pops.pops = self.n
+        self.Nlevel = Nlevel
+        self.Ntrans = len(self.trans)
+        self.index = None
+
+    def compute_collisions(self):
+        """rh_method.py:474-487 (iteration-invariant: evaluated once per Context, uploaded with the column)."""
+        self.C = np.zeros((self.Nlevel, self.Nlevel, self.atmos.Nspace))
+        for col in self.atomicModel.collisions:
+            col.compute_rates(self.atmos, self.nStar, self.C)
+        self.C[self.C < 0.0] = 0.0
+
+    @property
+    def Gamma(self):
+        return self.ctx._atom_Gamma(self.index)
+
+
+class Context:
+    """Drop-in for rh_method.Context (rh_method.py:490-745) -- one column on one GPU.
+
+    Batches of columns (response functions, 1.5D runs) go through lightspinner_b200.BatchContext / MaliEngine,
+    which run the same kernels over many columns per launch.
+    """
+
+    def __init__(self, atmos, spect, eqPops, background, device=None, _host_only=False):
+        self.atmos = atmos
+        self.atmos.nondimensionalise()                                    # rh_method.py:553
+        self.spect = spect
+        self.background = background
+        self.eqPops = eqPops
+        self.activeAtoms = []
+        for a in spect.radSet.activeAtoms:                                # rh_method.py:558-560
+            self.activeAtoms.append(ComputationalAtom(a, atmos, spect, eqPops, self))
+        self._problem = flatten_context(self)
+        self._cache = {}
+        self._engine = None
+        if _host_only:      # unit tests of the host-side flattening only; every compute method then fails
+            return
+        self._engine = MaliEngine(self._problem, 1, device=device)
+        self._engine.upload([self._problem])
+
+    # -- lazily fetched results (numpy, C order, the reference's shapes)
+    def _get(self, key, fn):
+        if key not in self._cache:
+            self._cache[key] = fn()
+        return self._cache[key]
+
+    @property
+    def J(self):
+        return self._get('J', lambda: self._engine.J(0))
+
+    @property
+    def I(self):
+        return self._get('I', lambda: self._engine.I(0))
+
+    def _atom_Gamma(self, a):
+        return self._get(('G', a), lambda: self._engine.atom_Gamma(0, a))
+
+    def _push_pops(self):
+        # the reference reads atom.n afresh on every call: honour edits made through the eqPops alias
+        self._engine.set_n(0, np.concatenate([a.n for a in self.activeAtoms], axis=0))
+
+    def formal_sol_gamma_matrices(self):
+        """rh_method.py:565-708.  Returns dJ = max |1 - JDag/J| as a float."""
+        self._push_pops()
+        self._cache = {}
+        return float(self._engine.formal_sol_gamma_matrices()[0])
+
+    def stat_equil(self):
+        """rh_method.py:710-745.  Updates every atom.n IN PLACE; raises numpy.linalg.LinAlgError if singular."""
+        dPops = float(self._engine.stat_equil()[0])
+        n = self._engine.n(0)
+        mt = self._engine.mt
+        for ia, atom in enumerate(self.activeAtoms):
+            atom.n[...] = n[mt.lvloff[ia]:mt.lvloff[ia + 1]]
+        return dPops
+
+    def close(self):
+        if self._engine is not None:
+            self._engine.close()
+
+
+def flatten_context(ctx):
+    """Reference-layout problem dict (lightspinner_b200/tables.py) from the host mirrors of a Context."""
+    atmos, spect, bg = ctx.atmos, ctx.spect, ctx.background
+    N = atmos.Nspace
+    Nlevel, trans, linepar, alpha, phi, phioff, wphi = [], [], [], [], [], [], []
+    nStar, nTotal, Cs, ns = [], [], [], []
+    off = 0
+    it = 0
+    for ia, atom in enumerate(ctx.activeAtoms):
+        atom.index = ia
+        atom.compute_collisions()
+        Nlevel.append(atom.Nlevel)
+        nStar.append(np.asarray(atom.nStar, dtype=np.float64))
+        nTotal.append(np.asarray(atom.nTotal, dtype=np.float64))
+        Cs.append(atom.C.reshape(atom.Nlevel * atom.Nlevel, N))
+        ns.append(np.asarray(atom.n, dtype=np.float64))
+        for t in atom.trans:
+            t.index = it
+            it += 1
+            Nlam = int(t.wavelength.shape[0])
+            if not np.array_equal(t.wavelength, spect.wavelength[t.Nblue:t.Nblue + Nlam]):
+                raise ValueError('transition wavelength grid is not a slice of the global grid')
+            act = np.zeros(spect.wavelength.shape[0], bool)
+            act[t.Nblue:t.Nblue + Nlam] = True
+            if not np.array_equal(act, t.active):
+                raise ValueError('transition is not active on a contiguous wavelength range')
+            trans.append([ia, t.i, t.j, int(t.isLine), t.Nblue, Nlam])
+            if t.isLine:
+                linepar.append([t.Aji, t.Bji, t.Bij, t.lambda0])
+                alpha.append(np.zeros(Nlam))
+                phioff.append(off)
+                phi.append(np.ascontiguousarray(t.phi).ravel())
+                off += t.phi.size
+                wphi.append(np.asarray(t.wphi, dtype=np.float64))
+            else:
+                linepar.append([0.0, 0.0, 0.0, 0.0])
+                alpha.append(np.asarray(t.alpha, dtype=np.float64))
+                phioff.append(0)
+                wphi.append(np.zeros(N))
+    return dict(
+        Nspace=N, Nrays=atmos.Nrays, Nspect=int(spect.wavelength.shape[0]),
+        wavelength=np.asarray(spect.wavelength, dtype=np.float64), muz=np.asarray(atmos.muz, dtype=np.float64),
+        wmu=np.asarray(atmos.wmu, dtype=np.float64), Nlevel=np.array(Nlevel, dtype=np.int32),
+        trans=np.array(trans, dtype=np.int32).reshape(-1, 6), linepar=np.array(linepar).reshape(-1, 4),
+        alpha=np.concatenate(alpha) if alpha else np.zeros(0),
+        height=np.asarray(atmos.height, dtype=np.float64), temperature=np.asarray(atmos.temperature, dtype=np.float64),
+        bg_chi=np.asarray(bg.chi), bg_eta=np.asarray(bg.eta), bg_sca=np.asarray(bg.sca),
+        nStar=np.concatenate(nStar, axis=0), nTotal=np.stack(nTotal), C=np.concatenate(Cs, axis=0),
+        n=np.concatenate(ns, axis=0), phi=np.concatenate(phi) if phi else np.zeros(0),
+        phioff=np.array(phioff, dtype=np.int64), wphi=np.stack(wphi) if wphi else np.zeros((0, N)))
+
+
+@dataclass
+class IPsi:
+    """formal_solver.py:6-12"""
+    I: np.ndarray
+    PsiStar: np.ndarray
+
+
+def piecewise_linear_1d(atmos, mu, toFrom, wav, chi, S):
+    """formal_solver.piecewise_linear_1d (formal_solver.py:144-212) on the GPU: same signature, same result bits."""
+    bbc = tables.planck_bc(np.array([wav], dtype=np.float64), np.asarray(atmos.temperature, dtype=np.float64))
+    I, Psi = piecewise_linear_1d_batch(np.asarray(atmos.height, dtype=np.float64), [atmos.muz[mu]], [int(bool(toFrom))],
+                                       [bbc[0, 0]], [bbc[0, 1]], np.asarray(chi, dtype=np.float64)[None, :],
+                                       np.asarray(S, dtype=np.float64)[None, :])
+    return IPsi(I[0], Psi[0])

@@ -90,8 +90,15 @@ __device__ __forceinline__ double reduce_scatter(double (&v)[8], int lane)
     return v[0];
 }
 
+#ifndef MALI_MINB4
+#define MALI_MINB4 3
+#endif
+#ifndef MALI_MINB8
+#define MALI_MINB8 2
+#endif
+
 template <int TMAX, int NA>
-__global__ void __launch_bounds__(128) fs_gamma_kernel_c(const __grid_constant__ ClassParams<TMAX> P)
+__global__ void __launch_bounds__(128, (TMAX <= 4) ? MALI_MINB4 : MALI_MINB8) fs_gamma_kernel_c(const __grid_constant__ ClassParams<TMAX> P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const FsCommon &p = P.c;
@@ -359,7 +366,15 @@ __global__ void __launch_bounds__(128) fs_gamma_kernel_c(const __grid_constant__
             {
                 const double x = valid ? hw * Ik : 0.0;
                 double sum = x;
-                for (int m = 1; m < Nrays; ++m) sum += __shfl_down_sync(0xffffffffu, x, m);
+                if (Nrays == 5) {  // the reference's quadrature(5): fully unrolled
+#pragma unroll
+                    for (int m = 1; m < 5; ++m) sum += __shfl_down_sync(0xffffffffu, x, m);
+                } else if (Nrays == 3) {
+#pragma unroll
+                    for (int m = 1; m < 3; ++m) sum += __shfl_down_sync(0xffffffffu, x, m);
+                } else {
+                    for (int m = 1; m < Nrays; ++m) sum += __shfl_down_sync(0xffffffffu, x, m);
+                }
                 if (leader) {
                     if (d == 0) {
                         __stcg(Jpart + klc, sum);

@@ -9,6 +9,7 @@ def problem_from_reference_context(ctx, copy_pops=True):
     N = atmos.Nspace
     Nlevel, trans, linepar, alpha, phi, phioff, wphi = [], [], [], [], [], [], []
     nStar, nTotal, Cs, ns = [], [], [], []
+    aDamp, vBroad = [], []
     off = 0
     for ia, atom in enumerate(ctx.activeAtoms):
         Nlevel.append(atom.Nlevel)
@@ -17,6 +18,7 @@ def problem_from_reference_context(ctx, copy_pops=True):
         nTotal.append(np.array(atom.nTotal))
         Cs.append(np.array(atom.C).reshape(atom.Nlevel * atom.Nlevel, N))
         ns.append(np.array(atom.n, copy=copy_pops))
+        vBroad.append(np.array(atom.vBroad))
         for t in atom.trans:
             Nlam = t.wavelength.shape[0]
             assert np.array_equal(t.wavelength, spect.wavelength[t.Nblue:t.Nblue + Nlam])
@@ -31,7 +33,9 @@ def problem_from_reference_context(ctx, copy_pops=True):
                 phi.append(np.ascontiguousarray(t.phi).ravel())
                 off += t.phi.size
                 wphi.append(np.array(t.wphi))
+                aDamp.append(np.array(t.transModel.damping(atmos, atom.vBroad, atom.hPops.n[0])[0]))
             else:
+                aDamp.append(np.zeros(N))
                 linepar.append([0.0, 0.0, 0.0, 0.0])
                 alpha.append(np.array(t.alpha, dtype=np.float64))
                 phioff.append(0)
@@ -43,7 +47,8 @@ def problem_from_reference_context(ctx, copy_pops=True):
         Nlevel=np.array(Nlevel, dtype=np.int32), trans=np.array(trans, dtype=np.int32),
         linepar=np.array(linepar), alpha=np.concatenate(alpha),
         height=np.array(atmos.height), temperature=np.array(atmos.temperature),
-        vlos=np.array(atmos.vlos),
+        vlos=np.array(atmos.vlos), vturb=np.array(atmos.vturb), aDamp=np.stack(aDamp), vBroad=np.stack(vBroad),
+        hGround=np.array(ctx.activeAtoms[0].hPops.n[0]),
         bg_chi=np.array(bg.chi), bg_eta=np.array(bg.eta), bg_sca=np.array(bg.sca),
         nStar=np.concatenate(nStar, axis=0), nTotal=np.stack(nTotal), C=np.concatenate(Cs, axis=0),
         n=np.concatenate(ns, axis=0),

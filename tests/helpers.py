@@ -31,3 +31,134 @@ def relerr(a, b):
     if (~nz).any():
         e = max(e, float(np.max(np.abs(a[~nz]))))
     return e
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Fixture-backed stand-ins for the reference's model objects (atmosphere, atoms, transitions, populations), so that
+# the drop-in lightspinner_b200.Context can be driven exactly like rh_method.Context on a box that has no reference.
+class _FakeAtmos:
+    def __init__(self, p):
+        self.height = np.array(p['height'])
+        self.temperature = np.array(p['temperature'])
+        self.vlos = np.array(p['vlos'])
+        self.vturb = np.array(p['vturb'])
+        self.muz = np.array(p['muz'])
+        self.wmu = np.array(p['wmu'])
+        self.dimensioned = True
+
+    @property
+    def Nspace(self):
+        return self.height.shape[0]
+
+    @property
+    def Nrays(self):
+        return self.muz.shape[0]
+
+    def nondimensionalise(self):
+        self.dimensioned = False
+
+    def dimensionalise(self):
+        self.dimensioned = True
+
+
+class _FakeLine:
+    def __init__(self, i, j, par, wavelength, aDamp):
+        self.i, self.j = int(i), int(j)
+        self.Aji, self.Bji, self.Bij, self.lambda0 = (np.float64(v) for v in par)
+        self.wavelength = wavelength
+        self._aDamp = aDamp
+
+    def damping(self, atmos, vBroad, hGround):
+        return self._aDamp, None
+
+
+class _FakeContinuum:
+    def __init__(self, i, j, alpha, wavelength):
+        self.i, self.j = int(i), int(j)
+        self.alpha = alpha
+        self.wavelength = wavelength
+
+
+class _FakeCollisions:
+    def __init__(self, C):
+        self._C = C
+
+    def compute_rates(self, atmos, nStar, C):
+        C += self._C
+
+
+class _FakeAtom:
+    def __init__(self, name, Nlevel, vBroad, C):
+        self.name = name
+        self.levels = [None] * int(Nlevel)
+        self.lines, self.continua = [], []
+        self.collisions = [_FakeCollisions(C)]
+        self._vBroad = vBroad
+
+    def v_broad(self, atmos):
+        return self._vBroad
+
+
+class _FakeState:
+    def __init__(self, nStar, nTotal, pops=None):
+        self.nStar, self.nTotal, self.pops = nStar, nTotal, pops
+
+    @property
+    def n(self):
+        return self.pops if self.pops is not None else self.nStar
+
+
+class _FakePops(dict):
+    atomicTable = None
+
+    def __getitem__(self, name):
+        return dict.__getitem__(self, name.upper().strip())
+
+
+class _NS:
+    pass
+
+
+def fake_reference_objects(p):
+    """(atmos, spect, eqPops, background) built from a fixture problem dict: duck-typed like the reference's."""
+    N = int(p['Nspace'])
+    atmos = _FakeAtmos(p)
+    names = [str(s).strip() for s in p['atom_names']]
+    lvloff = np.concatenate([[0], np.cumsum(p['Nlevel'])]).astype(int)
+    g2off = np.concatenate([[0], np.cumsum(np.asarray(p['Nlevel'], dtype=int) ** 2)]).astype(int)
+    toff = np.concatenate([[0], np.cumsum(p['trans'][:, 5])]).astype(int)
+    atoms = []
+    for a, nm in enumerate(names):
+        NL = int(p['Nlevel'][a])
+        C = np.array(p['C'][g2off[a]:g2off[a + 1]]).reshape(NL, NL, N)
+        atoms.append(_FakeAtom(nm, NL, np.array(p['vBroad'][a]), C))
+    transitions = []
+    wavelength = np.array(p['wavelength'])
+    for t, (atom, i, j, isLine, Nblue, Nlam) in enumerate(p['trans']):
+        wl = np.copy(wavelength[Nblue:Nblue + Nlam])
+        if isLine:
+            tr = _FakeLine(i, j, p['linepar'][t], wl, np.array(p['aDamp'][t]))
+            atoms[atom].lines.append(tr)
+        else:
+            tr = _FakeContinuum(i, j, np.array(p['alpha'][toff[t]:toff[t + 1]]), wl)
+            atoms[atom].continua.append(tr)
+        tr._range = (int(Nblue), int(Nblue + Nlam))
+        transitions.append(tr)
+    spect = _NS()
+    spect.wavelength = wavelength
+    spect.transitions = transitions
+    spect.activeSet = [[tr for tr in transitions if tr._range[0] <= la < tr._range[1]] for la in range(len(wavelength))]
+    spect.radSet = _NS()
+    spect.radSet.activeAtoms = atoms
+    eqPops = _FakePops()
+    for a, nm in enumerate(names):
+        nStar = np.array(p['nStar'][lvloff[a]:lvloff[a + 1]])
+        n0 = np.array(p['n'][lvloff[a]:lvloff[a + 1]])
+        eqPops[nm] = _FakeState(nStar, np.array(p['nTotal'][a]), None if np.array_equal(n0, nStar) else n0)
+    if 'H' not in eqPops:
+        hn = np.zeros((1, N))
+        hn[0] = p['hGround']
+        eqPops['H'] = _FakeState(hn, hn[0].copy(), None)
+    bg = _NS()
+    bg.chi, bg.eta, bg.sca = np.array(p['bg_chi']), np.array(p['bg_eta']), np.array(p['bg_sca'])
+    return atmos, spect, eqPops, bg

@@ -270,3 +270,66 @@ def test_device_loop_matches_host_loop(eng_mod):
         assert relerr(eng.I(c), r['final_I']) < TOL_FINAL
         assert relerr(eng.n(c), r['final_n']) < TOL_FINAL
     eng.close()
+
+
+def test_dropin_context_runs_the_test_py_loop(eng_mod):
+    """The reference-facing API: lightspinner_b200.Context(atmos, spect, eqPops, background) driven by the loop of
+    test.py:20-29, with fixture-backed stand-ins for the reference's objects.  Same iteration count, same results,
+    and the eqPops alias sees the converged populations (response_fn.py:62 reads them that way)."""
+    from helpers import fake_reference_objects
+    from lightspinner_b200 import Context
+    p, r = load_golden('c1_falc_ca')
+    atmos, spect, eqPops, bg = fake_reference_objects(p)
+    ctx = Context(atmos, spect, eqPops, bg)
+    dJ, dPops, i = 1.0, 1.0, 0
+    while dJ > 2e-3 or dPops > 1e-3:
+        i += 1
+        dJ = ctx.formal_sol_gamma_matrices()
+        if i > 3:
+            dPops = ctx.stat_equil()
+        assert isinstance(dJ, float) and isinstance(dPops, float)
+    assert i == 46
+    assert ctx.I.shape == r['final_I'].shape and ctx.J.shape == r['final_J'].shape
+    assert relerr(ctx.I, r['final_I']) < TOL_FINAL and relerr(ctx.J, r['final_J']) < TOL_FINAL
+    assert eqPops['CA'].pops is ctx.activeAtoms[0].n
+    assert relerr(eqPops['CA'].n, r['final_n']) < TOL_FINAL
+    G = ctx.activeAtoms[0].Gamma
+    assert G.shape == (6, 6, 82) and np.all(np.abs(G.sum(axis=0)) <= 1e-9 * np.abs(G).max(axis=0))   # columns sum to 0
+    # uv and the formal-solver drop-ins
+    t = ctx.activeAtoms[0].trans[0]
+    uv = t.uv(t.Nblue + 3, 2, True)
+    assert uv.Vij.shape == (82,) and np.all(uv.Vji == (t.Bji / t.Bij) * uv.Vij)
+    ctx.close()
+
+
+def test_dropin_piecewise_linear_1d(eng_mod):
+    from lightspinner_b200 import piecewise_linear_1d
+    u = load_units()
+
+    class A:
+        pass
+    for i in range(int(u['fs_ncase'])):
+        g = lambda nm: u['fs%d_%s' % (i, nm)]
+        a = A()
+        a.height, a.temperature, a.muz, a.Nspace = g('z'), g('T'), np.array([float(g('mu'))]), len(g('z'))
+        out = piecewise_linear_1d(a, 0, bool(g('toFrom')), float(g('wav')), g('chi'), g('S'))
+        assert np.array_equal(out.I, g('I')) and np.array_equal(out.PsiStar, g('Psi')), i
+
+
+def test_warm_started_context_via_eqpops_alias(eng_mod):
+    """response_fn.py:33: eqPops['Ca'].pops = startingPops before constructing the Context."""
+    from helpers import fake_reference_objects
+    from lightspinner_b200 import Context
+    p, r = load_golden('rf_k40p')
+    atmos, spect, eqPops, bg = fake_reference_objects(p)
+    assert eqPops['CA'].pops is not None
+    ctx = Context(atmos, spect, eqPops, bg)
+    dJ, dPops, i = 1.0, 1.0, 0
+    while dJ > 2e-3 or dPops > 1e-3:
+        i += 1
+        dJ = ctx.formal_sol_gamma_matrices()
+        if i > 3:
+            dPops = ctx.stat_equil()
+    assert i == int(r['niter'])
+    assert relerr(ctx.I, r['final_I']) < TOL_FINAL
+    ctx.close()

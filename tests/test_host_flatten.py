@@ -1,0 +1,74 @@
+"""Host-side logic of the drop-in Context (no GPU): the mirror of the reference's per-Context set-up
+(line profiles rh_method.py:198-243, wavelength weights :157-196, collisions :474-487, activity ranges :122-127)
+and the flattening / host-pack layout must reproduce what the reference computed, bit for bit."""
+import numpy as np
+import pytest
+
+from helpers import fake_reference_objects, load_golden
+
+KEYS = ['wavelength', 'muz', 'wmu', 'Nlevel', 'trans', 'linepar', 'alpha', 'height', 'temperature', 'bg_chi', 'bg_eta',
+        'bg_sca', 'nStar', 'nTotal', 'C', 'n', 'phi', 'phioff', 'wphi']
+
+
+@pytest.mark.parametrize('name', ['c1_falc_ca', 'c2_falc_cah', 'c1v_jitter_ca3', 'rf_k40p'])
+def test_context_flattening_reproduces_reference_arrays(name):
+    """Drive lightspinner_b200.Context's host mirror with fixture-backed stand-ins of the reference objects."""
+    from lightspinner_b200.context import Context
+    p, r = load_golden(name)
+    atmos, spect, eqPops, bg = fake_reference_objects(p)
+    ctx = Context(atmos, spect, eqPops, bg, _host_only=True)
+    q = ctx._problem
+    for k in KEYS:
+        assert np.array_equal(np.asarray(q[k]), np.asarray(p[k])), (name, k)
+    # aliasing contract of rh_method.py:411-416
+    for atom in ctx.activeAtoms:
+        assert eqPops[atom.atomicModel.name].pops is atom.n
+    with pytest.raises(Exception):
+        ctx.formal_sol_gamma_matrices()      # no engine: the host-only object cannot compute (no CPU fallback)
+
+
+def test_model_tables_match_oracle_tables(oracle):
+    from lightspinner_b200 import tables
+    for name in ['c1_falc_ca', 'c2_falc_cah']:
+        p, r = load_golden(name)
+        mt = tables.ModelTables(p)
+        ot = oracle.model_tables(p)
+        assert np.array_equal(mt.lineconst, ot['lineconst'])
+        assert np.array_equal(mt.wlambda, ot['wlambda'])
+        assert np.array_equal(mt.twohc_l3, ot['twohc_l3'])
+        assert np.array_equal(mt.wlacont, ot['wlacont'])
+        g = tables.gij_continuum(mt, p['nStar'], p['temperature'])
+        og = oracle.column_tables(p)['gijcont']
+        rows = np.concatenate([np.arange(ot['toff'][t], ot['toff'][t + 1]) for t in range(mt.Ntrans)
+                               if not p['trans'][t, 3]])
+        assert np.array_equal(g, og[rows])
+
+
+def test_synthetic_jitter_is_deterministic_and_mild():
+    from lightspinner_b200 import synth
+    p, r = load_golden('c1_falc_ca')
+    a, b = synth.jitter_problem(p, 7), synth.jitter_problem(p, 7)
+    assert np.array_equal(a['phi'], b['phi']) and np.array_equal(a['bg_chi'], b['bg_chi'])
+    c = synth.jitter_problem(p, 8)
+    assert not np.array_equal(a['bg_chi'], c['bg_chi'])
+    assert np.all(np.abs(np.log(a['bg_chi'] / p['bg_chi'])) < 0.25)
+
+
+@pytest.mark.reference
+def test_context_host_mirror_against_live_reference():
+    """With /root/reference present: the drop-in fed the REAL reference objects flattens to exactly what the
+    reference's own Context holds (phi, wphi, C, Nblue, ...)."""
+    from oracle.refharness import reference_available, load_reference, build_falc_setup
+    if not reference_available():
+        pytest.skip('Lightspinner reference not present')
+    from oracle.refharness.extract import problem_from_reference_context
+    from lightspinner_b200.context import Context
+    import copy
+    ref = load_reference()
+    atmos, spect, eqPops, bg = build_falc_setup(active=('Ca',), nrays=3)
+    eq2 = copy.deepcopy(eqPops)
+    rctx = ref['rh_method'].Context(atmos, spect, eqPops, bg)
+    pr = problem_from_reference_context(rctx)
+    ctx = Context(atmos, spect, eq2, bg, _host_only=True)
+    for k in KEYS:
+        assert np.array_equal(np.asarray(ctx._problem[k]), np.asarray(pr[k])), k
