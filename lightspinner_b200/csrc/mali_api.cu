@@ -6,13 +6,14 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
 #include <vector>
 
 #include "../../include/mali_b200.h"
-#include "mali_fs_kernel.cuh"
+#include "mali_fs_spec.cuh"
 
 using namespace mali;
 
@@ -81,6 +82,34 @@ __global__ void iterate_ctl_kernel(int phase, double *dJ, double *dPops, int32_t
 
 }  // namespace
 
+// Ahead-of-time instances of the structure-specialised kernel (generated: tools/gen_spec_instances.py)
+#define MALI_SPEC(ID, KEY, ...) \
+    struct SpecTag##ID {           \
+        static constexpr TileStruct S = {__VA_ARGS__}; \
+    };
+#include "spec_instances.inc"
+#undef MALI_SPEC
+#define MALI_SPEC(ID, KEY, ...) {KEY, SpecTag##ID::S.nslot, &spec_launch<SpecTag##ID>},
+static const SpecEntry kSpecRegistry[] = {
+#include "spec_instances.inc"
+    {nullptr, 0, nullptr}};
+#undef MALI_SPEC
+
+static const SpecEntry *find_spec(const std::string &key)
+{
+    static std::map<std::string, const SpecEntry *> index;
+    if (index.empty())
+        for (const SpecEntry *e = kSpecRegistry; e->key; ++e) index[e->key] = e;
+    auto it = index.find(key);
+    return it == index.end() ? nullptr : it->second;
+}
+
+struct SpecGroup {
+    const SpecEntry *entry;
+    std::vector<unsigned char> tiles;  // TileR<nslot> records, back to back
+    int ntile = 0;
+};
+
 struct mali_model {
     int device = 0;
     int N = 0, Nrays = 0, Nspect = 0, Natom = 0, Ntrans = 0, Lw = 0, ntile = 0, Dmax = 0, Tmax = 0;
@@ -91,6 +120,8 @@ struct mali_model {
     std::vector<SlotDesc> transSlot;  // one descriptor per transition (for the uv hook)
     std::vector<int32_t> classTiles[3];  // tiles with <= 4, 5..8, > 8 transitions
     int32_t *d_classTiles[3] = {nullptr, nullptr, nullptr};
+    std::vector<SpecGroup> specGroups;   // tiles served by structure-specialised kernel instances
+    int specTiles = 0;
     std::vector<TileC<4>> tiles4;        // constant-bank descriptors of the class-0 / class-1 tiles
     std::vector<TileC<8>> tiles8;
     int64_t off_zero = 0;
@@ -407,10 +438,62 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
         c.cB = sd.c1;
         return c;
     };
+    auto structure_key = [&](const TileDesc &td) {   // must match tools/gen_spec_instances.py
+        int kind[8] = {0}, atom[8] = {0}, lvI[8] = {0}, lvJ[8] = {0}, rowI[8] = {0}, rowJ[8] = {0};
+        for (int q = 0; q < td.nslot; ++q) {
+            const SlotDesc &sd = m->slots[td.slot0 + q];
+            kind[q] = sd.isLine ? 1 : 0;
+            atom[q] = sd.atom;
+            lvI[q] = sd.lsI;
+            lvJ[q] = sd.lsJ;
+            rowI[q] = sd.rowI;
+            rowJ[q] = sd.rowJ;
+        }
+        auto arr = [](const int *x) {
+            std::string r = "{";
+            for (int q = 0; q < 8; ++q) r += std::to_string(x[q]) + (q < 7 ? "," : "}");
+            return r;
+        };
+        return "{" + std::to_string(td.nslot) + "," + std::to_string(d->Natom) + "," + std::to_string(td.nlevslot) + "," +
+               arr(kind) + "," + arr(atom) + "," + arr(lvI) + "," + arr(lvJ) + "," + arr(rowI) + "," + arr(rowJ) + "}";
+    };
+    std::map<std::string, int> groupOf;
+    const bool noSpec = getenv("MALI_NO_SPEC") != nullptr;
     for (int ti = 0; ti < m->ntile; ++ti) {
         const TileDesc &td = m->tiles[ti];
         const int T = td.nslot;
         const int cls = (d->Natom > 4 || T > 8) ? 2 : (T > 4 ? 1 : 0);
+        if (cls < 2 && !noSpec) {
+            const std::string key = structure_key(td);
+            if (const SpecEntry *e = find_spec(key)) {
+                auto it = groupOf.find(key);
+                if (it == groupOf.end()) {
+                    it = groupOf.emplace(key, (int)m->specGroups.size()).first;
+                    m->specGroups.push_back(SpecGroup{e, {}, 0});
+                }
+                SpecGroup &g = m->specGroups[it->second];
+                const size_t rec = 8 + sizeof(SlotR) * std::max(T, 1);
+                const size_t o = g.tiles.size();
+                g.tiles.resize(o + rec, 0);
+                int32_t hdr[2] = {td.la0, td.partRow0};
+                memcpy(&g.tiles[o], hdr, 8);
+                for (int q = 0; q < T; ++q) {
+                    const SlotDesc &sd = m->slots[td.slot0 + q];
+                    SlotR r{};
+                    r.Nblue = sd.Nblue;
+                    r.Nlam = sd.Nlam;
+                    r.tabOff = (int32_t)sd.tabOff;
+                    r.wlaOff = (int32_t)sd.wlaOff;
+                    r.toff = sd.toff;
+                    r.cA = sd.c2;
+                    r.cB = sd.c1;
+                    memcpy(&g.tiles[o + 8 + sizeof(SlotR) * q], &r, sizeof(SlotR));
+                }
+                g.ntile++;
+                m->specTiles++;
+                continue;
+            }
+        }
         m->classTiles[cls].push_back(ti);
         if (cls == 0) {
             TileC<4> t{};
@@ -428,6 +511,8 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
             m->tiles8.push_back(t);
         }
     }
+    std::stable_sort(m->specGroups.begin(), m->specGroups.end(),
+                     [](const SpecGroup &a, const SpecGroup &b) { return a.entry->nslot > b.entry->nslot; });
     {   // per-warp shared memory of fs_gamma_kernel_c: populations | heights | level array | mbarrier
         auto even = [](int x) { return (x + 1) & ~1; };
         m->smemPopDoubles = m->sumNlevel * N;
@@ -692,6 +777,10 @@ static int launch_fs(const mali_model *m, const mali_buffers *b, int col0, int n
             if (int e = launch_fs_class<8>(m, m->tiles8, c, ncol, smem, st)) return fail(e, "fs_gamma_kernel_c<8>: %s", cudaGetErrorString((cudaError_t)e));
         if (!m->tiles4.empty())
             if (int e = launch_fs_class<4>(m, m->tiles4, c, ncol, smem, st)) return fail(e, "fs_gamma_kernel_c<4>: %s", cudaGetErrorString((cudaError_t)e));
+        for (const SpecGroup &g : m->specGroups) {
+            cudaError_t e = g.entry->launch(c, g.tiles.data(), g.ntile, ncol, smem, st, &m->launches);
+            if (e != cudaSuccess) return fail((int)e, "fs_gamma_kernel_s: %s", cudaGetErrorString(e));
+        }
     }
     if (rec) {
         cudaEventRecord(m->profEvents[m->profUsed + 1], st);

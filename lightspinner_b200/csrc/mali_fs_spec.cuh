@@ -1,0 +1,425 @@
+// mali_fs_spec.cuh -- structure-specialised formal-solution / Gamma kernel: fs_gamma_kernel_s<S>.
+//
+// Same mapping, memory layout and arithmetic as fs_gamma_kernel_c (mali_fs_kernel.cuh), but the STRUCTURE of the
+// tile -- how many transitions overlap it, which are lines, which atom and which lower / upper level each one
+// connects (i.e. which transitions share a level in the MALI cross terms, rh_method.py:619-622, 677-680) -- is a
+// compile-time constant (a C++20 class-type template parameter).  Consequences on sm_100a:
+//   * the per-level sums chi[level], U[level] and the per-atom emissivity are plain registers with compile-time
+//     indices: no shared-memory read-modify-write, no first-touch branches, no address arithmetic;
+//   * slot loops unroll to the exact transition count; line / continuum code is selected at compile time;
+//   * the Gamma reduce-scatter is sized to the exact number of matrix entries of the tile (2, 4, 8 or 16 values);
+//   * register allocation is exact for the tile, so light tiles run at higher occupancy.
+// What stays run-time (warp-uniform, constant bank): where the tile sits (first wavelength, table offsets, Nblue,
+// Nlambda per transition, the lines' Einstein ratios) -- so one instance serves every tile with that structure.
+//
+// Instances for the structures of known models are generated ahead of time (tools/gen_spec_instances.py ->
+// spec_instances.inc, compiled by nvcc into libmali_b200.so); tiles whose structure has no instance fall back to
+// the class kernels of mali_fs_kernel.cuh.
+#pragma once
+#include "mali_fs_kernel.cuh"
+
+namespace mali {
+
+constexpr int kSpecMaxSlots = 8;
+
+struct TileStruct {
+    int nslot;                    // transitions overlapping the tile
+    int natom;                    // atoms of the model (per-atom emissivity registers)
+    int nlev;                     // distinct (atom, level) pairs touched
+    int kind[kSpecMaxSlots];      // 1 = line, 0 = continuum
+    int atom[kSpecMaxSlots];
+    int lvI[kSpecMaxSlots], lvJ[kSpecMaxSlots];    // level-slot of the lower / upper level
+    int rowI[kSpecMaxSlots], rowJ[kSpecMaxSlots];  // row of the level in n[sumNlevel][N]
+};
+
+struct SlotR {  // run-time part of a slot, warp-uniform (constant bank), 40 B
+    int32_t Nblue, Nlam, tabOff, wlaOff, toff, pad;
+    double cA, cB;  // lines: Bji/Bij, Aji/Bji
+};
+
+template <int NS>
+struct TileR {
+    int32_t la0, partRow0;
+    SlotR s[NS > 0 ? NS : 1];
+};
+
+template <int NS>
+struct SpecParams {
+    static constexpr int kMaxTiles = (31 * 1024 - (int)sizeof(FsCommon)) / (int)sizeof(TileR<NS>);
+    FsCommon c;
+    TileR<NS> tiles[kMaxTiles];
+};
+
+__host__ __device__ constexpr int spec_pow2(int x) { return x <= 2 ? 2 : (x <= 4 ? 4 : (x <= 8 ? 8 : 16)); }
+__host__ __device__ constexpr int spec_minblocks(int nslot) { return nslot <= 2 ? 4 : (nslot <= 4 ? 3 : 2); }
+
+// deterministic reduce-scatter of M = 2..16 values per lane; the lane ends up with the total of value lane/(32/M)
+template <int M>
+__device__ __forceinline__ double reduce_scatter_n(double (&v)[M], int lane)
+{
+    const unsigned full = 0xffffffffu;
+    int off = 16;
+#pragma unroll
+    for (int m = M; m > 1; m >>= 1, off >>= 1) {
+        const bool up = lane & off;
+#pragma unroll
+        for (int j = 0; j < m / 2; ++j) {
+            const double send = up ? v[j] : v[j + m / 2];
+            const double keep = up ? v[j + m / 2] : v[j];
+            v[j] = keep + __shfl_xor_sync(full, send, off);
+        }
+    }
+#pragma unroll
+    for (; off > 0; off >>= 1) v[0] = v[0] + __shfl_xor_sync(full, v[0], off);
+    return v[0];
+}
+
+// SPEC is a tag type with a `static constexpr TileStruct S` member (nvcc cannot build host stubs for kernels with
+// class-type non-type template parameters, so the structure travels inside a type).
+template <class SPEC>
+__global__ void __launch_bounds__(128, spec_minblocks(SPEC::S.nslot))
+fs_gamma_kernel_s(const __grid_constant__ SpecParams<SPEC::S.nslot> P)
+{
+    constexpr TileStruct S = SPEC::S;
+    constexpr int NS = S.nslot;
+    constexpr int NSA = NS > 0 ? NS : 1;
+    constexpr int NLV = S.nlev > 0 ? S.nlev : 1;
+    constexpr int NA = S.natom > 0 ? S.natom : 1;
+    constexpr int M = spec_pow2(2 * NS);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const FsCommon &p = P.c;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int col = p.col0 + blockIdx.y * p.warpsPerBlock + warp;
+    if (col >= p.col0 + p.ncol) return;
+    if (p.done != nullptr && p.done[col] != 0) return;
+
+    const TileR<NS> &T = P.tiles[blockIdx.x];
+    const int N = p.N, Nrays = p.Nrays, Nspect = p.Nspect;
+    const int ls = lane / Nrays, mu = lane - ls * Nrays;
+    const int la = T.la0 + ls;
+    const bool valid = (ls < p.Lw) && (la < Nspect);
+    const int laC = valid ? la : T.la0;
+    const int muC = valid ? mu : 0;
+    const bool leader = valid && (mu == 0);
+
+    const double *__restrict__ cc = p.colconst + (size_t)col * p.colStride;
+    double *Jcol = p.J + (size_t)col * p.JStride;
+    double *scr = p.scratch + (size_t)col * p.scratchStride;
+    double *Jpart = scr + p.off_jpart;
+    double *part = scr + p.off_part + (size_t)T.partRow0 * N;
+
+    // ---- stage this column's depth profiles (populations, heights) into shared memory: TMA bulk copies
+    unsigned char *wbase = smem_raw + (size_t)warp * p.smemBytesPerWarp;
+    double *sN = reinterpret_cast<double *>(wbase);
+    double *sZ = sN + p.zOffDoubles;
+    {
+        const double *gN = p.pops + (size_t)col * p.popStride;
+        const double *gZ = cc + p.off_z;
+        if (p.useBulk) {
+            const uint32_t mbar = smem_u32(wbase + p.mbarOffBytes);
+            if (lane == 0) {
+                const uint32_t bytesN = (uint32_t)p.popDoubles * 8u, bytesZ = (uint32_t)N * 8u;
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytesN + bytesZ)
+                             : "memory");
+                asm volatile(
+                    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                        smem_u32(sN)),
+                    "l"(gN), "r"(bytesN), "r"(mbar)
+                    : "memory");
+                asm volatile(
+                    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                        smem_u32(sZ)),
+                    "l"(gZ), "r"(bytesZ), "r"(mbar)
+                    : "memory");
+            }
+            __syncwarp();
+            uint32_t ok = 0;
+            do {
+                asm volatile(
+                    "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                    : "=r"(ok)
+                    : "r"(mbar)
+                    : "memory");
+            } while (!ok);
+        } else {
+            for (int q = lane; q < p.popDoubles; q += 32) sN[q] = gN[q];
+            for (int q = lane; q < N; q += 32) sZ[q] = gZ[q];
+            __syncwarp();
+        }
+    }
+
+    const double zmu = p.zmu[muC], hw = p.hw[muC];
+    const double bbc0 = cc[p.off_bbc + 2 * laC], bbc1 = cc[p.off_bbc + 2 * laC + 1];
+    const double fourPi = 4.0 * kPi;
+    const int zeroIdx = (int)p.off_zero;
+
+    // ---- depth-invariant per-lane slot state
+    bool act[NSA];
+    double ca[NSA], cb[NSA], cw[NSA];  // continua: alpha, 2hc/lambda^3, wlamu (per lane)
+#pragma unroll
+    for (int tt = 0; tt < NS; ++tt) {
+        const SlotR &s = T.s[tt];
+        const int lt = laC - s.Nblue;
+        act[tt] = valid && lt >= 0 && lt < s.Nlam;
+        ca[tt] = 0.0;
+        cb[tt] = 0.0;
+        cw[tt] = 0.0;
+        if (!S.kind[tt] && act[tt]) {
+            ca[tt] = __ldg(p.alpha + s.toff + lt);
+            cb[tt] = __ldg(p.twohc + s.toff + lt);
+            cw[tt] = (__ldg(p.wlacont + s.toff + lt) * hw) * fourPi;
+        }
+    }
+
+    unsigned long long dJb = 0ull;
+
+    for (int d = 0; d < 2; ++d) {
+        const int dk = d ? -1 : 1;
+        const int kS = d ? N - 1 : 0;
+        int ia[NSA], sa[NSA], ib[NSA], sb[NSA];
+#pragma unroll
+        for (int tt = 0; tt < NS; ++tt) {
+            const SlotR &s = T.s[tt];
+            const int lt = laC - s.Nblue;
+            ia[tt] = zeroIdx;
+            sa[tt] = 0;
+            ib[tt] = zeroIdx;
+            sb[tt] = 0;
+            if (act[tt]) {
+                if (S.kind[tt]) {
+                    const int strA = s.Nlam * Nrays;
+                    ia[tt] = s.tabOff + lt * Nrays + muC + (d * N + kS) * strA;
+                    sa[tt] = dk * strA;
+                    ib[tt] = s.wlaOff + lt + kS * s.Nlam;
+                    sb[tt] = dk * s.Nlam;
+                } else {
+                    ia[tt] = s.tabOff + lt + kS * s.Nlam;
+                    sa[tt] = dk * s.Nlam;
+                }
+            }
+        }
+        int kl = kS * Nspect + laC;
+        const int dkl = dk * Nspect;
+
+        // thermalised lower boundary needs chi at kS+dk before the sweep starts (formal_solver.py:205)
+        double chiProbe = 0.0;
+        if (d) {
+            const int k = kS + dk;
+            double chiTot = 0.0;
+#pragma unroll
+            for (int tt = 0; tt < NS; ++tt) {
+                const double ld = __ldg(cc + ia[tt] + sa[tt]);
+                const double ni = sN[S.rowI[tt] * N + k], nj = sN[S.rowJ[tt] * N + k];
+                if (S.kind[tt])
+                    chiTot += ni * ld - nj * (T.s[tt].cA * ld);
+                else
+                    chiTot += ni * ca[tt] - nj * (ld * ca[tt]);
+            }
+            chiProbe = chiTot + __ldg(cc + p.off_bgchi + kl + dkl);
+        }
+
+        // software prefetch: the streams of step s+1 are in flight while step s is computed
+        double ldN[NSA], wlN[NSA], bgcN, bgeN, bgsN, JdN;
+#pragma unroll
+        for (int tt = 0; tt < NS; ++tt) {
+            ldN[tt] = __ldg(cc + ia[tt]);
+            wlN[tt] = 0.0;
+            if (S.kind[tt]) wlN[tt] = __ldg(cc + ib[tt]);
+        }
+        bgcN = __ldg(cc + p.off_bgchi + kl);
+        bgeN = __ldg(cc + p.off_bgeta + kl);
+        bgsN = __ldg(cc + p.off_bgsca + kl);
+        JdN = Jcol[kl];
+
+        Sweep sw;
+        for (int s = 0; s < N; ++s) {
+            const int k = kS + s * dk;
+            double ld[NSA], wl[NSA];
+#pragma unroll
+            for (int tt = 0; tt < NS; ++tt) {
+                ld[tt] = ldN[tt];
+                wl[tt] = wlN[tt];
+            }
+            const double bgc = bgcN, bge = bgeN, bgs = bgsN, Jdag = JdN;
+            const int klc = kl;
+            // partial sums written by the down sweep (read early: consumed at the end of the step)
+            double jOld = 0.0, gOld = 0.0;
+            const int e = lane / (32 / M);                       // Gamma value owned by this lane after the reduce
+            const bool writer = (lane % (32 / M)) == 0 && e < 2 * NS;
+            double *gdst = part + (size_t)e * N + k;
+            if (d) {
+                if (leader) jOld = __ldcg(Jpart + klc);
+                if (writer) gOld = __ldcg(gdst);
+            }
+            if (s + 1 < N) {
+                kl += dkl;
+#pragma unroll
+                for (int tt = 0; tt < NS; ++tt) {
+                    ia[tt] += sa[tt];
+                    ldN[tt] = __ldg(cc + ia[tt]);
+                    if (S.kind[tt]) {
+                        ib[tt] += sb[tt];
+                        wlN[tt] = __ldg(cc + ib[tt]);
+                    }
+                }
+                bgcN = __ldg(cc + p.off_bgchi + kl);
+                bgeN = __ldg(cc + p.off_bgeta + kl);
+                bgsN = __ldg(cc + p.off_bgsca + kl);
+                JdN = Jcol[kl];
+            }
+
+            // ---- (1) opacity / emissivity, rh_method.py:601-632.  chiL / UL / etaA: compile-time indexed registers
+            double chiTot = 0.0, etaTot = 0.0;
+            double chiL[NLV], UL[NLV], etaA[NA];
+            double Vij[NSA], Vji[NSA], Uji[NSA];
+#pragma unroll
+            for (int q = 0; q < NLV; ++q) {
+                chiL[q] = 0.0;
+                UL[q] = 0.0;
+            }
+#pragma unroll
+            for (int a = 0; a < NA; ++a) etaA[a] = 0.0;
+#pragma unroll
+            for (int tt = 0; tt < NS; ++tt) {
+                if (S.kind[tt]) {  // rh_method.py:278-281; the table holds hc/4pi*Bij*phi
+                    Vij[tt] = ld[tt];
+                    Vji[tt] = T.s[tt].cA * Vij[tt];
+                    Uji[tt] = T.s[tt].cB * Vji[tt];
+                } else {           // rh_method.py:284-286
+                    Vij[tt] = ca[tt];
+                    Vji[tt] = ld[tt] * Vij[tt];
+                    Uji[tt] = cb[tt] * Vji[tt];
+                }
+                const double ni = sN[S.rowI[tt] * N + k], nj = sN[S.rowJ[tt] * N + k];
+                const double chi_t = ni * Vij[tt] - nj * Vji[tt];
+                const double eta_t = nj * Uji[tt];
+                // first touch of a level / atom: the reference's 0.0 + x (== x up to the sign of zero)
+                bool firstI = true, firstJ = true, firstA = true;
+                for (int u = 0; u < tt; ++u) {
+                    if (S.lvI[u] == S.lvI[tt] || S.lvJ[u] == S.lvI[tt]) firstI = false;
+                    if (S.lvI[u] == S.lvJ[tt] || S.lvJ[u] == S.lvJ[tt]) firstJ = false;
+                    if (S.atom[u] == S.atom[tt]) firstA = false;
+                }
+                chiL[S.lvI[tt]] = firstI ? chi_t : chiL[S.lvI[tt]] + chi_t;
+                chiL[S.lvJ[tt]] = firstJ ? -chi_t : chiL[S.lvJ[tt]] - chi_t;
+                UL[S.lvJ[tt]] = firstJ ? Uji[tt] : UL[S.lvJ[tt]] + Uji[tt];
+                etaA[S.atom[tt]] = firstA ? eta_t : etaA[S.atom[tt]] + eta_t;
+                chiTot = (tt == 0) ? chi_t : chiTot + chi_t;
+                etaTot = (tt == 0) ? eta_t : etaTot + eta_t;
+            }
+            chiTot += bgc;
+            const double Ssrc = (etaTot + bge + bgs * Jdag) / chiTot;
+
+            // ---- (2) short characteristic
+            const double zk = sZ[k];
+            double Ik, Psi;
+            if (s == 0)
+                sw.first(d != 0, zmu, chiTot, Ssrc, zk, chiProbe, sZ[kS + dk], bbc0, bbc1, Ik, Psi);
+            else
+                sw.step(s == N - 1, zmu, chiTot, Ssrc, zk, Ik, Psi);
+
+            // ---- (3) J, rh_method.py:640
+            {
+                const double x = valid ? hw * Ik : 0.0;
+                double sum = x;
+                if (Nrays == 5) {
+#pragma unroll
+                    for (int m = 1; m < 5; ++m) sum += __shfl_down_sync(0xffffffffu, x, m);
+                } else if (Nrays == 3) {
+#pragma unroll
+                    for (int m = 1; m < 3; ++m) sum += __shfl_down_sync(0xffffffffu, x, m);
+                } else {
+                    for (int m = 1; m < Nrays; ++m) sum += __shfl_down_sync(0xffffffffu, x, m);
+                }
+                if (leader) {
+                    if (d == 0) {
+                        __stcg(Jpart + klc, sum);
+                    } else {
+                        const double Jn = jOld + sum;
+                        Jcol[klc] = Jn;
+                        const unsigned long long b = absbits(1.0 - Jdag / Jn);
+                        dJb = b > dJb ? b : dJb;
+                    }
+                }
+            }
+
+            // ---- (4) Gamma integrands, rh_method.py:643-681
+            if constexpr (NS > 0) {
+                double v[M];
+#pragma unroll
+                for (int q = 0; q < M; ++q) v[q] = 0.0;
+                double Ieff[NA];
+#pragma unroll
+                for (int a = 0; a < NA; ++a) Ieff[a] = Ik - Psi * etaA[a];
+#pragma unroll
+                for (int tt = 0; tt < NS; ++tt) {
+                    const double wlamu = S.kind[tt] ? (wl[tt] * hw) * fourPi : cw[tt];  // rh_method.py:665
+                    const double Ie = Ieff[S.atom[tt]];
+                    // Ulvl of a level no active transition has as its upper level is exactly 0: the reference's
+                    // (chi*Psi)*0.0 term is +-0 and drops out of the subtraction
+                    bool uJ = false, uI = false;
+                    for (int u = 0; u < NS; ++u) {
+                        if (S.lvJ[u] == S.lvJ[tt]) uJ = true;
+                        if (S.lvJ[u] == S.lvI[tt]) uI = true;
+                    }
+                    double g1 = Uji[tt] + Vji[tt] * Ie;
+                    if (uJ) g1 = g1 - ((chiL[S.lvI[tt]] * Psi) * UL[S.lvJ[tt]]);
+                    double g2 = Vij[tt] * Ie;
+                    if (uI) g2 = g2 - ((chiL[S.lvJ[tt]] * Psi) * UL[S.lvI[tt]]);
+                    v[2 * tt] = g1 * wlamu;  // inactive lanes: wlamu == 0
+                    v[2 * tt + 1] = g2 * wlamu;
+                }
+                const double tot = reduce_scatter_n<M>(v, lane);
+                if (writer) __stcg(gdst, d == 0 ? tot : gOld + tot);
+            }
+        }
+        if (d == 1 && valid) p.I[(size_t)col * p.IStride + (size_t)la * Nrays + mu] = sw.Iupw;
+    }
+
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(0xffffffffu, dJb, off);
+        dJb = o > dJb ? o : dJb;
+    }
+    if (lane == 0) atomicMax(p.dJbits + col, dJb);
+}
+
+// ---- registry of ahead-of-time instances -----------------------------------------------------------------
+typedef cudaError_t (*SpecLaunchFn)(const FsCommon &c, const void *tilesR, int ntile, int ncol, size_t smem,
+                                    cudaStream_t st, long long *launches);
+struct SpecEntry {
+    const char *key;
+    int nslot;
+    SpecLaunchFn launch;
+};
+
+template <class SPEC>
+cudaError_t spec_launch(const FsCommon &c, const void *tilesR, int ntile, int ncol, size_t smem, cudaStream_t st,
+                        long long *launches)
+{
+    constexpr TileStruct S = SPEC::S;
+    using SP = SpecParams<S.nslot>;
+    static thread_local SP *P = nullptr;
+    static thread_local bool attr = false;
+    if (!P) P = new SP();
+    auto kern = fs_gamma_kernel_s<SPEC>;
+    if (smem > 48 * 1024 && !attr) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    P->c = c;
+    const TileR<S.nslot> *tiles = static_cast<const TileR<S.nslot> *>(tilesR);
+    for (int t0 = 0; t0 < ntile; t0 += SP::kMaxTiles) {
+        const int n = ntile - t0 < SP::kMaxTiles ? ntile - t0 : SP::kMaxTiles;
+        memcpy(P->tiles, tiles + t0, sizeof(TileR<S.nslot>) * n);
+        dim3 grid(n, (ncol + c.warpsPerBlock - 1) / c.warpsPerBlock);
+        kern<<<grid, 32 * c.warpsPerBlock, smem, st>>>(*P);
+        if (launches) *launches += 1;
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace mali
