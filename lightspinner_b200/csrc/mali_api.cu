@@ -89,11 +89,33 @@ __global__ void iterate_ctl_kernel(int phase, double *dJ, double *dPops, int32_t
     };
 #include "spec_instances.inc"
 #undef MALI_SPEC
-#define MALI_SPEC(ID, KEY, ...) {KEY, SpecTag##ID::S.nslot, &spec_launch<SpecTag##ID>},
+#define MALI_SPEC(ID, KEY, ...) {KEY, SpecTag##ID::S.nslot, ID},
 static const SpecEntry kSpecRegistry[] = {
 #include "spec_instances.inc"
-    {nullptr, 0, nullptr}};
+    {nullptr, 0, 0}};
 #undef MALI_SPEC
+
+namespace mali {
+// One kernel per register class; the structure id of the tile selects the specialised body (uniform switch).
+template <int CLS>
+__global__ void __launch_bounds__(128, spec_class_minblocks(CLS)) fs_gamma_kernel_m(const __grid_constant__ MegaParams<CLS> P)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // blockIdx.x runs over column groups, blockIdx.y over tiles: co-resident blocks share a structure -> one
+    // instruction stream per SM (the specialised bodies are ~40 KB of SASS each)
+    const TileR<MegaParams<CLS>::NSP> &T = P.tiles[blockIdx.y];
+    switch (T.spec) {
+#define MALI_SPEC(ID, KEY, ...)                                                              \
+    case ID:                                                                                 \
+        if constexpr (spec_class(SpecTag##ID::S.nslot) == CLS) fs_body<SpecTag##ID>(P.c, T, smem_raw); \
+        break;
+#include "spec_instances.inc"
+#undef MALI_SPEC
+        default:
+            break;
+    }
+}
+}  // namespace mali
 
 static const SpecEntry *find_spec(const std::string &key)
 {
@@ -104,11 +126,31 @@ static const SpecEntry *find_spec(const std::string &key)
     return it == index.end() ? nullptr : it->second;
 }
 
-struct SpecGroup {
-    const SpecEntry *entry;
-    std::vector<unsigned char> tiles;  // TileR<nslot> records, back to back
-    int ntile = 0;
-};
+template <int CLS>
+static cudaError_t launch_mega(const FsCommon &c, const std::vector<TileR<spec_class_slots(CLS)>> &tiles, int ncol,
+                               size_t smem, cudaStream_t st, long long *launches)
+{
+    using MP = MegaParams<CLS>;
+    static thread_local MP *P = nullptr;
+    static thread_local bool attr = false;
+    if (!P) P = new MP();
+    auto kern = fs_gamma_kernel_m<CLS>;
+    if (smem > 48 * 1024 && !attr) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    P->c = c;
+    const int nt = (int)tiles.size();
+    for (int t0 = 0; t0 < nt; t0 += MP::kMaxTiles) {
+        const int n = std::min(MP::kMaxTiles, nt - t0);
+        memcpy(P->tiles, tiles.data() + t0, sizeof(tiles[0]) * n);
+        dim3 grid((ncol + c.warpsPerBlock - 1) / c.warpsPerBlock, n);
+        kern<<<grid, 32 * c.warpsPerBlock, smem, st>>>(*P);
+        if (launches) *launches += 1;
+    }
+    return cudaGetLastError();
+}
 
 struct mali_model {
     int device = 0;
@@ -120,7 +162,9 @@ struct mali_model {
     std::vector<SlotDesc> transSlot;  // one descriptor per transition (for the uv hook)
     std::vector<int32_t> classTiles[3];  // tiles with <= 4, 5..8, > 8 transitions
     int32_t *d_classTiles[3] = {nullptr, nullptr, nullptr};
-    std::vector<SpecGroup> specGroups;   // tiles served by structure-specialised kernel instances
+    std::vector<TileR<2>> spec0;         // tiles served by the structure-specialised kernels, per register class,
+    std::vector<TileR<4>> spec1;         // heaviest first
+    std::vector<TileR<8>> spec2;
     int specTiles = 0;
     std::vector<TileC<4>> tiles4;        // constant-bank descriptors of the class-0 / class-1 tiles
     std::vector<TileC<8>> tiles8;
@@ -457,39 +501,46 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
         return "{" + std::to_string(td.nslot) + "," + std::to_string(d->Natom) + "," + std::to_string(td.nlevslot) + "," +
                arr(kind) + "," + arr(atom) + "," + arr(lvI) + "," + arr(lvJ) + "," + arr(rowI) + "," + arr(rowJ) + "}";
     };
-    std::map<std::string, int> groupOf;
     const bool noSpec = getenv("MALI_NO_SPEC") != nullptr;
-    for (int ti = 0; ti < m->ntile; ++ti) {
+    auto fill_tile = [&](auto &t, const TileDesc &td, int spec) {
+        t.la0 = td.la0;
+        t.partRow0 = td.partRow0;
+        t.spec = spec;
+        for (int q = 0; q < td.nslot; ++q) {
+            const SlotDesc &sd = m->slots[td.slot0 + q];
+            SlotR &r = t.s[q];
+            r.Nblue = sd.Nblue;
+            r.Nlam = sd.Nlam;
+            r.tabOff = (int32_t)sd.tabOff;
+            r.wlaOff = (int32_t)sd.wlaOff;
+            r.toff = sd.toff;
+            r.cA = sd.c2;
+            r.cB = sd.c1;
+        }
+    };
+    std::vector<int> order(m->ntile);
+    for (int ti = 0; ti < m->ntile; ++ti) order[ti] = ti;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return m->tiles[a].nslot > m->tiles[b].nslot; });
+    for (int ti : order) {
         const TileDesc &td = m->tiles[ti];
         const int T = td.nslot;
         const int cls = (d->Natom > 4 || T > 8) ? 2 : (T > 4 ? 1 : 0);
         if (cls < 2 && !noSpec) {
-            const std::string key = structure_key(td);
-            if (const SpecEntry *e = find_spec(key)) {
-                auto it = groupOf.find(key);
-                if (it == groupOf.end()) {
-                    it = groupOf.emplace(key, (int)m->specGroups.size()).first;
-                    m->specGroups.push_back(SpecGroup{e, {}, 0});
+            if (const SpecEntry *e = find_spec(structure_key(td))) {
+                const int sc = spec_class(T);
+                if (sc == 0) {
+                    TileR<2> t{};
+                    fill_tile(t, td, e->id);
+                    m->spec0.push_back(t);
+                } else if (sc == 1) {
+                    TileR<4> t{};
+                    fill_tile(t, td, e->id);
+                    m->spec1.push_back(t);
+                } else {
+                    TileR<8> t{};
+                    fill_tile(t, td, e->id);
+                    m->spec2.push_back(t);
                 }
-                SpecGroup &g = m->specGroups[it->second];
-                const size_t rec = 8 + sizeof(SlotR) * std::max(T, 1);
-                const size_t o = g.tiles.size();
-                g.tiles.resize(o + rec, 0);
-                int32_t hdr[2] = {td.la0, td.partRow0};
-                memcpy(&g.tiles[o], hdr, 8);
-                for (int q = 0; q < T; ++q) {
-                    const SlotDesc &sd = m->slots[td.slot0 + q];
-                    SlotR r{};
-                    r.Nblue = sd.Nblue;
-                    r.Nlam = sd.Nlam;
-                    r.tabOff = (int32_t)sd.tabOff;
-                    r.wlaOff = (int32_t)sd.wlaOff;
-                    r.toff = sd.toff;
-                    r.cA = sd.c2;
-                    r.cB = sd.c1;
-                    memcpy(&g.tiles[o + 8 + sizeof(SlotR) * q], &r, sizeof(SlotR));
-                }
-                g.ntile++;
                 m->specTiles++;
                 continue;
             }
@@ -511,8 +562,6 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
             m->tiles8.push_back(t);
         }
     }
-    std::stable_sort(m->specGroups.begin(), m->specGroups.end(),
-                     [](const SpecGroup &a, const SpecGroup &b) { return a.entry->nslot > b.entry->nslot; });
     {   // per-warp shared memory of fs_gamma_kernel_c: populations | heights | level array | mbarrier
         auto even = [](int x) { return (x + 1) & ~1; };
         m->smemPopDoubles = m->sumNlevel * N;
@@ -777,10 +826,11 @@ static int launch_fs(const mali_model *m, const mali_buffers *b, int col0, int n
             if (int e = launch_fs_class<8>(m, m->tiles8, c, ncol, smem, st)) return fail(e, "fs_gamma_kernel_c<8>: %s", cudaGetErrorString((cudaError_t)e));
         if (!m->tiles4.empty())
             if (int e = launch_fs_class<4>(m, m->tiles4, c, ncol, smem, st)) return fail(e, "fs_gamma_kernel_c<4>: %s", cudaGetErrorString((cudaError_t)e));
-        for (const SpecGroup &g : m->specGroups) {
-            cudaError_t e = g.entry->launch(c, g.tiles.data(), g.ntile, ncol, smem, st, &m->launches);
-            if (e != cudaSuccess) return fail((int)e, "fs_gamma_kernel_s: %s", cudaGetErrorString(e));
-        }
+        cudaError_t e = cudaSuccess;
+        if (!m->spec2.empty()) e = launch_mega<2>(c, m->spec2, ncol, smem, st, &m->launches);
+        if (e == cudaSuccess && !m->spec1.empty()) e = launch_mega<1>(c, m->spec1, ncol, smem, st, &m->launches);
+        if (e == cudaSuccess && !m->spec0.empty()) e = launch_mega<0>(c, m->spec0, ncol, smem, st, &m->launches);
+        if (e != cudaSuccess) return fail((int)e, "fs_gamma_kernel_m: %s", cudaGetErrorString(e));
     }
     if (rec) {
         cudaEventRecord(m->profEvents[m->profUsed + 1], st);

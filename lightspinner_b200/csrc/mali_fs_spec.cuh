@@ -37,21 +37,26 @@ struct SlotR {  // run-time part of a slot, warp-uniform (constant bank), 40 B
     double cA, cB;  // lines: Bji/Bij, Aji/Bji
 };
 
-template <int NS>
-struct TileR {
-    int32_t la0, partRow0;
-    SlotR s[NS > 0 ? NS : 1];
-};
-
-template <int NS>
-struct SpecParams {
-    static constexpr int kMaxTiles = (31 * 1024 - (int)sizeof(FsCommon)) / (int)sizeof(TileR<NS>);
-    FsCommon c;
-    TileR<NS> tiles[kMaxTiles];
-};
-
+// Tiles are grouped into three register classes by slot count; one "mega" kernel per class dispatches on the
+// tile's structure id (a warp-uniform switch), so a whole class is ONE launch however many structures it holds.
+__host__ __device__ constexpr int spec_class(int nslot) { return nslot <= 2 ? 0 : (nslot <= 4 ? 1 : 2); }
+__host__ __device__ constexpr int spec_class_slots(int cls) { return cls == 0 ? 2 : (cls == 1 ? 4 : 8); }
+__host__ __device__ constexpr int spec_class_minblocks(int cls) { return cls == 0 ? 4 : (cls == 1 ? 3 : 2); }
 __host__ __device__ constexpr int spec_pow2(int x) { return x <= 2 ? 2 : (x <= 4 ? 4 : (x <= 8 ? 8 : 16)); }
-__host__ __device__ constexpr int spec_minblocks(int nslot) { return nslot <= 2 ? 4 : (nslot <= 4 ? 3 : 2); }
+
+template <int NSP>
+struct TileR {
+    int32_t la0, partRow0, spec, pad;  // spec: structure id (index of the ahead-of-time instance)
+    SlotR s[NSP];
+};
+
+template <int CLS>
+struct MegaParams {
+    static constexpr int NSP = spec_class_slots(CLS);
+    static constexpr int kMaxTiles = (31 * 1024 - (int)sizeof(FsCommon)) / (int)sizeof(TileR<NSP>);
+    FsCommon c;
+    TileR<NSP> tiles[kMaxTiles];
+};
 
 // deterministic reduce-scatter of M = 2..16 values per lane; the lane ends up with the total of value lane/(32/M)
 template <int M>
@@ -74,11 +79,9 @@ __device__ __forceinline__ double reduce_scatter_n(double (&v)[M], int lane)
     return v[0];
 }
 
-// SPEC is a tag type with a `static constexpr TileStruct S` member (nvcc cannot build host stubs for kernels with
-// class-type non-type template parameters, so the structure travels inside a type).
-template <class SPEC>
-__global__ void __launch_bounds__(128, spec_minblocks(SPEC::S.nslot))
-fs_gamma_kernel_s(const __grid_constant__ SpecParams<SPEC::S.nslot> P)
+// SPEC is a tag type with a `static constexpr TileStruct S` member (the structure travels inside a type).
+template <class SPEC, int NSP>
+__device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, unsigned char *smem_raw)
 {
     constexpr TileStruct S = SPEC::S;
     constexpr int NS = S.nslot;
@@ -86,14 +89,11 @@ fs_gamma_kernel_s(const __grid_constant__ SpecParams<SPEC::S.nslot> P)
     constexpr int NLV = S.nlev > 0 ? S.nlev : 1;
     constexpr int NA = S.natom > 0 ? S.natom : 1;
     constexpr int M = spec_pow2(2 * NS);
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const FsCommon &p = P.c;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int col = p.col0 + blockIdx.y * p.warpsPerBlock + warp;
+    const int col = p.col0 + blockIdx.x * p.warpsPerBlock + warp;
     if (col >= p.col0 + p.ncol) return;
     if (p.done != nullptr && p.done[col] != 0) return;
 
-    const TileR<NS> &T = P.tiles[blockIdx.x];
     const int N = p.N, Nrays = p.Nrays, Nspect = p.Nspect;
     const int ls = lane / Nrays, mu = lane - ls * Nrays;
     const int la = T.la0 + ls;
@@ -387,39 +387,10 @@ fs_gamma_kernel_s(const __grid_constant__ SpecParams<SPEC::S.nslot> P)
 }
 
 // ---- registry of ahead-of-time instances -----------------------------------------------------------------
-typedef cudaError_t (*SpecLaunchFn)(const FsCommon &c, const void *tilesR, int ntile, int ncol, size_t smem,
-                                    cudaStream_t st, long long *launches);
 struct SpecEntry {
     const char *key;
     int nslot;
-    SpecLaunchFn launch;
+    int id;
 };
-
-template <class SPEC>
-cudaError_t spec_launch(const FsCommon &c, const void *tilesR, int ntile, int ncol, size_t smem, cudaStream_t st,
-                        long long *launches)
-{
-    constexpr TileStruct S = SPEC::S;
-    using SP = SpecParams<S.nslot>;
-    static thread_local SP *P = nullptr;
-    static thread_local bool attr = false;
-    if (!P) P = new SP();
-    auto kern = fs_gamma_kernel_s<SPEC>;
-    if (smem > 48 * 1024 && !attr) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return e;
-        attr = true;
-    }
-    P->c = c;
-    const TileR<S.nslot> *tiles = static_cast<const TileR<S.nslot> *>(tilesR);
-    for (int t0 = 0; t0 < ntile; t0 += SP::kMaxTiles) {
-        const int n = ntile - t0 < SP::kMaxTiles ? ntile - t0 : SP::kMaxTiles;
-        memcpy(P->tiles, tiles + t0, sizeof(TileR<S.nslot>) * n);
-        dim3 grid(n, (ncol + c.warpsPerBlock - 1) / c.warpsPerBlock);
-        kern<<<grid, 32 * c.warpsPerBlock, smem, st>>>(*P);
-        if (launches) *launches += 1;
-    }
-    return cudaGetLastError();
-}
 
 }  // namespace mali
