@@ -98,7 +98,7 @@ static const SpecEntry kSpecRegistry[] = {
 namespace mali {
 // One kernel per register class; the structure id of the tile selects the specialised body (uniform switch).
 template <int CLS>
-__global__ void __launch_bounds__(128, spec_class_minblocks(CLS)) fs_gamma_kernel_m(const __grid_constant__ MegaParams<CLS> P)
+__global__ void __launch_bounds__(32, 4 * spec_class_minblocks(CLS)) fs_gamma_kernel_m(const __grid_constant__ MegaParams<CLS> P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // blockIdx.x runs over column groups, blockIdx.y over tiles: co-resident blocks share a structure -> one
@@ -262,7 +262,7 @@ static int launch_fs_class(const mali_model *m, const std::vector<TileC<TMAX>> &
     for (int t0 = 0; t0 < nt; t0 += CP::kMaxTiles) {
         const int n = std::min(CP::kMaxTiles, nt - t0);
         memcpy(P->tiles, tiles.data() + t0, sizeof(TileC<TMAX>) * n);
-        dim3 grid(n, (ncol + c.warpsPerBlock - 1) / c.warpsPerBlock);
+        dim3 grid((ncol + c.warpsPerBlock - 1) / c.warpsPerBlock, n);
         kern<<<grid, 32 * c.warpsPerBlock, smem, st>>>(*P);
         m->launches += 1;
     }
@@ -567,7 +567,7 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
         m->smemPopDoubles = m->sumNlevel * N;
         m->smemZOff = even(m->smemPopDoubles);
         m->smemLvlOff = m->smemZOff + even(N);
-        m->smemMbarOff = (m->smemLvlOff + std::max(m->Dmax, 1) * 64) * 8;
+        m->smemMbarOff = (m->smemLvlOff + std::max(std::max(m->Dmax, 1) * 64, 16 * 36)) * 8;
         m->smemBytesPerWarp = (int)align_up(m->smemMbarOff + 16, 16);
         m->useBulk = (N % 2 == 0 && m->smemPopDoubles % 2 == 0) ? 1 : 0;  // cp.async.bulk: 16-byte sizes / addresses
     }
@@ -795,7 +795,7 @@ static FinishParams make_finish_params(const mali_model *m, const mali_buffers *
 static int launch_fs(const mali_model *m, const mali_buffers *b, int col0, int ncol, cudaStream_t st)
 {
     // Few (column, tile) pairs: one warp per block so that the work spreads over all 148 SMs; otherwise 4.
-    const int wpb = ((int64_t)ncol * m->ntile >= 148 * 16) ? 4 : 1;
+    const int wpb = 1;  // one warp per block: column-uniform addressing; up to 32 blocks resident per SM
     col_zero_bits_kernel<<<(ncol + 127) / 128, 128, 0, st>>>(reinterpret_cast<unsigned long long *>(b->dJ), b->done,
                                                            nullptr, 0, col0, ncol);
     m->launches += 1;
@@ -839,7 +839,12 @@ static int launch_fs(const mali_model *m, const mali_buffers *b, int col0, int n
     FinishParams f = make_finish_params(m, b, col0, ncol);
     dim3 grid((m->N + 63) / 64, m->Natom, ncol);
     gamma_finish_kernel<<<grid, 64, 0, st>>>(f);
-    m->launches += 1;
+    {
+        const int nb = (int)std::min<int64_t>(16, (m->lay.J + 255) / 256);
+        j_finish_kernel<<<dim3(nb, ncol), 256, 0, st>>>(b->J, m->lay.J, b->scratch, m->lay.scratch, m->off_jpart,
+                                                      reinterpret_cast<unsigned long long *>(b->dJ), b->done, col0);
+    }
+    m->launches += 2;
     CU(cudaGetLastError());
     return MALI_OK;
 }

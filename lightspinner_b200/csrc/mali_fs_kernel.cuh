@@ -103,11 +103,11 @@ __global__ void __launch_bounds__(128, (TMAX <= 4) ? MALI_MINB4 : MALI_MINB8) fs
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const FsCommon &p = P.c;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int col = p.col0 + blockIdx.y * p.warpsPerBlock + warp;
+    const int col = p.col0 + blockIdx.x * p.warpsPerBlock + warp;
     if (col >= p.col0 + p.ncol) return;
     if (p.done != nullptr && p.done[col] != 0) return;
 
-    const TileC<TMAX> &T = P.tiles[blockIdx.x];
+    const TileC<TMAX> &T = P.tiles[blockIdx.y];
     const int N = p.N, Nrays = p.Nrays, Nspect = p.Nspect;
     const int nslot = T.nslot;
     const int ls = lane / Nrays, mu = lane - ls * Nrays;
@@ -191,8 +191,6 @@ __global__ void __launch_bounds__(128, (TMAX <= 4) ? MALI_MINB4 : MALI_MINB8) fs
             }
         }
     }
-
-    unsigned long long dJb = 0ull;
 
     for (int d = 0; d < 2; ++d) {
         const int dk = d ? -1 : 1;
@@ -375,16 +373,8 @@ __global__ void __launch_bounds__(128, (TMAX <= 4) ? MALI_MINB4 : MALI_MINB8) fs
                 } else {
                     for (int m = 1; m < Nrays; ++m) sum += __shfl_down_sync(0xffffffffu, x, m);
                 }
-                if (leader) {
-                    if (d == 0) {
-                        __stcg(Jpart + klc, sum);
-                    } else {
-                        const double Jn = jOld + sum;
-                        Jcol[klc] = Jn;
-                        const unsigned long long b = absbits(1.0 - Jdag / Jn);
-                        dJb = b > dJb ? b : dJb;
-                    }
-                }
+                // down: store the partial; up: complete it.  j_finish_kernel then forms dJ and moves Jpart -> J
+                if (leader) __stcg(Jpart + klc, d == 0 ? sum : jOld + sum);
             }
 
             // ---- (4) Gamma integrands, rh_method.py:643-681
@@ -436,12 +426,6 @@ __global__ void __launch_bounds__(128, (TMAX <= 4) ? MALI_MINB4 : MALI_MINB8) fs
         if (d == 1 && valid) p.I[(size_t)col * p.IStride + (size_t)la * Nrays + mu] = sw.Iupw;
     }
 
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        const unsigned long long o = __shfl_xor_sync(0xffffffffu, dJb, off);
-        dJb = o > dJb ? o : dJb;
-    }
-    if (lane == 0) atomicMax(p.dJbits + col, dJb);
 }
 
 }  // namespace mali

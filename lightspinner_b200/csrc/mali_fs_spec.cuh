@@ -79,6 +79,32 @@ __device__ __forceinline__ double reduce_scatter_n(double (&v)[M], int lane)
     return v[0];
 }
 
+// Warp reduce-scatter through shared memory: every lane stores its M values, then lane L sums 32/M... see below.
+// red: per-warp scratch of M rows x 36 doubles (lane l of a row sits at l + l/8: conflict-free stores and loads).
+// After the call the lane holds the total over the 32 lanes of value index L / (32/M).  Fixed order -> deterministic.
+template <int M>
+__device__ __forceinline__ double reduce_transpose(const double (&v)[M], int lane, double *red)
+{
+    constexpr int G = 32 / M;      // lanes that share one value after the reduction
+    constexpr int SEG = 32 / G;    // source lanes each of them sums
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < M; ++q) red[q * 36 + lane + (lane >> 3)] = v[q];
+    __syncwarp();
+    const int e = lane / G, part = lane % G;
+    const double *row = red + e * 36;
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < SEG; ++i) {
+        const int l = part * SEG + i;
+        const double x = row[l + (l >> 3)];
+        acc = (i == 0) ? x : acc + x;
+    }
+#pragma unroll
+    for (int off = G / 2; off > 0; off >>= 1) acc = acc + __shfl_xor_sync(0xffffffffu, acc, off);
+    return acc;
+}
+
 // SPEC is a tag type with a `static constexpr TileStruct S` member (the structure travels inside a type).
 template <class SPEC, int NSP>
 __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, unsigned char *smem_raw)
@@ -89,8 +115,9 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
     constexpr int NLV = S.nlev > 0 ? S.nlev : 1;
     constexpr int NA = S.natom > 0 ? S.natom : 1;
     constexpr int M = spec_pow2(2 * NS);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int col = p.col0 + blockIdx.x * p.warpsPerBlock + warp;
+    // one warp per block: the column (hence every base pointer) is block-uniform -> uniform-register addressing
+    const int warp = 0, lane = threadIdx.x;
+    const int col = p.col0 + blockIdx.x;
     if (col >= p.col0 + p.ncol) return;
     if (p.done != nullptr && p.done[col] != 0) return;
 
@@ -112,6 +139,7 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
     unsigned char *wbase = smem_raw + (size_t)warp * p.smemBytesPerWarp;
     double *sN = reinterpret_cast<double *>(wbase);
     double *sZ = sN + p.zOffDoubles;
+    double *red = sN + p.lvlOffDoubles;  // Gamma reduce scratch (shares the level-array slot of the class kernels)
     {
         const double *gN = p.pops + (size_t)col * p.popStride;
         const double *gZ = cc + p.off_z;
@@ -172,8 +200,6 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
             cw[tt] = (__ldg(p.wlacont + s.toff + lt) * hw) * fourPi;
         }
     }
-
-    unsigned long long dJb = 0ull;
 
     for (int d = 0; d < 2; ++d) {
         const int dk = d ? -1 : 1;
@@ -333,16 +359,8 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
                 } else {
                     for (int m = 1; m < Nrays; ++m) sum += __shfl_down_sync(0xffffffffu, x, m);
                 }
-                if (leader) {
-                    if (d == 0) {
-                        __stcg(Jpart + klc, sum);
-                    } else {
-                        const double Jn = jOld + sum;
-                        Jcol[klc] = Jn;
-                        const unsigned long long b = absbits(1.0 - Jdag / Jn);
-                        dJb = b > dJb ? b : dJb;
-                    }
-                }
+                // down: store the partial; up: complete it.  j_finish_kernel then forms dJ and moves Jpart -> J
+                if (leader) __stcg(Jpart + klc, d == 0 ? sum : jOld + sum);
             }
 
             // ---- (4) Gamma integrands, rh_method.py:643-681
@@ -371,19 +389,13 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
                     v[2 * tt] = g1 * wlamu;  // inactive lanes: wlamu == 0
                     v[2 * tt + 1] = g2 * wlamu;
                 }
-                const double tot = reduce_scatter_n<M>(v, lane);
+                const double tot = reduce_transpose<M>(v, lane, red);
                 if (writer) __stcg(gdst, d == 0 ? tot : gOld + tot);
             }
         }
         if (d == 1 && valid) p.I[(size_t)col * p.IStride + (size_t)la * Nrays + mu] = sw.Iupw;
     }
 
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        const unsigned long long o = __shfl_xor_sync(0xffffffffu, dJb, off);
-        dJb = o > dJb ? o : dJb;
-    }
-    if (lane == 0) atomicMax(p.dJbits + col, dJb);
 }
 
 // ---- registry of ahead-of-time instances -----------------------------------------------------------------

@@ -211,8 +211,6 @@ __global__ void __launch_bounds__(128) fs_gamma_kernel(const FsParams p)
     const double bbc0 = cc[p.off_bbc + 2 * laC], bbc1 = cc[p.off_bbc + 2 * laC + 1];
     const double fourPi = 4.0 * kPi;  // (x*4)*pi == x*(4*pi) exactly: scaling by 4 commutes with rounding
 
-    unsigned long long dJb = 0ull;
-
     for (int d = 0; d < 2; ++d) {
         const int dk = d ? -1 : 1;
         const int kS = d ? N - 1 : 0;
@@ -285,16 +283,8 @@ __global__ void __launch_bounds__(128) fs_gamma_kernel(const FsParams p)
                 const double x = valid ? hw * Ik : 0.0;
                 double sum = x;
                 for (int m = 1; m < Nrays; ++m) sum += __shfl_down_sync(0xffffffffu, x, m);
-                if (leader) {
-                    if (d == 0) {
-                        __stcg(Jpart + kl, sum);
-                    } else {
-                        const double Jn = __ldcg(Jpart + kl) + sum;
-                        Jcol[kl] = Jn;
-                        const unsigned long long b = absbits(1.0 - Jdag / Jn);
-                        dJb = b > dJb ? b : dJb;
-                    }
-                }
+                // down: store the partial; up: complete it.  j_finish_kernel then forms dJ and moves Jpart -> J
+                if (leader) __stcg(Jpart + kl, d == 0 ? sum : __ldcg(Jpart + kl) + sum);
             }
 
             // ---- (4) Gamma integrands: rh_method.py:643-681
@@ -350,16 +340,40 @@ __global__ void __launch_bounds__(128) fs_gamma_kernel(const FsParams p)
         if (d == 1 && valid) p.I[(size_t)col * p.IStride + (size_t)la * Nrays + mu] = sw.Iupw;
     }
 
-    // dJ = max |1 - JDag/J| (rh_method.py:705-706)
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        const unsigned long long o = __shfl_xor_sync(0xffffffffu, dJb, off);
-        dJb = o > dJb ? o : dJb;
-    }
-    if (lane == 0) atomicMax(p.dJbits + col, dJb);
 #undef CHI_L
 #undef U_L
 #undef ETA_A
+}
+
+// --------------------------------------------------------------------------------------------------------
+// dJ = max |1 - JDag/J| (rh_method.py:705-706) and J <- the new mean intensity the sweeps accumulated in Jpart.
+// Elementwise over one column's [Nspace][Nspect] plane; block max -> one atomicMax per block.
+__global__ void j_finish_kernel(double *J, int64_t JStride, const double *scratch, int64_t scratchStride,
+                                int64_t offJpart, unsigned long long *dJbits, const int32_t *done, int col0)
+{
+    const int col = col0 + blockIdx.y;
+    if (done != nullptr && done[col] != 0) return;
+    double *Jc = J + (size_t)col * JStride;
+    const double *Jn = scratch + (size_t)col * scratchStride + offJpart;
+    unsigned long long b = 0ull;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < JStride; q += (int64_t)gridDim.x * blockDim.x) {
+        const double jn = Jn[q];
+        const unsigned long long v = absbits(1.0 - Jc[q] / jn);
+        b = v > b ? v : b;
+        Jc[q] = jn;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(0xffffffffu, b, off);
+        b = o > b ? o : b;
+    }
+    __shared__ unsigned long long wmax[8];
+    if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = b;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) b = wmax[w] > b ? wmax[w] : b;
+        atomicMax(dJbits + col, b);
+    }
 }
 
 // --------------------------------------------------------------------------------------------------------
