@@ -97,7 +97,8 @@ typedef struct {
     double *scratch;   /* [ncol][layout.scratch]  */
     double *dJ;        /* [ncol] max |1 - Jold/Jnew| of the last formal solution (NaN-propagating) */
     double *dPops;     /* [ncol] max |1 - nold/nnew| of the last stat_equil */
-    int32_t *status;   /* [ncol] bit 0: a singular / non-finite statistical-equilibrium system was met */
+    int32_t *status;   /* [ncol] bit 0: a singular / non-finite statistical-equilibrium system was met;
+                          bit 1: an opacity / optical-depth step left [2^-1000, 2^1000] (formal solution invalid) */
     int32_t *iter;     /* [ncol] iterations done by mali_iterate */
     int32_t *done;     /* [ncol] non-zero: column is skipped by the compute entry points (converged) */
 } mali_buffers;
@@ -149,6 +150,9 @@ int mali_piecewise_linear_1d(int32_t Nspace, int32_t nray, const double *z_dev, 
 /* y[i] = exp(x[i]) with the kernel's own exp (valid for 2^-54 <= |x| < 512): must equal libm's exp bit for bit,
  * which is what numba calls in formal_solver.py:41. */
 int mali_exp_hook(int32_t n, const double *x_dev, double *y_dev, void *stream);
+/* q[i] = a[i] / b[i] with the kernels' shared-reciprocal division; bad[i] != 0 where (a, b) is outside its domain.
+ * Must equal the IEEE quotient bit for bit inside the domain. */
+int mali_div_hook(int32_t n, const double *a_dev, const double *b_dev, double *q_dev, int32_t *bad_dev, void *stream);
 /* ComputationalTransition.uv(la, mu, toFrom) for transition t of column col: writes Uji, Vij, Vji [Nspace]. */
 int mali_uv(const mali_model *m, const mali_buffers *bufs, int32_t col, int32_t t, int32_t la, int32_t mu,
             int32_t toFrom, double *Uji_dev, double *Vij_dev, double *Vji_dev, void *stream);

@@ -234,6 +234,7 @@ static FsCommon make_fs_common(const mali_model *m, const mali_buffers *b, int c
     c.I = b->I;
     c.scratch = b->scratch;
     c.dJbits = reinterpret_cast<unsigned long long *>(b->dJ);
+    c.status = b->status;
     c.done = b->done;
     return c;
 }
@@ -755,6 +756,7 @@ static FsParams make_fs_params(const mali_model *m, const mali_buffers *b, int c
     p.I = b->I;
     p.scratch = b->scratch;
     p.dJbits = reinterpret_cast<unsigned long long *>(b->dJ);
+    p.status = b->status;
     p.done = b->done;
     return p;
 }
@@ -948,6 +950,14 @@ int mali_profile_end(const mali_model *m, double *fs_ms_total, int32_t *fs_launc
 }
 
 long long mali_launch_count(const mali_model *m) { return m ? m->launches : 0; }
+
+int mali_div_hook(int32_t n, const double *a_dev, const double *b_dev, double *q_dev, int32_t *bad_dev, void *stream)
+{
+    if (n < 1 || !a_dev || !b_dev || !q_dev || !bad_dev) return fail(MALI_EINVAL, "mali_div_hook: bad argument");
+    div_hook_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, a_dev, b_dev, q_dev, bad_dev);
+    CU(cudaGetLastError());
+    return MALI_OK;
+}
 
 int mali_exp_hook(int32_t n, const double *x_dev, double *y_dev, void *stream)
 {

@@ -56,6 +56,7 @@ struct FsCommon {
     const double *colconst, *pops;
     double *J, *I, *scratch;
     unsigned long long *dJbits;
+    int32_t *status;
     const int32_t *done;
 };
 
@@ -350,7 +351,8 @@ __global__ void __launch_bounds__(128, (TMAX <= 4) ? MALI_MINB4 : MALI_MINB8) fs
                 }
             }
             chiTot += bgc;
-            const double S = (etaTot + bge + bgs * Jdag) / chiTot;
+            const double rchi = rcp_full(chiTot);
+            const double S = div_by(etaTot + bge + bgs * Jdag, chiTot, rchi);
 
             // ---- (2) short characteristic
             const double zk = sZ[k];
@@ -358,7 +360,7 @@ __global__ void __launch_bounds__(128, (TMAX <= 4) ? MALI_MINB4 : MALI_MINB8) fs
             if (s == 0)
                 sw.first(d != 0, zmu, chiTot, S, zk, chiProbe, sZ[kS + dk], bbc0, bbc1, Ik, Psi);
             else
-                sw.step(s == N - 1, zmu, chiTot, S, zk, Ik, Psi);
+                sw.step(s == N - 1, zmu, chiTot, rchi, S, zk, Ik, Psi);
 
             // ---- (3) J, rh_method.py:640
             {
@@ -424,6 +426,7 @@ __global__ void __launch_bounds__(128, (TMAX <= 4) ? MALI_MINB4 : MALI_MINB8) fs
             }
         }
         if (d == 1 && valid) p.I[(size_t)col * p.IStride + (size_t)la * Nrays + mu] = sw.Iupw;
+        if (valid && sw.bad && p.status != nullptr) atomicOr(p.status + col, 2);
     }
 
 }

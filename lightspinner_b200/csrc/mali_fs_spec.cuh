@@ -41,7 +41,7 @@ struct SlotR {  // run-time part of a slot, warp-uniform (constant bank), 40 B
 // tile's structure id (a warp-uniform switch), so a whole class is ONE launch however many structures it holds.
 __host__ __device__ constexpr int spec_class(int nslot) { return nslot <= 2 ? 0 : (nslot <= 4 ? 1 : 2); }
 __host__ __device__ constexpr int spec_class_slots(int cls) { return cls == 0 ? 2 : (cls == 1 ? 4 : 8); }
-__host__ __device__ constexpr int spec_class_minblocks(int cls) { return cls == 0 ? 4 : (cls == 1 ? 3 : 2); }
+__host__ __device__ constexpr int spec_class_minblocks(int cls) { return cls == 0 ? 5 : (cls == 1 ? 4 : 3); }
 __host__ __device__ constexpr int spec_pow2(int x) { return x <= 2 ? 2 : (x <= 4 ? 4 : (x <= 8 ? 8 : 16)); }
 
 template <int NSP>
@@ -336,7 +336,8 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
                 etaTot = (tt == 0) ? eta_t : etaTot + eta_t;
             }
             chiTot += bgc;
-            const double Ssrc = (etaTot + bge + bgs * Jdag) / chiTot;
+            const double rchi = rcp_full(chiTot);
+            const double Ssrc = div_by(etaTot + bge + bgs * Jdag, chiTot, rchi);
 
             // ---- (2) short characteristic
             const double zk = sZ[k];
@@ -344,7 +345,7 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
             if (s == 0)
                 sw.first(d != 0, zmu, chiTot, Ssrc, zk, chiProbe, sZ[kS + dk], bbc0, bbc1, Ik, Psi);
             else
-                sw.step(s == N - 1, zmu, chiTot, Ssrc, zk, Ik, Psi);
+                sw.step(s == N - 1, zmu, chiTot, rchi, Ssrc, zk, Ik, Psi);
 
             // ---- (3) J, rh_method.py:640
             {
@@ -394,6 +395,7 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
             }
         }
         if (d == 1 && valid) p.I[(size_t)col * p.IStride + (size_t)la * Nrays + mu] = sw.Iupw;
+        if (valid && sw.bad && p.status != nullptr) atomicOr(p.status + col, 2);
     }
 
 }

@@ -57,6 +57,53 @@ __global__ void exp_hook_kernel(int n, const double *x, double *y)
 }
 
 // --------------------------------------------------------------------------------------------------------
+// Correctly rounded fp64 division with a SHARED reciprocal.  The formal solver divides twice by the same optical
+// depth step (dS = (S' - S)/dtau, w1/dtau) and twice by the same opacity (S = .../chi, Psi = Lambda/chi); nvcc's
+// a / b expands to: 20-bit reciprocal seed, two Newton steps to a full-precision reciprocal r, q0 = a r,
+// rem = fma(-b, q0, a), q = fma(r, rem, q0) -- exactly rounded for normal-range operands -- plus a branch to a slow
+// path for subnormal / overflowing cases.  rcp_full() is that reciprocal, div_by() that quotient: 3 dependent
+// operations per division instead of 9, no branch in the instruction stream.  Domain (always met by physical
+// opacities / source functions; checked by div_domain_ok and reported through the column status word):
+// b finite, normal, non-zero; a == 0 or 2^-969 <= |a|; |a / b| normal.
+// tests: test_gpu_parity.py::test_shared_reciprocal_division_bitwise compares with a / b bit for bit.
+__device__ __forceinline__ double rcp_full(double b)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    r = __hiloint2double(__double2hiint(r), 1);  // nvcc's own division seeds the low word with 1 (MUFU.RCP64H + MOV)
+    double e = __fma_rn(-b, r, 1.0);
+    e = __fma_rn(e, e, e);
+    r = __fma_rn(r, e, r);
+    e = __fma_rn(-b, r, 1.0);
+    return __fma_rn(r, e, r);
+}
+
+__device__ __forceinline__ double div_by(double a, double b, double r)
+{
+    const double q0 = __dmul_rn(a, r);
+    const double rem = __fma_rn(-b, q0, a);
+    return __fma_rn(r, rem, q0);
+}
+
+__device__ __forceinline__ bool div_domain_ok(double a, double b, double q)
+{
+    const double aa = fabs(a), ab = fabs(b), aq = fabs(q);
+    const bool b_ok = ab >= 0x1p-1000 && ab <= 0x1p1000;
+    const bool a_ok = (a == 0.0) || (aa >= 0x1p-969 && aa <= 0x1p1000);
+    const bool q_ok = (a == 0.0) || (aq >= 0x1p-1021 && aq <= 0x1p1022);
+    return b_ok && a_ok && q_ok;
+}
+
+__global__ void div_hook_kernel(int n, const double *a, const double *b, double *q, int *bad)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double r = rcp_full(b[i]);
+    q[i] = div_by(a[i], b[i], r);
+    bad[i] = div_domain_ok(a[i], b[i], q[i]) ? 0 : 1;
+}
+
+// --------------------------------------------------------------------------------------------------------
 // formal_solver.py:14-44
 __device__ __forceinline__ void w2(double dtau, double &w0, double &w1)
 {
@@ -77,6 +124,14 @@ __device__ __forceinline__ void w2(double dtau, double &w0, double &w1)
 // The caller supplies chi, S at the current point in sweep order; step() returns I and PsiStar = LambdaStar/chi there.
 struct Sweep {
     double Iupw, chiPrev, SPrev, zPrev, w0, w1;
+    unsigned bad;  // sticky: a divisor left the domain of the shared-reciprocal division (reported via status bit 1)
+
+    __device__ __forceinline__ static unsigned out_of_range(double b)
+    {
+        // exponent of |b| outside [2^-1000, 2^1000] (also catches 0, subnormals, inf, NaN)
+        const unsigned e = ((unsigned)__double2hiint(b) >> 20) & 0x7ffu;
+        return (e - 23u) > 2000u ? 1u : 0u;
+    }
 
     // first point of the sweep (k = kStart).  chiNext = chi[kStart+dk] is only needed for the upgoing boundary.
     __device__ __forceinline__ void first(bool up, double zmu, double chi, double S, double z, double chiNext,
@@ -94,16 +149,21 @@ struct Sweep {
         zPrev = z;
         w0 = 0.0;
         w1 = 0.0;
+        bad = 0u;
         I = Iupw;
         Psi = 0.0 / chi;  // LambdaStar[kStart] = 0
     }
 
     // interior point (formal_solver.py:120-135) or, with last = true, the final point with the reference's
-    // stale-w / S[kEnd-dk] behaviour (formal_solver.py:137-139).
-    __device__ __forceinline__ void step(bool last, double zmu, double chi, double S, double z, double &I, double &Psi)
+    // stale-w / S[kEnd-dk] behaviour (formal_solver.py:137-139).  rchi = rcp_full(chi) (shared with the caller's
+    // S = .../chi); the two divisions by dtau share one reciprocal as well.
+    __device__ __forceinline__ void step(bool last, double zmu, double chi, double rchi, double S, double z, double &I,
+                                         double &Psi)
     {
         const double dtau = 0.5 * (chiPrev + chi) * zmu * fabs(zPrev - z);
-        const double dS = (SPrev - S) / dtau;
+        const double rdt = rcp_full(dtau);
+        bad |= out_of_range(dtau) | out_of_range(chi);
+        const double dS = div_by(SPrev - S, dtau, rdt);
         double Ik, Lam;
         if (!last) {
             w2(dtau, w0, w1);
@@ -111,13 +171,13 @@ struct Sweep {
         } else {
             Ik = (1.0 - w0) * Iupw + w0 * SPrev + w1 * dS;
         }
-        Lam = w0 - w1 / dtau;
+        Lam = w0 - div_by(w1, dtau, rdt);
         Iupw = Ik;
         chiPrev = chi;
         SPrev = S;
         zPrev = z;
         I = Ik;
-        Psi = Lam / chi;
+        Psi = div_by(Lam, chi, rchi);
     }
 };
 
@@ -268,7 +328,8 @@ __global__ void __launch_bounds__(128) fs_gamma_kernel(const FsParams p)
                 continue;
             }
             const double Jdag = Jcol[kl];
-            const double S = (etaTot + __ldg(bgeta + kl) + __ldg(bgsca + kl) * Jdag) / chiTot;
+            const double rchi = rcp_full(chiTot);
+            const double S = div_by(etaTot + __ldg(bgeta + kl) + __ldg(bgsca + kl) * Jdag, chiTot, rchi);
 
             // ---- (2) short characteristic: formal_solver.py
             const double zk = zz[k];
@@ -276,7 +337,7 @@ __global__ void __launch_bounds__(128) fs_gamma_kernel(const FsParams p)
             if (s == 0)
                 sw.first(d != 0, zmu, chiTot, S, zk, chiProbe, zz[kS + dk], bbc0, bbc1, Ik, Psi);
             else
-                sw.step(s == N - 1, zmu, chiTot, S, zk, Ik, Psi);
+                sw.step(s == N - 1, zmu, chiTot, rchi, S, zk, Ik, Psi);
 
             // ---- (3) J: rh_method.py:640.  Sum over the Nrays lanes of this wavelength in mu order.
             {
@@ -338,6 +399,7 @@ __global__ void __launch_bounds__(128) fs_gamma_kernel(const FsParams p)
         }
         // emergent intensity: rh_method.py:638 (the upgoing value survives)
         if (d == 1 && valid) p.I[(size_t)col * p.IStride + (size_t)la * Nrays + mu] = sw.Iupw;
+        if (valid && sw.bad && p.status != nullptr) atomicOr(p.status + col, 2);
     }
 
 #undef CHI_L
@@ -478,7 +540,7 @@ __global__ void sweep_hook_kernel(int N, int nray, const double *z, const double
     Psi[(size_t)r * N + kS] = Pk;
     for (int q = 1; q < N; ++q) {
         const int k = kS + q * dk;
-        sw.step(q == N - 1, zmu, c[k], s[k], z[k], Ik, Pk);
+        sw.step(q == N - 1, zmu, c[k], rcp_full(c[k]), s[k], z[k], Ik, Pk);
         I[(size_t)r * N + k] = Ik;
         Psi[(size_t)r * N + k] = Pk;
     }

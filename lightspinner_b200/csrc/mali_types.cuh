@@ -65,6 +65,7 @@ struct FsParams {
     const double *pops;
     double *J, *I, *scratch;
     unsigned long long *dJbits;
+    int32_t *status;      // may be null; bit 1: a divisor left the fast-division domain
     const int32_t *done;  // may be null
 };
 

@@ -123,7 +123,14 @@ class MaliEngine:
     def formal_sol_gamma_matrices(self):
         """One Lambda iteration for every column; returns dJ per column (device->host read of ncol doubles)."""
         self.formal_sol_gamma_async()
-        return self.t_dJ.cpu().numpy()
+        dJ = self.t_dJ.cpu().numpy()
+        status = self.t_status.cpu().numpy()
+        if (status & 2).any():
+            bad = np.nonzero(status & 2)[0]
+            self.t_status.bitwise_and_(~2)
+            raise FloatingPointError('opacity or optical-depth step outside the formal solver\'s numeric domain '
+                                     '(zero, subnormal, infinite or NaN) in column(s) %s' % bad[:8].tolist())
+        return dJ
 
     def stat_equil(self):
         self.stat_equil_async()
@@ -229,3 +236,16 @@ def exp_hook(x, device=None):
         _capi.check(_capi.load().mali_exp_hook(tx.numel(), C.c_void_p(tx.data_ptr()), C.c_void_p(ty.data_ptr()),
                                                C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
     return ty.cpu().numpy()
+
+
+def div_hook(a, b, device=None):
+    """The kernels' shared-reciprocal division on the GPU (test hook): returns (q, bad)."""
+    dev = torch.device('cuda', torch.cuda.current_device() if device is None else device)
+    ta = torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
+    tb = torch.as_tensor(np.ascontiguousarray(b, dtype=np.float64)).to(dev)
+    tq = torch.empty_like(ta)
+    tbad = torch.zeros(ta.numel(), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _capi.check(_capi.load().mali_div_hook(ta.numel(), *(C.c_void_p(t.data_ptr()) for t in (ta, tb, tq, tbad)),
+                                               C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    return tq.cpu().numpy(), tbad.cpu().numpy()

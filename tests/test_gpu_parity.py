@@ -333,3 +333,29 @@ def test_warm_started_context_via_eqpops_alias(eng_mod):
     assert i == int(r['niter'])
     assert relerr(ctx.I, r['final_I']) < TOL_FINAL
     ctx.close()
+
+
+def test_shared_reciprocal_division_bitwise(eng_mod):
+    """The formal solver's shared-reciprocal division == IEEE a / b, bit for bit, inside its documented domain
+    (and the domain check flags everything outside it)."""
+    rng = np.random.default_rng(99)
+    n = 2_000_000
+    a = np.exp(rng.uniform(-60, 60, n)) * rng.choice([-1.0, 1.0], n)
+    b = np.exp(rng.uniform(-60, 60, n)) * rng.choice([-1.0, 1.0], n)
+    # adversarial significands: near powers of two, all-ones mantissas, ties
+    m = 200_000
+    a[:m] = np.ldexp(1.0 + rng.integers(0, 8, m) * 2.0 ** -52, rng.integers(-200, 200, m))
+    b[:m] = np.ldexp(2.0 - rng.integers(1, 8, m) * 2.0 ** -52, rng.integers(-200, 200, m))
+    a[m:2 * m] = np.ldexp(rng.integers(1, 2 ** 53, m).astype(np.float64), rng.integers(-300, 200, m))
+    b[m:2 * m] = np.ldexp(rng.integers(1, 2 ** 53, m).astype(np.float64), rng.integers(-300, 200, m))
+    a[2 * m:2 * m + 1000] = 0.0
+    q, bad = eng_mod.div_hook(a, b)
+    assert not bad.any()
+    with np.errstate(all='ignore'):
+        ref = a / b
+    assert np.array_equal(q, ref), 'differs in %d of %d' % ((q != ref).sum(), n)
+    # outside the domain the check must fire
+    a2 = np.array([1e-300, 1.0, 1.0, np.inf, 1.0, 5e-324])
+    b2 = np.array([1e10, 0.0, np.inf, 1.0, 1e-320, 1.0])
+    q2, bad2 = eng_mod.div_hook(a2, b2)
+    assert bad2.all()
