@@ -337,13 +337,43 @@ def main():
                'sample': '%d of the %d synthetic columns x %d MALI iterations, oracle C restatement with OpenMP '
                          'over columns, %.1f s' % (ncol_cpu, ncol, iters, dt)}
 
+    # ---- BASELINE configs 1/2 on the side: one CaII/FALC column to convergence (latency-bound by construction)
+    single = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            c1 = load_base('c1_falc_ca')
+            e1 = MaliEngine(c1, 1, device=local)
+            e1.upload([c1])
+            out = {}
+            for mode in ('host_loop', 'device_loop'):
+                e1.upload([c1])
+                e1.reset_iteration_state()
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                if mode == 'host_loop':       # test.py:20-29 driven from Python, two scalar reads per iteration
+                    dJ, dP, it = 1.0, 1.0, 0
+                    while (dJ > 2e-3 or dP > 1e-3) and it < 500:
+                        it += 1
+                        dJ = float(e1.formal_sol_gamma_matrices()[0])
+                        if it > 3:
+                            dP = float(e1.stat_equil()[0])
+                else:                         # mali_iterate: the loop stays on the device
+                    e1.iterate_async(64)
+                    torch.cuda.synchronize(dev)
+                    it = int(e1.t_iter.cpu()[0])
+                out[mode] = {'iterations': it, 'seconds': time.perf_counter() - t0}
+            single = {'config': 'CaII/FALC single column (test.py problem), to convergence', **out}
+            e1.close()
+        except Exception as ex:   # never let the side measurement break the main line
+            single = {'error': repr(ex)}
+
     if rank == 0:
         cfg = workload_config(args, base)
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
                 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': cfg, 'clocks': clocks,
                 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu,
-                'results_finite': finite}
+                'single_column': single, 'results_finite': finite}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

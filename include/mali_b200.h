@@ -129,7 +129,8 @@ int mali_stat_equil(const mali_model *m, const mali_buffers *bufs, int32_t col0,
 /* The loop of test.py:20-29 kept on the device: up to max_iter iterations of formal solution (+ stat_equil once
  * a column's own iteration counter exceeds 3); a column whose (dJ, dPops) satisfy dJ <= tolJ && dPops <= tolPops
  * is flagged done and no longer touched.  tolJ < 0 disables the convergence test (fixed iteration count).
- * Captured into a CUDA graph per (model, ncol) internally.  bufs->iter / done must be zeroed by the caller first. */
+ * All launches are asynchronous on `stream`; no host synchronisation happens inside.  bufs->iter / done must be
+ * zeroed and bufs->dPops set to 1.0 by the caller first (dPops stays 1.0 until a column's first stat_equil). */
 int mali_iterate(const mali_model *m, const mali_buffers *bufs, int32_t col0, int32_t ncol, int32_t max_iter,
                  double tolJ, double tolPops, void *stream);
 

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIBDIR = os.path.join(HERE, '_lib')
-LIB = os.path.join(LIBDIR, 'libmali_b200.so')
+LIB = os.path.join(LIBDIR, os.environ.get('MALI_LIB_NAME', 'libmali_b200.so'))
 SOURCES = ['mali_api.cu']
 DEPS = ['mali_api.cu', 'mali_kernels.cuh', 'mali_types.cuh', 'exp_table.inc', 'mali_solve.h', 'mali_fs_kernel.cuh', 'mali_fs_spec.cuh', 'spec_instances.inc', os.path.join('..', '..', 'include', 'mali_b200.h')]
 

@@ -98,7 +98,7 @@ static const SpecEntry kSpecRegistry[] = {
 namespace mali {
 // One kernel per register class; the structure id of the tile selects the specialised body (uniform switch).
 template <int CLS>
-__global__ void __launch_bounds__(32, 4 * spec_class_minblocks(CLS)) fs_gamma_kernel_m(const __grid_constant__ MegaParams<CLS> P)
+__global__ void __launch_bounds__(32, spec_class_warps(CLS)) fs_gamma_kernel_m(const __grid_constant__ MegaParams<CLS> P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // blockIdx.x runs over column groups, blockIdx.y over tiles: co-resident blocks share a structure -> one

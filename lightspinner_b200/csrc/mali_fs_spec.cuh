@@ -41,7 +41,17 @@ struct SlotR {  // run-time part of a slot, warp-uniform (constant bank), 40 B
 // tile's structure id (a warp-uniform switch), so a whole class is ONE launch however many structures it holds.
 __host__ __device__ constexpr int spec_class(int nslot) { return nslot <= 2 ? 0 : (nslot <= 4 ? 1 : 2); }
 __host__ __device__ constexpr int spec_class_slots(int cls) { return cls == 0 ? 2 : (cls == 1 ? 4 : 8); }
-__host__ __device__ constexpr int spec_class_minblocks(int cls) { return cls == 0 ? 5 : (cls == 1 ? 4 : 3); }
+// resident warps per SM requested from ptxas (blocks are single warps): sets the register budget per class
+#ifndef MALI_OCC0
+#define MALI_OCC0 16
+#endif
+#ifndef MALI_OCC1
+#define MALI_OCC1 12
+#endif
+#ifndef MALI_OCC2
+#define MALI_OCC2 8
+#endif
+__host__ __device__ constexpr int spec_class_warps(int cls) { return cls == 0 ? MALI_OCC0 : (cls == 1 ? MALI_OCC1 : MALI_OCC2); }
 __host__ __device__ constexpr int spec_pow2(int x) { return x <= 2 ? 2 : (x <= 4 ? 4 : (x <= 8 ? 8 : 16)); }
 
 template <int NSP>
