@@ -54,6 +54,14 @@ def algorithmic_bytes_per_column(p):
     return 8 * (2 * line_nl * R * N + 5 * S * N + int(((2 * nl * nl + 2 * nl + 1) * N).sum()) + S * R)
 
 
+def algorithmic_flops_per_column(p):
+    """F = 2 [31 + 28 A] fp64 operations per unit, A = mean active transitions per wavelength."""
+    tr = np.asarray(p['trans'])
+    S, R, N = int(p['Nspect']), int(p['Nrays']), int(p['Nspace'])
+    abar = float(tr[:, 5].sum()) / S
+    return 2.0 * (31.0 + 28.0 * abar) * S * R * N
+
+
 def measured_peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.isfile(path):
@@ -278,6 +286,15 @@ def main():
                 'algorithmic_bytes_per_launch': alg_bytes, 'mean_launch_ms': fs_ms_mean, 'launches_timed': fs_n,
                 'share_of_step': fs_ms / ms if ms > 0 else None,
                 'note': 'fp64 CUDA-core work binds before HBM on this path (SURVEY.md 7.3-2); see DESIGN.md'}
+    try:    # the roof that actually binds: unfused fp64 on the CUDA cores, peak measured live
+        from lightspinner_b200.engine import fp64_peak
+        pk = fp64_peak(local)
+        fl = algorithmic_flops_per_column(base) * ncol / (fs_ms_mean * 1e-3)
+        roofline['fp64'] = {'achieved': fl / 1e12, 'peak': pk / 1e12, 'unit': 'Tflop/s (unfused mul/add)',
+                            'frac': fl / pk, 'algorithmic_flops_per_launch': algorithmic_flops_per_column(base) * ncol,
+                            'peak_source': 'measured live (mali_fp64_peak: 8 independent mul+add chains per thread)'}
+    except Exception as ex:
+        roofline['fp64'] = {'error': repr(ex)}
 
     # ---- e2e: host buffers -> H2D -> re-layout -> iterate -> D2H, double-buffered over column chunks
     e2e = None

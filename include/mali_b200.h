@@ -141,6 +141,10 @@ int mali_profile_begin(const mali_model *m, int32_t max_launches);
 int mali_profile_end(const mali_model *m, double *fs_ms_total, int32_t *fs_launches);
 long long mali_launch_count(const mali_model *m);
 
+/* fp64 CUDA-core peak probe: unfused mul + add operations per second on the current device (roofline denominator;
+ * MEASURED_PEAKS.json has no fp64 entry). */
+int mali_fp64_peak(int32_t iters, double *scratch_dev, double *ops_per_second);
+
 /* Test hooks ---------------------------------------------------------------------------------------------- */
 /* piecewise_linear_1d for nray independent rays: chi, S, I, Psi are [nray][Nspace]; muz, bbc0/bbc1 (planck at
  * T[-2], T[-1]) and toFrom are per ray; z is [Nspace] (shared). */

@@ -41,7 +41,7 @@ class Buffers(C.Structure):
 EXPORTS = ['mali_last_error', 'mali_device_count', 'mali_model_create', 'mali_model_destroy', 'mali_model_layout',
            'mali_planck_bc', 'mali_upload_columns', 'mali_formal_sol_gamma', 'mali_stat_equil', 'mali_iterate',
            'mali_piecewise_linear_1d', 'mali_uv', 'mali_exp_hook', 'mali_div_hook', 'mali_profile_begin',
-           'mali_profile_end', 'mali_launch_count']
+           'mali_profile_end', 'mali_launch_count', 'mali_fp64_peak']
 
 _lib = None
 
@@ -74,6 +74,7 @@ def load():
     L.mali_launch_count.argtypes = [C.c_void_p]
     L.mali_launch_count.restype = C.c_longlong
     L.mali_div_hook.argtypes = [C.c_int32] + [C.c_void_p] * 5
+    L.mali_fp64_peak.argtypes = [C.c_int32, C.c_void_p, C.POINTER(C.c_double)]
     L.mali_exp_hook.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.mali_uv.argtypes = [C.c_void_p, C.POINTER(Buffers)] + [C.c_int32] * 5 + [C.c_void_p] * 4
     _lib = L

@@ -169,7 +169,7 @@ struct mali_model {
     std::vector<TileC<4>> tiles4;        // constant-bank descriptors of the class-0 / class-1 tiles
     std::vector<TileC<8>> tiles8;
     int64_t off_zero = 0;
-    int smemPopDoubles = 0, smemZOff = 0, smemLvlOff = 0, smemMbarOff = 0, smemBytesPerWarp = 0, useBulk = 0;
+    int smemPopDoubles = 0, smemZOff = 0, smemLvlOff = 0, smemMbarOff = 0, smemExpOff = 0, smemBytesPerWarp = 0, useBulk = 0;
     mali_layout lay{};
     int64_t off_z = 0, off_bbc = 0, off_bgchi = 0, off_bgeta = 0, off_bgsca = 0, off_C = 0, off_nTotal = 0;
     int64_t off_jpart = 0, off_part = 0;
@@ -210,6 +210,7 @@ static FsCommon make_fs_common(const mali_model *m, const mali_buffers *b, int c
     c.zOffDoubles = m->smemZOff;
     c.lvlOffDoubles = m->smemLvlOff;
     c.mbarOffBytes = m->smemMbarOff;
+    c.expTabOffBytes = m->smemExpOff;
     c.colStride = m->lay.colconst;
     c.popStride = m->lay.pops;
     c.JStride = m->lay.J;
@@ -569,7 +570,8 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
         m->smemZOff = even(m->smemPopDoubles);
         m->smemLvlOff = m->smemZOff + even(N);
         m->smemMbarOff = (m->smemLvlOff + std::max(std::max(m->Dmax, 1) * 64, 16 * 36)) * 8;
-        m->smemBytesPerWarp = (int)align_up(m->smemMbarOff + 16, 16);
+        m->smemExpOff = (int)align_up(m->smemMbarOff + 16, 16);
+        m->smemBytesPerWarp = m->smemExpOff + 128 * 16;
         m->useBulk = (N % 2 == 0 && m->smemPopDoubles % 2 == 0) ? 1 : 0;  // cp.async.bulk: 16-byte sizes / addresses
     }
     std::vector<int32_t> trPartOff(d->Ntrans + 1, 0), trPartRows;
@@ -956,6 +958,26 @@ int mali_div_hook(int32_t n, const double *a_dev, const double *b_dev, double *q
     if (n < 1 || !a_dev || !b_dev || !q_dev || !bad_dev) return fail(MALI_EINVAL, "mali_div_hook: bad argument");
     div_hook_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, a_dev, b_dev, q_dev, bad_dev);
     CU(cudaGetLastError());
+    return MALI_OK;
+}
+
+int mali_fp64_peak(int32_t iters, double *scratch_dev, double *ops_per_second)
+{
+    if (iters < 1 || !scratch_dev || !ops_per_second) return fail(MALI_EINVAL, "mali_fp64_peak: bad argument");
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    const int blocks = 148 * 8, threads = 256;
+    fp64_peak_kernel<<<blocks, threads>>>(iters / 8 + 1, 1.0, scratch_dev);  // warm-up
+    CU(cudaEventRecord(e0));
+    fp64_peak_kernel<<<blocks, threads>>>(iters, 1.0, scratch_dev);
+    CU(cudaEventRecord(e1));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    CU(cudaEventDestroy(e0));
+    CU(cudaEventDestroy(e1));
+    *ops_per_second = (double)blocks * threads * (double)iters * 16.0 / (ms * 1e-3);  // 8 chains x (mul + add)
     return MALI_OK;
 }
 

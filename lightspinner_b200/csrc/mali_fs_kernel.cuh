@@ -48,7 +48,7 @@ struct TileC {
 struct FsCommon {
     int32_t N, Nrays, Nspect, Lw;
     int32_t col0, ncol, warpsPerBlock, useBulk;
-    int32_t smemBytesPerWarp, popDoubles, zOffDoubles, lvlOffDoubles, mbarOffBytes, pad0;
+    int32_t smemBytesPerWarp, popDoubles, zOffDoubles, lvlOffDoubles, mbarOffBytes, expTabOffBytes;
     int64_t colStride, popStride, JStride, IStride, scratchStride;
     int64_t off_z, off_bbc, off_bgchi, off_bgeta, off_bgsca, off_zero;
     int64_t off_jpart, off_part;

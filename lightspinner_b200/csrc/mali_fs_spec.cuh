@@ -89,6 +89,14 @@ __device__ __forceinline__ double reduce_scatter_n(double (&v)[M], int lane)
     return v[0];
 }
 
+// streaming read (each element is used by exactly one lane, once per direction): do not allocate in L1
+__device__ __forceinline__ double ld_stream(const double *p)
+{
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
 // Warp reduce-scatter through shared memory: every lane stores its M values, then lane L sums 32/M... see below.
 // red: per-warp scratch of M rows x 36 doubles (lane l of a row sits at l + l/8: conflict-free stores and loads).
 // After the call the lane holds the total over the 32 lanes of value index L / (32/M).  Fixed order -> deterministic.
@@ -103,13 +111,17 @@ __device__ __forceinline__ double reduce_transpose(const double (&v)[M], int lan
     __syncwarp();
     const int e = lane / G, part = lane % G;
     const double *row = red + e * 36;
-    double acc = 0.0;
+    double acc = 0.0, acc1 = 0.0;   // two interleaved partial sums halve the dependent-add chain
 #pragma unroll
     for (int i = 0; i < SEG; ++i) {
         const int l = part * SEG + i;
         const double x = row[l + (l >> 3)];
-        acc = (i == 0) ? x : acc + x;
+        if (i & 1)
+            acc1 = (i == 1) ? x : acc1 + x;
+        else
+            acc = (i == 0) ? x : acc + x;
     }
+    if (SEG > 1) acc = acc + acc1;
 #pragma unroll
     for (int off = G / 2; off > 0; off >>= 1) acc = acc + __shfl_xor_sync(0xffffffffu, acc, off);
     return acc;
@@ -188,10 +200,17 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
         }
     }
 
+    // the exp table (2 KB) in shared memory: one 16-byte LDS per exp instead of a global load in the critical chain
+    ulonglong2 *stab = reinterpret_cast<ulonglong2 *>(wbase + p.expTabOffBytes);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) stab[lane + 32 * q] = kExpTab[lane + 32 * q];
+    __syncwarp();
+
     const double zmu = p.zmu[muC], hw = p.hw[muC];
     const double bbc0 = cc[p.off_bbc + 2 * laC], bbc1 = cc[p.off_bbc + 2 * laC + 1];
     const double fourPi = 4.0 * kPi;
     const int zeroIdx = (int)p.off_zero;
+    const double r3 = rcp_full(3.0);
 
     // ---- depth-invariant per-lane slot state
     bool act[NSA];
@@ -270,6 +289,8 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
         JdN = Jcol[kl];
 
         Sweep sw;
+        sw.r3 = r3;
+        sw.stab = stab;
         for (int s = 0; s < N; ++s) {
             const int k = kS + s * dk;
             double ld[NSA], wl[NSA];
@@ -294,7 +315,7 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
 #pragma unroll
                 for (int tt = 0; tt < NS; ++tt) {
                     ia[tt] += sa[tt];
-                    ldN[tt] = __ldg(cc + ia[tt]);
+                    ldN[tt] = ld_stream(cc + ia[tt]);
                     if (S.kind[tt]) {
                         ib[tt] += sb[tt];
                         wlN[tt] = __ldg(cc + ib[tt]);

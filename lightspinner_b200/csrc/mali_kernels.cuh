@@ -26,6 +26,32 @@ __device__ const ulonglong2 kExpTab[128] = {
 #include "exp_table.inc"
 };
 
+// tab: the 128-entry table, either kExpTab (global, read-only path) or a shared-memory copy of it
+template <bool SMEM_TAB>
+__device__ __forceinline__ double exp_m_t(double x, const ulonglong2 *tab)
+{
+    const double InvLn2N = 0x1.71547652b82fep+7, Shift = 0x1.8p+52;
+    const double NegLn2hiN = -0x1.62e42fefa0000p-8, NegLn2loN = -0x1.cf79abc9e3b3ap-47;
+    const double C2 = 0x1.ffffffffffdbdp-2, C3 = 0x1.555555555543cp-3, C4 = 0x1.55555cf172b91p-5,
+                 C5 = 0x1.1111167a4d017p-7;
+    double kd = __fma_rn(x, InvLn2N, Shift);
+    const unsigned long long ki = (unsigned long long)__double_as_longlong(kd);
+    const ulonglong2 e = SMEM_TAB ? tab[ki & 127ull] : __ldg(&tab[ki & 127ull]);
+    kd = __dsub_rn(kd, Shift);
+    double r = __fma_rn(kd, NegLn2hiN, x);
+    r = __fma_rn(kd, NegLn2loN, r);
+    const double tail = __longlong_as_double((long long)e.x);
+    const double scale = __longlong_as_double((long long)(e.y + (ki << 45)));
+    const double t1 = __fma_rn(r, C3, C2);
+    const double s = __dadd_rn(r, tail);
+    const double r2 = __dmul_rn(r, r);
+    const double t2 = __fma_rn(r, C5, C4);
+    const double s2 = __fma_rn(t1, r2, s);
+    const double r4 = __dmul_rn(r2, r2);
+    const double tmp = __fma_rn(r4, t2, s2);
+    return __fma_rn(scale, tmp, scale);
+}
+
 __device__ __forceinline__ double exp_m(double x)
 {
     const double InvLn2N = 0x1.71547652b82fep+7, Shift = 0x1.8p+52;
@@ -48,6 +74,23 @@ __device__ __forceinline__ double exp_m(double x)
     const double r4 = __dmul_rn(r2, r2);
     const double tmp = __fma_rn(r4, t2, s2);
     return __fma_rn(scale, tmp, scale);
+}
+
+// fp64 CUDA-core peak probe for the roofline: 8 independent unfused mul/add chains per thread.
+__global__ void fp64_peak_kernel(int iters, double seed, double *out)
+{
+    double a[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) a[q] = seed + q + threadIdx.x * 1e-9;
+    const double m = 1.0000001, c = 1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) a[q] = __dadd_rn(__dmul_rn(a[q], m), c);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s += a[q];
+    if (s == 123.456) out[0] = s;  // keeps the work alive
 }
 
 __global__ void exp_hook_kernel(int n, const double *x, double *y)
@@ -120,10 +163,28 @@ __device__ __forceinline__ void w2(double dtau, double &w0, double &w1)
     }
 }
 
+// w2 with the exp table in shared memory and dtau / 3.0 through the shared-reciprocal division (r3 = rcp_full(3.0))
+__device__ __forceinline__ void w2_fast(double dtau, double r3, const ulonglong2 *stab, double &w0, double &w1)
+{
+    if (dtau < 5e-4) {
+        w0 = dtau * (1.0 - 0.5 * dtau);
+        w1 = (dtau * dtau) * (0.5 - div_by(dtau, 3.0, r3));
+    } else if (dtau > 50.0) {
+        w0 = 1.0;
+        w1 = 1.0;
+    } else {
+        const double expdt = exp_m_t<true>(-dtau, stab);
+        w0 = 1.0 - expdt;
+        w1 = w0 - dtau * expdt;
+    }
+}
+
 // One ray's short-characteristic recurrence, one depth point per step() (formal_solver.py:46-142,191-211).
 // The caller supplies chi, S at the current point in sweep order; step() returns I and PsiStar = LambdaStar/chi there.
 struct Sweep {
     double Iupw, chiPrev, SPrev, zPrev, w0, w1;
+    double r3 = 0.0;                      // rcp_full(3.0) when the fast w2 is used
+    const ulonglong2 *stab = nullptr;     // shared-memory copy of the exp table (nullptr: global table)
     unsigned bad;  // sticky: a divisor left the domain of the shared-reciprocal division (reported via status bit 1)
 
     __device__ __forceinline__ static unsigned out_of_range(double b)
@@ -166,7 +227,10 @@ struct Sweep {
         const double dS = div_by(SPrev - S, dtau, rdt);
         double Ik, Lam;
         if (!last) {
-            w2(dtau, w0, w1);
+            if (stab != nullptr)
+                w2_fast(dtau, r3, stab, w0, w1);
+            else
+                w2(dtau, w0, w1);
             Ik = Iupw * (1.0 - w0) + w0 * S + w1 * dS;
         } else {
             Ik = (1.0 - w0) * Iupw + w0 * SPrev + w1 * dS;

@@ -249,3 +249,13 @@ def div_hook(a, b, device=None):
         _capi.check(_capi.load().mali_div_hook(ta.numel(), *(C.c_void_p(t.data_ptr()) for t in (ta, tb, tq, tbad)),
                                                C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
     return tq.cpu().numpy(), tbad.cpu().numpy()
+
+
+def fp64_peak(device=None, iters=4096):
+    """Measured unfused fp64 mul+add throughput of the device (operations / s)."""
+    dev = torch.device('cuda', torch.cuda.current_device() if device is None else device)
+    scratch = torch.zeros(8, dtype=torch.float64, device=dev)
+    out = C.c_double(0.0)
+    with torch.cuda.device(dev):
+        _capi.check(_capi.load().mali_fp64_peak(int(iters), C.c_void_p(scratch.data_ptr()), C.byref(out)))
+    return out.value
