@@ -67,7 +67,8 @@ typedef struct {
  * arrays inside one column's host staging block ("host pack": plain concatenation, no transposition). */
 typedef struct {
     int64_t hostpack;  /* staging block: what mali_upload_columns copies host->device */
-    int64_t colconst;  /* packed iteration-invariant device block (depth-major, wavelength-contiguous) */
+    int64_t colconst;  /* packed iteration-invariant device block: z, planck BC, C, nTotal, then the tile-major
+                          table [Nspace][tile records] (see csrc/mali_types.cuh) */
     int64_t pops;      /* sumNlevel * Nspace        n[level][k]            (in/out) */
     int64_t J;         /* Nspace * Nspect           J[k][la]  (depth-major) (in/out) */
     int64_t I;         /* Nspect * Nrays            I[la][mu]               (out) */
@@ -109,6 +110,9 @@ int mali_device_count(void);
 int mali_model_create(const mali_model_desc *desc, int device, mali_model **out);
 void mali_model_destroy(mali_model *m);
 int mali_model_layout(const mali_model *m, mali_layout *out);
+/* out8: ntile, tiles on structure-specialised kernels, tiles on the generic kernel, max transitions per tile,
+ * max levels per tile, doubles per depth row of the tile-major table, shared-memory bytes per warp, TMA staging on/off */
+int mali_model_info(const mali_model *m, int32_t *out8);
 
 /* Host helper: out[la][0..1] = planck(T[Nspace-2]), planck(T[Nspace-1]) at wavelength[la]  (utils.py:17-22, glibc exp). */
 int mali_planck_bc(const double *wavelength, int32_t Nspect, double Tm2, double Tm1, double *out);

@@ -38,7 +38,7 @@ class Buffers(C.Structure):
                 ('dPops', C.c_void_p), ('status', C.c_void_p), ('iter', C.c_void_p), ('done', C.c_void_p)]
 
 
-EXPORTS = ['mali_last_error', 'mali_device_count', 'mali_model_create', 'mali_model_destroy', 'mali_model_layout',
+EXPORTS = ['mali_last_error', 'mali_device_count', 'mali_model_create', 'mali_model_destroy', 'mali_model_layout', 'mali_model_info',
            'mali_planck_bc', 'mali_upload_columns', 'mali_formal_sol_gamma', 'mali_stat_equil', 'mali_iterate',
            'mali_piecewise_linear_1d', 'mali_uv', 'mali_exp_hook', 'mali_div_hook', 'mali_profile_begin',
            'mali_profile_end', 'mali_launch_count', 'mali_fp64_peak']
@@ -61,6 +61,7 @@ def load():
     L.mali_model_destroy.argtypes = [C.c_void_p]
     L.mali_model_destroy.restype = None
     L.mali_model_layout.argtypes = [C.c_void_p, C.POINTER(Layout)]
+    L.mali_model_info.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
     L.mali_planck_bc.argtypes = [_dp, C.c_int32, C.c_double, C.c_double, _dp]
     L.mali_upload_columns.argtypes = [C.c_void_p, C.POINTER(Buffers), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                       C.c_void_p]

@@ -1,4 +1,4 @@
-// mali_api.cu -- host side of libmali_b200.so: model flattening (tiles / slots / layouts) and the C ABI
+// mali_api.cu -- host side of libmali_b200.so: model flattening (tiles / slots / record layout) and the C ABI
 // declared in include/mali_b200.h.  No torch types, no exceptions across the boundary.
 #include <cuda_runtime.h>
 
@@ -75,17 +75,18 @@ __global__ void iterate_ctl_kernel(int phase, double *dJ, double *dPops, int32_t
         iter[col] += 1;
     } else if (tolJ >= 0.0) {
         const double a = dJ[col], b = dPops[col];
-        if (!(a > tolJ || b > tolPops)) done[col] = 1;  // `while dJ > 2e-3 or dPops > 1e-3` (NaN keeps iterating... never)
+        if (!(a > tolJ || b > tolPops)) done[col] = 1;  // the negation of `while dJ > 2e-3 or dPops > 1e-3`
         if (a != a || b != b) done[col] = 2;            // NaN: stop touching the column, flag it
     }
 }
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------------------
 // Ahead-of-time instances of the structure-specialised kernel (generated: tools/gen_spec_instances.py)
-#define MALI_SPEC(ID, KEY, ...) \
-    struct SpecTag##ID {           \
-        static constexpr TileStruct S = {__VA_ARGS__}; \
+#define MALI_SPEC(ID, KEY, ...)                          \
+    struct SpecTag##ID {                                 \
+        static constexpr TileStruct S = {__VA_ARGS__};   \
     };
 #include "spec_instances.inc"
 #undef MALI_SPEC
@@ -97,16 +98,16 @@ static const SpecEntry kSpecRegistry[] = {
 
 namespace mali {
 // One kernel per register class; the structure id of the tile selects the specialised body (uniform switch).
+// blockIdx.x runs over columns, blockIdx.y over tiles: co-resident blocks share a structure, hence one instruction
+// stream per SM (each specialised body is ~40 KB of SASS).
 template <int CLS>
 __global__ void __launch_bounds__(32, spec_class_warps(CLS)) fs_gamma_kernel_m(const __grid_constant__ MegaParams<CLS> P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // blockIdx.x runs over column groups, blockIdx.y over tiles: co-resident blocks share a structure -> one
-    // instruction stream per SM (the specialised bodies are ~40 KB of SASS each)
     const TileR<MegaParams<CLS>::NSP> &T = P.tiles[blockIdx.y];
     switch (T.spec) {
-#define MALI_SPEC(ID, KEY, ...)                                                              \
-    case ID:                                                                                 \
+#define MALI_SPEC(ID, KEY, ...)                                                                        \
+    case ID:                                                                                           \
         if constexpr (spec_class(SpecTag##ID::S.nslot) == CLS) fs_body<SpecTag##ID>(P.c, T, smem_raw); \
         break;
 #include "spec_instances.inc"
@@ -145,13 +146,14 @@ static cudaError_t launch_mega(const FsCommon &c, const std::vector<TileR<spec_c
     for (int t0 = 0; t0 < nt; t0 += MP::kMaxTiles) {
         const int n = std::min(MP::kMaxTiles, nt - t0);
         memcpy(P->tiles, tiles.data() + t0, sizeof(tiles[0]) * n);
-        dim3 grid((ncol + c.warpsPerBlock - 1) / c.warpsPerBlock, n);
-        kern<<<grid, 32 * c.warpsPerBlock, smem, st>>>(*P);
+        dim3 grid(ncol, n);
+        kern<<<grid, 32, smem, st>>>(*P);
         if (launches) *launches += 1;
     }
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------------------
 struct mali_model {
     int device = 0;
     int N = 0, Nrays = 0, Nspect = 0, Natom = 0, Ntrans = 0, Lw = 0, ntile = 0, Dmax = 0, Tmax = 0;
@@ -159,117 +161,35 @@ struct mali_model {
     std::vector<int32_t> Nlevel, lvlOff, g2Off, trans, toff;
     std::vector<SlotDesc> slots;
     std::vector<TileDesc> tiles;
-    std::vector<SlotDesc> transSlot;  // one descriptor per transition (for the uv hook)
-    std::vector<int32_t> classTiles[3];  // tiles with <= 4, 5..8, > 8 transitions
-    int32_t *d_classTiles[3] = {nullptr, nullptr, nullptr};
+    std::vector<SlotDesc> transSlot;     // one descriptor per transition (uv hook)
+    std::vector<int32_t> genericTiles;   // tiles without a specialised instance -> generic kernel
     std::vector<TileR<2>> spec0;         // tiles served by the structure-specialised kernels, per register class,
     std::vector<TileR<4>> spec1;         // heaviest first
     std::vector<TileR<8>> spec2;
     int specTiles = 0;
-    std::vector<TileC<4>> tiles4;        // constant-bank descriptors of the class-0 / class-1 tiles
-    std::vector<TileC<8>> tiles8;
-    int64_t off_zero = 0;
-    int smemPopDoubles = 0, smemZOff = 0, smemLvlOff = 0, smemMbarOff = 0, smemExpOff = 0, smemBytesPerWarp = 0, useBulk = 0;
     mali_layout lay{};
-    int64_t off_z = 0, off_bbc = 0, off_bgchi = 0, off_bgeta = 0, off_bgsca = 0, off_C = 0, off_nTotal = 0;
+    int64_t off_z = 0, off_bbc = 0, off_C = 0, off_nTotal = 0, off_tab = 0, rowStride = 0;
     int64_t off_jpart = 0, off_part = 0;
-    std::vector<TransposeJob> tjobs;
+    int smemPopDoubles = 0, smemZOff = 0, smemLvlOff = 0, smemMbarOff = 0, smemExpOff = 0, smemBytesPerWarp = 0, useBulk = 0;
     std::vector<CopyJob> cjobs;
-    std::vector<WlaJob> wjobs;
-    int transposeTiles = 0;
+    int packChunks = 0;
     // device copies
     TileDesc *d_tiles = nullptr;
     SlotDesc *d_slots = nullptr;
     double *d_alpha = nullptr, *d_twohc = nullptr, *d_wlacont = nullptr, *d_wlambda = nullptr, *d_zmu = nullptr,
            *d_hw = nullptr;
     int32_t *d_Nlevel = nullptr, *d_lvlOff = nullptr, *d_g2Off = nullptr, *d_trans = nullptr, *d_trPartOff = nullptr,
-            *d_trPartRows = nullptr;
-    TransposeJob *d_tjobs = nullptr;
+            *d_trPartRows = nullptr, *d_genericTiles = nullptr;
     CopyJob *d_cjobs = nullptr;
-    WlaJob *d_wjobs = nullptr;
-    // optional per-launch timing of fs_gamma_kernel (mali_profile_begin / mali_profile_end)
+    PackChunk *d_pchunks = nullptr;
+    PackTile *d_ptiles = nullptr;
+    PackSlot *d_pslots = nullptr;
+    // optional per-launch timing of the formal-solution stage (mali_profile_begin / mali_profile_end)
     mutable std::vector<cudaEvent_t> profEvents;
     mutable int profUsed = 0;
     mutable bool profOn = false;
     mutable long long launches = 0;  // kernels launched through this model since creation
 };
-
-static FsCommon make_fs_common(const mali_model *m, const mali_buffers *b, int col0, int ncol, int wpb)
-{
-    FsCommon c{};
-    c.N = m->N;
-    c.Nrays = m->Nrays;
-    c.Nspect = m->Nspect;
-    c.Lw = m->Lw;
-    c.col0 = col0;
-    c.ncol = ncol;
-    c.warpsPerBlock = wpb;
-    c.useBulk = m->useBulk;
-    c.smemBytesPerWarp = m->smemBytesPerWarp;
-    c.popDoubles = m->smemPopDoubles;
-    c.zOffDoubles = m->smemZOff;
-    c.lvlOffDoubles = m->smemLvlOff;
-    c.mbarOffBytes = m->smemMbarOff;
-    c.expTabOffBytes = m->smemExpOff;
-    c.colStride = m->lay.colconst;
-    c.popStride = m->lay.pops;
-    c.JStride = m->lay.J;
-    c.IStride = m->lay.I;
-    c.scratchStride = m->lay.scratch;
-    c.off_z = m->off_z;
-    c.off_bbc = m->off_bbc;
-    c.off_bgchi = m->off_bgchi;
-    c.off_bgeta = m->off_bgeta;
-    c.off_bgsca = m->off_bgsca;
-    c.off_zero = m->off_zero;
-    c.off_jpart = m->off_jpart;
-    c.off_part = m->off_part;
-    c.alpha = m->d_alpha;
-    c.twohc = m->d_twohc;
-    c.wlacont = m->d_wlacont;
-    c.zmu = m->d_zmu;
-    c.hw = m->d_hw;
-    c.colconst = b->colconst;
-    c.pops = b->pops;
-    c.J = b->J;
-    c.I = b->I;
-    c.scratch = b->scratch;
-    c.dJbits = reinterpret_cast<unsigned long long *>(b->dJ);
-    c.status = b->status;
-    c.done = b->done;
-    return c;
-}
-
-
-// Launches fs_gamma_kernel_c over one tile class, at most ClassParams<TMAX>::kMaxTiles tiles per launch
-// (the tile descriptors travel in the kernel parameters).
-template <int TMAX>
-static int launch_fs_class(const mali_model *m, const std::vector<TileC<TMAX>> &tiles, const FsCommon &c, int ncol,
-                           size_t smem, cudaStream_t st)
-{
-    using CP = ClassParams<TMAX>;
-    static thread_local CP *P = nullptr;  // 32 KB: keep it off the stack
-    if (!P) P = new CP();
-    void (*kern)(const CP) = m->Natom == 1 ? fs_gamma_kernel_c<TMAX, 1>
-                             : m->Natom == 2 ? fs_gamma_kernel_c<TMAX, 2> : fs_gamma_kernel_c<TMAX, 4>;
-    static thread_local const void *attr_done[3] = {nullptr, nullptr, nullptr};
-    const int ai = m->Natom == 1 ? 0 : (m->Natom == 2 ? 1 : 2);
-    if (smem > 48 * 1024 && attr_done[ai] != (const void *)kern) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return (int)e;
-        attr_done[ai] = (const void *)kern;
-    }
-    P->c = c;
-    const int nt = (int)tiles.size();
-    for (int t0 = 0; t0 < nt; t0 += CP::kMaxTiles) {
-        const int n = std::min(CP::kMaxTiles, nt - t0);
-        memcpy(P->tiles, tiles.data() + t0, sizeof(TileC<TMAX>) * n);
-        dim3 grid((ncol + c.warpsPerBlock - 1) / c.warpsPerBlock, n);
-        kern<<<grid, 32 * c.warpsPerBlock, smem, st>>>(*P);
-        m->launches += 1;
-    }
-    return 0;
-}
 
 extern "C" {
 
@@ -323,7 +243,7 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
     m->Ntrans = d->Ntrans;
     m->Lw = 32 / d->Nrays;
     m->ntile = (d->Nspect + m->Lw - 1) / m->Lw;
-    const int N = m->N;
+    const int N = m->N, Lw = m->Lw;
 
     m->Nlevel.assign(d->Nlevel, d->Nlevel + d->Natom);
     m->lvlOff.assign(d->Natom + 1, 0);
@@ -354,39 +274,8 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
     }
     const int ntab = m->toff[d->Ntrans];
 
-    // ---- layouts.  colconst: every table depth-major with the wavelength (and angle) index contiguous.
-    int64_t o = 0;
-    auto take = [&](int64_t n) { int64_t r = o; o = align_up(o + n, 16); return r; };
-    m->off_z = take(N);
-    m->off_bbc = take(2 * (int64_t)d->Nspect);
-    m->off_bgchi = take((int64_t)N * d->Nspect);
-    m->off_bgeta = take((int64_t)N * d->Nspect);
-    m->off_bgsca = take((int64_t)N * d->Nspect);
-    m->off_C = take((int64_t)m->sumNlevel2 * N);
-    m->off_nTotal = take((int64_t)d->Natom * N);
-    m->off_zero = take(16);  // zeros: lanes on which a transition is inactive read here with stride 0
-    std::vector<int64_t> tabOff(d->Ntrans), wlaOff(d->Ntrans, 0);
-    for (int t = 0; t < d->Ntrans; ++t) {
-        const int32_t *tr = &m->trans[(size_t)t * 6];
-        if (tr[3]) {
-            tabOff[t] = take(2 * (int64_t)N * tr[5] * d->Nrays);
-            wlaOff[t] = take((int64_t)N * tr[5]);
-        } else {
-            tabOff[t] = take((int64_t)N * tr[5]);
-        }
-    }
+    // ---- host pack: reference layouts, plain concatenation
     mali_layout &L = m->lay;
-    L.colconst = o;
-    L.pops = (int64_t)m->sumNlevel * N;
-    L.J = (int64_t)N * d->Nspect;
-    L.I = (int64_t)d->Nspect * d->Nrays;
-    L.Gamma = (int64_t)m->sumNlevel2 * N;
-    L.sumNlevel = m->sumNlevel;
-    L.sumNlevel2 = m->sumNlevel2;
-    L.ntile = m->ntile;
-    L.lambda_per_warp = m->Lw;
-
-    // host pack: reference layouts, plain concatenation
     int64_t h = 0;
     auto htake = [&](int64_t n) { int64_t r = h; h += n; return r; };
     L.hp_height = htake(N);
@@ -407,7 +296,7 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
     L.hp_n = htake((int64_t)m->sumNlevel * N);
     L.hostpack = h;
 
-    // ---- per-transition descriptors, tiles and slots
+    // ---- per-transition descriptors
     m->transSlot.resize(d->Ntrans);
     for (int t = 0; t < d->Ntrans; ++t) {
         const int32_t *tr = &m->trans[(size_t)t * 6];
@@ -420,22 +309,28 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
         s.rowI = m->lvlOff[tr[0]] + tr[1];
         s.rowJ = m->lvlOff[tr[0]] + tr[2];
         s.toff = m->toff[t];
-        s.tabOff = tabOff[t];
-        s.wlaOff = wlaOff[t];
+        s.vOff = -1;
         s.c0 = d->lineconst[3 * t + 0];
         s.c1 = d->lineconst[3 * t + 1];
         s.c2 = d->lineconst[3 * t + 2];
         m->transSlot[t] = s;
     }
+
+    // ---- tiles, slots and the tile-major record layout (mali_types.cuh)
     std::vector<std::vector<int32_t>> trRows(d->Ntrans);
+    std::vector<PackTile> ptiles;
+    std::vector<PackSlot> pslots;
+    std::vector<PackChunk> pchunks;
     int partRow = 0;
+    int64_t rowOff = 0;
     for (int ti = 0; ti < m->ntile; ++ti) {
-        const int la0 = ti * m->Lw, la1 = std::min(d->Nspect, la0 + m->Lw);
+        const int la0 = ti * Lw, la1 = std::min(d->Nspect, la0 + Lw);
         TileDesc td{};
         td.la0 = la0;
         td.slot0 = (int)m->slots.size();
         td.partRow0 = partRow;
         std::map<std::pair<int, int>, int> lev;
+        int nLine = 0;
         for (int t = 0; t < d->Ntrans; ++t) {
             const int32_t *tr = &m->trans[(size_t)t * 6];
             if (!(tr[4] < la1 && tr[4] + tr[5] > la0)) continue;
@@ -452,39 +347,84 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
             s.flags = 0;
             s.lsI = slot_of(tr[1], 1);
             s.lsJ = slot_of(tr[2], 2);
+            if (s.isLine) s.vOff = 2 * kVRow * nLine++;
             trRows[t].push_back(partRow);
             partRow += 2;
             m->slots.push_back(s);
             td.nslot++;
         }
+        const int sb = 2 * kVRow * nLine;
+        PackTile pt{};
+        pt.recOff = (int32_t)rowOff;
+        pt.recSize = (int32_t)align_up(sb + (3 + td.nslot) * Lw, 16);
+        pt.la0 = la0;
+        pt.nslot = td.nslot;
+        pt.slot0 = (int32_t)pslots.size();
+        pt.sb = sb;
+        int lineIdx = 0;
+        for (int q = 0; q < td.nslot; ++q) {
+            SlotDesc &s = m->slots[td.slot0 + q];
+            s.fOff = sb + (3 + q) * Lw;
+            PackSlot ps{};
+            ps.isLine = s.isLine;
+            ps.Nblue = s.Nblue;
+            ps.Nlam = s.Nlam;
+            ps.lineIdx = s.isLine ? lineIdx++ : -1;
+            ps.toff = s.toff;
+            ps.srcOff = s.isLine ? hpPhi[s.t] : hpGij[s.t];
+            ps.wphiOff = L.hp_wphi + (int64_t)s.t * N;
+            ps.c0 = s.c0;
+            pslots.push_back(ps);
+        }
+        for (int e0 = 0; e0 < pt.recSize; e0 += 32) pchunks.push_back(PackChunk{ti, e0});
+        ptiles.push_back(pt);
+        td.recOff = pt.recOff;
+        td.bgOff = sb;
         td.nlevslot = (int)lev.size();
+        rowOff += pt.recSize;
         m->Dmax = std::max(m->Dmax, td.nlevslot);
         m->Tmax = std::max(m->Tmax, td.nslot);
         m->tiles.push_back(td);
     }
     m->nPartRows = partRow;
-    if (m->Dmax > 255 || L.colconst >= (int64_t)1 << 31) {
-        delete m;
-        return fail(MALI_ELIMIT, "tile touches %d levels / column block of %lld doubles: beyond the 32-bit offsets of the kernel", m->Dmax, (long long)L.colconst);
+    m->rowStride = rowOff;
+    m->packChunks = (int)pchunks.size();
+    std::vector<int32_t> trPartOff(d->Ntrans + 1, 0), trPartRows;
+    for (int t = 0; t < d->Ntrans; ++t) {
+        trPartOff[t + 1] = trPartOff[t] + (int)trRows[t].size();
+        trPartRows.insert(trPartRows.end(), trRows[t].begin(), trRows[t].end());
     }
-    auto slotc = [&](const SlotDesc &sd) {
-        SlotC c{};
-        c.kind = (sd.isLine ? 1 : 0) | ((sd.flags & 1) ? 2 : 0) | ((sd.flags & 2) ? 4 : 0);
-        c.Nblue = sd.Nblue;
-        c.Nlam = sd.Nlam;
-        c.tabOff = (int32_t)sd.tabOff;
-        c.wlaOff = (int32_t)sd.wlaOff;
-        c.toff = sd.toff;
-        c.rowIN = sd.rowI * N;
-        c.rowJN = sd.rowJ * N;
-        c.lvI = sd.lsI * 32;
-        c.lvJ = sd.lsJ * 32;
-        c.atom = sd.atom;
-        c.cA = sd.c2;
-        c.cB = sd.c1;
-        return c;
-    };
-    auto structure_key = [&](const TileDesc &td) {   // must match tools/gen_spec_instances.py
+
+    // ---- colconst block of one column
+    int64_t o = 0;
+    auto take = [&](int64_t n) { int64_t r = o; o = align_up(o + n, 16); return r; };
+    m->off_z = take(N);
+    m->off_bbc = take(2 * (int64_t)d->Nspect);
+    m->off_C = take((int64_t)m->sumNlevel2 * N);
+    m->off_nTotal = take((int64_t)d->Natom * N);
+    m->off_tab = take((int64_t)N * m->rowStride);
+    L.colconst = o;
+    L.pops = (int64_t)m->sumNlevel * N;
+    L.J = (int64_t)N * d->Nspect;
+    L.I = (int64_t)d->Nspect * d->Nrays;
+    L.Gamma = (int64_t)m->sumNlevel2 * N;
+    L.sumNlevel = m->sumNlevel;
+    L.sumNlevel2 = m->sumNlevel2;
+    L.ntile = m->ntile;
+    L.lambda_per_warp = Lw;
+    int64_t so = 0;
+    m->off_jpart = so;
+    so = align_up(so + L.J, 16);
+    m->off_part = so;
+    so = align_up(so + (int64_t)std::max(partRow, 1) * N, 16);
+    L.scratch = so;
+    if (m->Dmax > 255 || m->sumNlevel > 65535) {
+        delete m;
+        return fail(MALI_ELIMIT, "tile touches %d levels / model has %d levels: beyond the kernel's packed indices", m->Dmax, m->sumNlevel);
+    }
+
+    // ---- which tiles have a structure-specialised kernel instance
+    auto structure_key = [&](const TileDesc &td) {  // must match tools/gen_spec_instances.py
         int kind[8] = {0}, atom[8] = {0}, lvI[8] = {0}, lvJ[8] = {0}, rowI[8] = {0}, rowJ[8] = {0};
         for (int q = 0; q < td.nslot; ++q) {
             const SlotDesc &sd = m->slots[td.slot0 + q];
@@ -500,122 +440,64 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
             for (int q = 0; q < 8; ++q) r += std::to_string(x[q]) + (q < 7 ? "," : "}");
             return r;
         };
-        return "{" + std::to_string(td.nslot) + "," + std::to_string(d->Natom) + "," + std::to_string(td.nlevslot) + "," +
-               arr(kind) + "," + arr(atom) + "," + arr(lvI) + "," + arr(lvJ) + "," + arr(rowI) + "," + arr(rowJ) + "}";
+        return "{" + std::to_string(Lw) + "," + std::to_string(td.nslot) + "," + std::to_string(d->Natom) + "," +
+               std::to_string(td.nlevslot) + "," + arr(kind) + "," + arr(atom) + "," + arr(lvI) + "," + arr(lvJ) + "," +
+               arr(rowI) + "," + arr(rowJ) + "}";
     };
-    const bool noSpec = getenv("MALI_NO_SPEC") != nullptr;
     auto fill_tile = [&](auto &t, const TileDesc &td, int spec) {
         t.la0 = td.la0;
         t.partRow0 = td.partRow0;
         t.spec = spec;
+        t.recOff = td.recOff;
         for (int q = 0; q < td.nslot; ++q) {
             const SlotDesc &sd = m->slots[td.slot0 + q];
             SlotR &r = t.s[q];
             r.Nblue = sd.Nblue;
             r.Nlam = sd.Nlam;
-            r.tabOff = (int32_t)sd.tabOff;
-            r.wlaOff = (int32_t)sd.wlaOff;
             r.toff = sd.toff;
             r.cA = sd.c2;
             r.cB = sd.c1;
         }
     };
+    const bool noSpec = getenv("MALI_NO_SPEC") != nullptr;
     std::vector<int> order(m->ntile);
     for (int ti = 0; ti < m->ntile; ++ti) order[ti] = ti;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return m->tiles[a].nslot > m->tiles[b].nslot; });
     for (int ti : order) {
         const TileDesc &td = m->tiles[ti];
-        const int T = td.nslot;
-        const int cls = (d->Natom > 4 || T > 8) ? 2 : (T > 4 ? 1 : 0);
-        if (cls < 2 && !noSpec) {
-            if (const SpecEntry *e = find_spec(structure_key(td))) {
-                const int sc = spec_class(T);
-                if (sc == 0) {
-                    TileR<2> t{};
-                    fill_tile(t, td, e->id);
-                    m->spec0.push_back(t);
-                } else if (sc == 1) {
-                    TileR<4> t{};
-                    fill_tile(t, td, e->id);
-                    m->spec1.push_back(t);
-                } else {
-                    TileR<8> t{};
-                    fill_tile(t, td, e->id);
-                    m->spec2.push_back(t);
-                }
-                m->specTiles++;
-                continue;
-            }
+        const SpecEntry *e = (!noSpec && td.nslot <= kSpecMaxSlots && d->Natom <= 4) ? find_spec(structure_key(td)) : nullptr;
+        if (!e) {
+            m->genericTiles.push_back(ti);
+            continue;
         }
-        m->classTiles[cls].push_back(ti);
-        if (cls == 0) {
-            TileC<4> t{};
-            t.la0 = td.la0;
-            t.nslot = T;
-            t.partRow0 = td.partRow0;
-            for (int q = 0; q < T; ++q) t.s[q] = slotc(m->slots[td.slot0 + q]);
-            m->tiles4.push_back(t);
-        } else if (cls == 1) {
-            TileC<8> t{};
-            t.la0 = td.la0;
-            t.nslot = T;
-            t.partRow0 = td.partRow0;
-            for (int q = 0; q < T; ++q) t.s[q] = slotc(m->slots[td.slot0 + q]);
-            m->tiles8.push_back(t);
+        const int sc = spec_class(td.nslot);
+        if (sc == 0) {
+            TileR<2> t{};
+            fill_tile(t, td, e->id);
+            m->spec0.push_back(t);
+        } else if (sc == 1) {
+            TileR<4> t{};
+            fill_tile(t, td, e->id);
+            m->spec1.push_back(t);
+        } else {
+            TileR<8> t{};
+            fill_tile(t, td, e->id);
+            m->spec2.push_back(t);
         }
+        m->specTiles++;
     }
-    {   // per-warp shared memory of fs_gamma_kernel_c: populations | heights | level array | mbarrier
+    {   // per-warp shared memory: populations | heights | level array / reduce scratch | mbarrier | exp table
         auto even = [](int x) { return (x + 1) & ~1; };
         m->smemPopDoubles = m->sumNlevel * N;
         m->smemZOff = even(m->smemPopDoubles);
         m->smemLvlOff = m->smemZOff + even(N);
-        m->smemMbarOff = (m->smemLvlOff + std::max(std::max(m->Dmax, 1) * 64, 16 * 36)) * 8;
+        m->smemMbarOff = (m->smemLvlOff + std::max(std::max(m->Dmax, 1) * 64 + d->Natom * 32, 16 * 36)) * 8;
         m->smemExpOff = (int)align_up(m->smemMbarOff + 16, 16);
         m->smemBytesPerWarp = m->smemExpOff + 128 * 16;
         m->useBulk = (N % 2 == 0 && m->smemPopDoubles % 2 == 0) ? 1 : 0;  // cp.async.bulk: 16-byte sizes / addresses
     }
-    std::vector<int32_t> trPartOff(d->Ntrans + 1, 0), trPartRows;
-    for (int t = 0; t < d->Ntrans; ++t) {
-        trPartOff[t + 1] = trPartOff[t] + (int)trRows[t].size();
-        trPartRows.insert(trPartRows.end(), trRows[t].begin(), trRows[t].end());
-    }
-    int64_t so = 0;
-    m->off_jpart = so;
-    so = align_up(so + L.J, 16);
-    m->off_part = so;
-    so = align_up(so + (int64_t)std::max(partRow, 1) * N, 16);
-    L.scratch = so;
 
-    // ---- upload jobs
-    auto add_transpose = [&](int64_t src, int64_t dst, int R, int C, double scale = 1.0) {
-        TransposeJob j{};
-        j.scale = scale;
-        j.srcOff = src;
-        j.dstOff = dst;
-        j.R = R;
-        j.C = C;
-        j.tile0 = m->transposeTiles;
-        j.tilesC = (C + 31) / 32;
-        m->transposeTiles += ((R + 31) / 32) * j.tilesC;
-        m->tjobs.push_back(j);
-    };
-    add_transpose(L.hp_bg_chi, m->off_bgchi, d->Nspect, N);
-    add_transpose(L.hp_bg_eta, m->off_bgeta, d->Nspect, N);
-    add_transpose(L.hp_bg_sca, m->off_bgsca, d->Nspect, N);
-    for (int t = 0; t < d->Ntrans; ++t) {
-        const int32_t *tr = &m->trans[(size_t)t * 6];
-        if (tr[3]) {
-            add_transpose(hpPhi[t], tabOff[t], tr[5] * d->Nrays, 2 * N, d->lineconst[3 * t + 0]);
-            WlaJob w{};
-            w.wphiOff = L.hp_wphi + (int64_t)t * N;
-            w.dstOff = wlaOff[t];
-            w.toff = m->toff[t];
-            w.Nlam = tr[5];
-            m->wjobs.push_back(w);
-        } else {
-            add_transpose(hpGij[t], tabOff[t], tr[5], N);
-        }
-    }
+    // ---- small copies of the upload path
     auto add_copy = [&](int64_t src, int64_t dst, int64_t len, int toPops) {
         CopyJob c{};
         c.srcOff = src;
@@ -654,10 +536,11 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
     up(to_device(m->trans, &m->d_trans));
     up(to_device(trPartOff, &m->d_trPartOff));
     up(to_device(trPartRows, &m->d_trPartRows));
-    for (int c = 0; c < 3; ++c) up(to_device(m->classTiles[c], &m->d_classTiles[c]));
-    up(to_device(m->tjobs, &m->d_tjobs));
+    up(to_device(m->genericTiles, &m->d_genericTiles));
     up(to_device(m->cjobs, &m->d_cjobs));
-    up(to_device(m->wjobs, &m->d_wjobs));
+    up(to_device(pchunks, &m->d_pchunks));
+    up(to_device(ptiles, &m->d_ptiles));
+    up(to_device(pslots, &m->d_pslots));
     if (e != cudaSuccess) {
         mali_model_destroy(m);
         return fail((int)e, "mali_model_create: %s", cudaGetErrorString(e));
@@ -671,8 +554,8 @@ void mali_model_destroy(mali_model *m)
     if (!m) return;
     cudaSetDevice(m->device);
     void *ptrs[] = {m->d_tiles, m->d_slots, m->d_alpha, m->d_twohc, m->d_wlacont, m->d_wlambda, m->d_zmu, m->d_hw,
-                    m->d_Nlevel, m->d_lvlOff, m->d_g2Off, m->d_trans, m->d_trPartOff, m->d_trPartRows, m->d_tjobs,
-                    m->d_cjobs, m->d_wjobs, m->d_classTiles[0], m->d_classTiles[1], m->d_classTiles[2]};
+                    m->d_Nlevel, m->d_lvlOff, m->d_g2Off, m->d_trans, m->d_trPartOff, m->d_trPartRows,
+                    m->d_genericTiles, m->d_cjobs, m->d_pchunks, m->d_ptiles, m->d_pslots};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (cudaEvent_t e : m->profEvents) cudaEventDestroy(e);
@@ -683,6 +566,20 @@ int mali_model_layout(const mali_model *m, mali_layout *out)
 {
     if (!m || !out) return fail(MALI_EINVAL, "mali_model_layout: null argument");
     *out = m->lay;
+    return MALI_OK;
+}
+
+int mali_model_info(const mali_model *m, int32_t *out8)
+{
+    if (!m || !out8) return fail(MALI_EINVAL, "mali_model_info: null argument");
+    out8[0] = m->ntile;
+    out8[1] = m->specTiles;
+    out8[2] = (int32_t)m->genericTiles.size();
+    out8[3] = m->Tmax;
+    out8[4] = m->Dmax;
+    out8[5] = (int32_t)m->rowStride;
+    out8[6] = m->smemBytesPerWarp;
+    out8[7] = m->useBulk;
     return MALI_OK;
 }
 
@@ -702,17 +599,18 @@ int mali_upload_columns(const mali_model *m, const mali_buffers *b, int32_t col0
     const mali_layout &L = m->lay;
     if (host_pack)
         CU(cudaMemcpyAsync(staging_dev, host_pack, (size_t)ncol * L.hostpack * sizeof(double), cudaMemcpyHostToDevice, st));
-    if (m->transposeTiles > 0) {
-        dim3 grid(m->transposeTiles, ncol), block(32, 8);
-        pack_transpose_kernel<<<grid, block, 0, st>>>(m->d_tjobs, (int)m->tjobs.size(), staging_dev, L.hostpack,
-                                                      b->colconst, L.colconst, col0);
+    if (m->packChunks > 0) {
+        dim3 grid(m->packChunks, (m->N + 31) / 32, ncol), block(32, 8);
+        pack_tiles_kernel<<<grid, block, 0, st>>>(m->d_pchunks, m->d_ptiles, m->d_pslots, m->d_wlambda, m->N, m->Nrays,
+                                                  m->Nspect, m->Lw, staging_dev, L.hostpack, L.hp_bg_chi, L.hp_bg_eta,
+                                                  L.hp_bg_sca, b->colconst, L.colconst, m->off_tab, m->rowStride, col0);
     }
     {
         dim3 grid(32, ncol);
-        pack_misc_kernel<<<grid, 256, 0, st>>>(m->d_cjobs, (int)m->cjobs.size(), m->d_wjobs, (int)m->wjobs.size(),
-                                               m->d_wlambda, m->N, staging_dev, L.hostpack, b->colconst, L.colconst,
-                                               b->pops, L.pops, b->J, L.J, col0, m->off_zero);
+        pack_misc_kernel<<<grid, 256, 0, st>>>(m->d_cjobs, (int)m->cjobs.size(), staging_dev, L.hostpack, b->colconst,
+                                               L.colconst, b->pops, L.pops, b->J, L.J, col0);
     }
+    m->launches += 2;
     CU(cudaGetLastError());
     return MALI_OK;
 }
@@ -740,13 +638,14 @@ static FsParams make_fs_params(const mali_model *m, const mali_buffers *b, int c
     p.scratchStride = m->lay.scratch;
     p.off_z = m->off_z;
     p.off_bbc = m->off_bbc;
-    p.off_bgchi = m->off_bgchi;
-    p.off_bgeta = m->off_bgeta;
-    p.off_bgsca = m->off_bgsca;
+    p.off_tab = m->off_tab;
+    p.rowStride = m->rowStride;
     p.off_jpart = m->off_jpart;
     p.off_part = m->off_part;
     p.tiles = m->d_tiles;
     p.slots = m->d_slots;
+    p.classTiles = m->d_genericTiles;
+    p.nClassTiles = (int32_t)m->genericTiles.size();
     p.alpha = m->d_alpha;
     p.twohc = m->d_twohc;
     p.wlacont = m->d_wlacont;
@@ -761,6 +660,50 @@ static FsParams make_fs_params(const mali_model *m, const mali_buffers *b, int c
     p.status = b->status;
     p.done = b->done;
     return p;
+}
+
+static FsCommon make_fs_common(const mali_model *m, const mali_buffers *b, int col0, int ncol)
+{
+    FsCommon c{};
+    c.N = m->N;
+    c.Nrays = m->Nrays;
+    c.Nspect = m->Nspect;
+    c.Lw = m->Lw;
+    c.col0 = col0;
+    c.ncol = ncol;
+    c.warpsPerBlock = 1;
+    c.useBulk = m->useBulk;
+    c.smemBytesPerWarp = m->smemBytesPerWarp;
+    c.popDoubles = m->smemPopDoubles;
+    c.zOffDoubles = m->smemZOff;
+    c.lvlOffDoubles = m->smemLvlOff;
+    c.mbarOffBytes = m->smemMbarOff;
+    c.expTabOffBytes = m->smemExpOff;
+    c.colStride = m->lay.colconst;
+    c.popStride = m->lay.pops;
+    c.JStride = m->lay.J;
+    c.IStride = m->lay.I;
+    c.scratchStride = m->lay.scratch;
+    c.off_z = m->off_z;
+    c.off_bbc = m->off_bbc;
+    c.off_tab = m->off_tab;
+    c.rowStride = m->rowStride;
+    c.off_jpart = m->off_jpart;
+    c.off_part = m->off_part;
+    c.alpha = m->d_alpha;
+    c.twohc = m->d_twohc;
+    c.wlacont = m->d_wlacont;
+    c.zmu = m->d_zmu;
+    c.hw = m->d_hw;
+    c.colconst = b->colconst;
+    c.pops = b->pops;
+    c.J = b->J;
+    c.I = b->I;
+    c.scratch = b->scratch;
+    c.dJbits = reinterpret_cast<unsigned long long *>(b->dJ);
+    c.status = b->status;
+    c.done = b->done;
+    return c;
 }
 
 static FinishParams make_finish_params(const mali_model *m, const mali_buffers *b, int col0, int ncol)
@@ -798,15 +741,14 @@ static FinishParams make_finish_params(const mali_model *m, const mali_buffers *
 
 static int launch_fs(const mali_model *m, const mali_buffers *b, int col0, int ncol, cudaStream_t st)
 {
-    // Few (column, tile) pairs: one warp per block so that the work spreads over all 148 SMs; otherwise 4.
-    const int wpb = 1;  // one warp per block: column-uniform addressing; up to 32 blocks resident per SM
     col_zero_bits_kernel<<<(ncol + 127) / 128, 128, 0, st>>>(reinterpret_cast<unsigned long long *>(b->dJ), b->done,
                                                            nullptr, 0, col0, ncol);
     m->launches += 1;
     const bool rec = m->profOn && m->profUsed + 2 <= (int)m->profEvents.size();
     if (rec) cudaEventRecord(m->profEvents[m->profUsed], st);
-    // heaviest class first so that the light tiles fill the tail
-    if (!m->classTiles[2].empty()) {  // generic kernel: any number of transitions per tile / atoms
+    // heaviest work first so that the light tiles fill the tail
+    if (!m->genericTiles.empty()) {  // tiles without a specialised instance (any slot count, any number of atoms)
+        const int wpb = 1;
         FsParams p = make_fs_params(m, b, col0, ncol, wpb);
         const size_t smem = (size_t)p.smemPerWarp * wpb * sizeof(double);
         if (smem > 227 * 1024) return fail(MALI_ELIMIT, "tile needs %zu B of shared memory", smem);
@@ -815,21 +757,15 @@ static int launch_fs(const mali_model *m, const mali_buffers *b, int col0, int n
             CU(cudaFuncSetAttribute(fs_gamma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             attr_set = true;
         }
-        const int nt = (int)m->classTiles[2].size();
-        p.classTiles = m->d_classTiles[2];
-        p.nClassTiles = nt;
+        const int nt = (int)m->genericTiles.size();
         p.blocksPerCol = (nt + wpb - 1) / wpb;
         fs_gamma_kernel<<<(unsigned)(p.blocksPerCol * ncol), 32 * wpb, smem, st>>>(p);
         m->launches += 1;
     }
-    {
-        const FsCommon c = make_fs_common(m, b, col0, ncol, wpb);
-        const size_t smem = (size_t)m->smemBytesPerWarp * wpb;
-        if (smem > 227 * 1024) return fail(MALI_ELIMIT, "column needs %zu B of shared memory per block", smem);
-        if (!m->tiles8.empty())
-            if (int e = launch_fs_class<8>(m, m->tiles8, c, ncol, smem, st)) return fail(e, "fs_gamma_kernel_c<8>: %s", cudaGetErrorString((cudaError_t)e));
-        if (!m->tiles4.empty())
-            if (int e = launch_fs_class<4>(m, m->tiles4, c, ncol, smem, st)) return fail(e, "fs_gamma_kernel_c<4>: %s", cudaGetErrorString((cudaError_t)e));
+    if (m->specTiles > 0) {
+        const FsCommon c = make_fs_common(m, b, col0, ncol);
+        const size_t smem = (size_t)m->smemBytesPerWarp;
+        if (smem > 227 * 1024) return fail(MALI_ELIMIT, "column needs %zu B of shared memory per warp", smem);
         cudaError_t e = cudaSuccess;
         if (!m->spec2.empty()) e = launch_mega<2>(c, m->spec2, ncol, smem, st, &m->launches);
         if (e == cudaSuccess && !m->spec1.empty()) e = launch_mega<1>(c, m->spec1, ncol, smem, st, &m->launches);
@@ -995,10 +931,17 @@ int mali_uv(const mali_model *m, const mali_buffers *b, int32_t col, int32_t t, 
     if (int r = check_range(m, b, col, 1, "mali_uv")) return r;
     if (t < 0 || t >= m->Ntrans || mu < 0 || mu >= m->Nrays || !Uji || !Vij || !Vji)
         return fail(MALI_EINVAL, "mali_uv: bad argument");
-    const SlotDesc sd = m->transSlot[t];
-    if (la < sd.Nblue || la >= sd.Nblue + sd.Nlam) return fail(MALI_EINVAL, "mali_uv: transition %d is not active at wavelength %d", t, la);
+    const SlotDesc &ts = m->transSlot[t];
+    if (la < ts.Nblue || la >= ts.Nblue + ts.Nlam) return fail(MALI_EINVAL, "mali_uv: transition %d is not active at wavelength %d", t, la);
+    const int ti = la / m->Lw;
+    const TileDesc &td = m->tiles[ti];
+    const SlotDesc *sd = nullptr;
+    for (int q = 0; q < td.nslot; ++q)
+        if (m->slots[td.slot0 + q].t == t) sd = &m->slots[td.slot0 + q];
+    if (!sd) return fail(MALI_EINVAL, "mali_uv: internal error, transition %d missing from tile %d", t, ti);
     FsParams p = make_fs_params(m, b, col, 1, 1);
-    uv_hook_kernel<<<(m->N + 63) / 64, 64, 0, (cudaStream_t)stream>>>(p, col, sd, la, mu, toFrom ? 1 : 0, Uji, Vij, Vji);
+    uv_hook_kernel<<<(m->N + 63) / 64, 64, 0, (cudaStream_t)stream>>>(p, col, *sd, td.recOff, la, la - td.la0, mu,
+                                                                      toFrom ? 1 : 0, Uji, Vij, Vji);
     CU(cudaGetLastError());
     return MALI_OK;
 }

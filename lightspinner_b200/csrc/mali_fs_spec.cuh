@@ -16,13 +16,31 @@
 // spec_instances.inc, compiled by nvcc into libmali_b200.so); tiles whose structure has no instance fall back to
 // the class kernels of mali_fs_kernel.cuh.
 #pragma once
-#include "mali_fs_kernel.cuh"
+#include "mali_kernels.cuh"
 
 namespace mali {
 
 constexpr int kSpecMaxSlots = 8;
 
+struct FsCommon {  // launch-invariant parameters of the specialised kernels (constant bank)
+    int32_t N, Nrays, Nspect, Lw;
+    int32_t col0, ncol, warpsPerBlock, useBulk;
+    int32_t smemBytesPerWarp, popDoubles, zOffDoubles, lvlOffDoubles, mbarOffBytes, expTabOffBytes;
+    int64_t colStride, popStride, JStride, IStride, scratchStride;
+    int64_t off_z, off_bbc, off_tab, rowStride;
+    int64_t off_jpart, off_part;
+    const double *alpha, *twohc, *wlacont, *zmu, *hw;
+    const double *colconst, *pops;
+    double *J, *I, *scratch;
+    unsigned long long *dJbits;
+    int32_t *status;
+    const int32_t *done;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
 struct TileStruct {
+    int lw;                       // wavelengths per tile (32 / Nrays): fixes every offset inside a record
     int nslot;                    // transitions overlapping the tile
     int natom;                    // atoms of the model (per-atom emissivity registers)
     int nlev;                     // distinct (atom, level) pairs touched
@@ -32,8 +50,8 @@ struct TileStruct {
     int rowI[kSpecMaxSlots], rowJ[kSpecMaxSlots];  // row of the level in n[sumNlevel][N]
 };
 
-struct SlotR {  // run-time part of a slot, warp-uniform (constant bank), 40 B
-    int32_t Nblue, Nlam, tabOff, wlaOff, toff, pad;
+struct SlotR {  // run-time part of a slot, warp-uniform (constant bank), 32 B
+    int32_t Nblue, Nlam, toff, pad;
     double cA, cB;  // lines: Bji/Bij, Aji/Bji
 };
 
@@ -52,11 +70,18 @@ __host__ __device__ constexpr int spec_class_slots(int cls) { return cls == 0 ? 
 #define MALI_OCC2 8
 #endif
 __host__ __device__ constexpr int spec_class_warps(int cls) { return cls == 0 ? MALI_OCC0 : (cls == 1 ? MALI_OCC1 : MALI_OCC2); }
+// number of line slots among the first tt slots (tt == nslot: all of them) -> position of a line's Vij rows
+__host__ __device__ constexpr int spec_line_index(const TileStruct &S, int tt)
+{
+    int n = 0;
+    for (int u = 0; u < tt; ++u) n += S.kind[u] ? 1 : 0;
+    return n;
+}
 __host__ __device__ constexpr int spec_pow2(int x) { return x <= 2 ? 2 : (x <= 4 ? 4 : (x <= 8 ? 8 : 16)); }
 
 template <int NSP>
 struct TileR {
-    int32_t la0, partRow0, spec, pad;  // spec: structure id (index of the ahead-of-time instance)
+    int32_t la0, partRow0, spec, recOff;  // spec: structure id (index of the ahead-of-time instance)
     SlotR s[NSP];
 };
 
@@ -67,27 +92,6 @@ struct MegaParams {
     FsCommon c;
     TileR<NSP> tiles[kMaxTiles];
 };
-
-// deterministic reduce-scatter of M = 2..16 values per lane; the lane ends up with the total of value lane/(32/M)
-template <int M>
-__device__ __forceinline__ double reduce_scatter_n(double (&v)[M], int lane)
-{
-    const unsigned full = 0xffffffffu;
-    int off = 16;
-#pragma unroll
-    for (int m = M; m > 1; m >>= 1, off >>= 1) {
-        const bool up = lane & off;
-#pragma unroll
-        for (int j = 0; j < m / 2; ++j) {
-            const double send = up ? v[j] : v[j + m / 2];
-            const double keep = up ? v[j + m / 2] : v[j];
-            v[j] = keep + __shfl_xor_sync(full, send, off);
-        }
-    }
-#pragma unroll
-    for (; off > 0; off >>= 1) v[0] = v[0] + __shfl_xor_sync(full, v[0], off);
-    return v[0];
-}
 
 // streaming read (each element is used by exactly one lane, once per direction): do not allocate in L1
 __device__ __forceinline__ double ld_stream(const double *p)
@@ -209,21 +213,32 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
     const double zmu = p.zmu[muC], hw = p.hw[muC];
     const double bbc0 = cc[p.off_bbc + 2 * laC], bbc1 = cc[p.off_bbc + 2 * laC + 1];
     const double fourPi = 4.0 * kPi;
-    const int zeroIdx = (int)p.off_zero;
     const double r3 = rcp_full(3.0);
 
-    // ---- depth-invariant per-lane slot state
-    bool act[NSA];
-    double ca[NSA], cb[NSA], cw[NSA];  // continua: alpha, 2hc/lambda^3, wlamu (per lane)
+    // ---- compile-time record geometry (see mali_types.cuh): Vij rows, then bg chi/eta/sca, then one field per slot
+    constexpr int LW = S.lw;
+    constexpr int NLINE = spec_line_index(S, S.nslot);
+    constexpr int SB = 2 * NLINE * kVRow;  // record offset of bg chi
+#define line_index(tt) spec_line_index(S, (tt))
+    // idle lanes (lane >= Lw * Nrays) read the zero padding of the Vij rows and the last wavelength's fields; lanes
+    // past the end of the spectrum read the zero / clamped entries packed for them.  Their weights are zero.
+    const int lsC = ls < p.Lw ? ls : p.Lw - 1;
+    const int laneV = lane;
+    const double hwG = valid ? hw : 0.0;
+    const long long rowBytesStep = p.rowStride;  // doubles per depth row
+    const double *tab0 = cc + p.off_tab + T.recOff;
+
+    // ---- depth-invariant per-lane constants of the continuum slots (alpha, 2hc/lambda^3, wlamu)
+    double ca[NSA], cb[NSA], cw[NSA];
 #pragma unroll
     for (int tt = 0; tt < NS; ++tt) {
         const SlotR &s = T.s[tt];
         const int lt = laC - s.Nblue;
-        act[tt] = valid && lt >= 0 && lt < s.Nlam;
+        const bool act = valid && lt >= 0 && lt < s.Nlam;
         ca[tt] = 0.0;
         cb[tt] = 0.0;
         cw[tt] = 0.0;
-        if (!S.kind[tt] && act[tt]) {
+        if (!S.kind[tt] && act) {
             ca[tt] = __ldg(p.alpha + s.toff + lt);
             cb[tt] = __ldg(p.twohc + s.toff + lt);
             cw[tt] = (__ldg(p.wlacont + s.toff + lt) * hw) * fourPi;
@@ -233,28 +248,10 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
     for (int d = 0; d < 2; ++d) {
         const int dk = d ? -1 : 1;
         const int kS = d ? N - 1 : 0;
-        int ia[NSA], sa[NSA], ib[NSA], sb[NSA];
-#pragma unroll
-        for (int tt = 0; tt < NS; ++tt) {
-            const SlotR &s = T.s[tt];
-            const int lt = laC - s.Nblue;
-            ia[tt] = zeroIdx;
-            sa[tt] = 0;
-            ib[tt] = zeroIdx;
-            sb[tt] = 0;
-            if (act[tt]) {
-                if (S.kind[tt]) {
-                    const int strA = s.Nlam * Nrays;
-                    ia[tt] = s.tabOff + lt * Nrays + muC + (d * N + kS) * strA;
-                    sa[tt] = dk * strA;
-                    ib[tt] = s.wlaOff + lt + kS * s.Nlam;
-                    sb[tt] = dk * s.Nlam;
-                } else {
-                    ia[tt] = s.tabOff + lt + kS * s.Nlam;
-                    sa[tt] = dk * s.Nlam;
-                }
-            }
-        }
+        // one running pointer per access pattern; every table offset below is a compile-time immediate
+        const double *pV = tab0 + (size_t)kS * rowBytesStep + d * kVRow + laneV;  // Vij rows: lane order
+        const double *pS = tab0 + (size_t)kS * rowBytesStep + SB + lsC;           // per-wavelength fields
+        const long long step = dk * rowBytesStep;
         int kl = kS * Nspect + laC;
         const int dkl = dk * Nspect;
 
@@ -265,27 +262,33 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
             double chiTot = 0.0;
 #pragma unroll
             for (int tt = 0; tt < NS; ++tt) {
-                const double ld = __ldg(cc + ia[tt] + sa[tt]);
                 const double ni = sN[S.rowI[tt] * N + k], nj = sN[S.rowJ[tt] * N + k];
-                if (S.kind[tt])
+                if (S.kind[tt]) {
+                    const double ld = __ldg(pV + step + 2 * line_index(tt) * kVRow);
                     chiTot += ni * ld - nj * (T.s[tt].cA * ld);
-                else
+                } else {
+                    const double ld = __ldg(pS + step + (3 + tt) * LW);
                     chiTot += ni * ca[tt] - nj * (ld * ca[tt]);
+                }
             }
-            chiProbe = chiTot + __ldg(cc + p.off_bgchi + kl + dkl);
+            chiProbe = chiTot + __ldg(pS + step);
         }
 
         // software prefetch: the streams of step s+1 are in flight while step s is computed
         double ldN[NSA], wlN[NSA], bgcN, bgeN, bgsN, JdN;
 #pragma unroll
         for (int tt = 0; tt < NS; ++tt) {
-            ldN[tt] = __ldg(cc + ia[tt]);
             wlN[tt] = 0.0;
-            if (S.kind[tt]) wlN[tt] = __ldg(cc + ib[tt]);
+            if (S.kind[tt]) {
+                ldN[tt] = ld_stream(pV + 2 * line_index(tt) * kVRow);
+                wlN[tt] = __ldg(pS + (3 + tt) * LW);
+            } else {
+                ldN[tt] = __ldg(pS + (3 + tt) * LW);
+            }
         }
-        bgcN = __ldg(cc + p.off_bgchi + kl);
-        bgeN = __ldg(cc + p.off_bgeta + kl);
-        bgsN = __ldg(cc + p.off_bgsca + kl);
+        bgcN = __ldg(pS);
+        bgeN = __ldg(pS + LW);
+        bgsN = __ldg(pS + 2 * LW);
         JdN = Jcol[kl];
 
         Sweep sw;
@@ -312,18 +315,20 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
             }
             if (s + 1 < N) {
                 kl += dkl;
+                pV += step;
+                pS += step;
 #pragma unroll
                 for (int tt = 0; tt < NS; ++tt) {
-                    ia[tt] += sa[tt];
-                    ldN[tt] = ld_stream(cc + ia[tt]);
                     if (S.kind[tt]) {
-                        ib[tt] += sb[tt];
-                        wlN[tt] = __ldg(cc + ib[tt]);
+                        ldN[tt] = ld_stream(pV + 2 * line_index(tt) * kVRow);
+                        wlN[tt] = __ldg(pS + (3 + tt) * LW);
+                    } else {
+                        ldN[tt] = __ldg(pS + (3 + tt) * LW);
                     }
                 }
-                bgcN = __ldg(cc + p.off_bgchi + kl);
-                bgeN = __ldg(cc + p.off_bgeta + kl);
-                bgsN = __ldg(cc + p.off_bgsca + kl);
+                bgcN = __ldg(pS);
+                bgeN = __ldg(pS + LW);
+                bgsN = __ldg(pS + 2 * LW);
                 JdN = Jcol[kl];
             }
 
@@ -405,9 +410,9 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
                 for (int a = 0; a < NA; ++a) Ieff[a] = Ik - Psi * etaA[a];
 #pragma unroll
                 for (int tt = 0; tt < NS; ++tt) {
-                    const double wlamu = S.kind[tt] ? (wl[tt] * hw) * fourPi : cw[tt];  // rh_method.py:665
+                    const double wlamu = S.kind[tt] ? (wl[tt] * hwG) * fourPi : cw[tt];  // rh_method.py:665
                     const double Ie = Ieff[S.atom[tt]];
-                    // Ulvl of a level no active transition has as its upper level is exactly 0: the reference's
+                    // Ulvl of a level no transition of the tile has as its upper level is exactly 0: the reference's
                     // (chi*Psi)*0.0 term is +-0 and drops out of the subtraction
                     bool uJ = false, uI = false;
                     for (int u = 0; u < NS; ++u) {
@@ -418,7 +423,7 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
                     if (uJ) g1 = g1 - ((chiL[S.lvI[tt]] * Psi) * UL[S.lvJ[tt]]);
                     double g2 = Vij[tt] * Ie;
                     if (uI) g2 = g2 - ((chiL[S.lvJ[tt]] * Psi) * UL[S.lvI[tt]]);
-                    v[2 * tt] = g1 * wlamu;  // inactive lanes: wlamu == 0
+                    v[2 * tt] = g1 * wlamu;  // wavelengths without this transition: wlamu == 0 (zero table entries)
                     v[2 * tt + 1] = g2 * wlamu;
                 }
                 const double tot = reduce_transpose<M>(v, lane, red);
@@ -428,7 +433,7 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
         if (d == 1 && valid) p.I[(size_t)col * p.IStride + (size_t)la * Nrays + mu] = sw.Iupw;
         if (valid && sw.bad && p.status != nullptr) atomicOr(p.status + col, 2);
     }
-
+#undef line_index
 }
 
 // ---- registry of ahead-of-time instances -----------------------------------------------------------------

@@ -322,7 +322,9 @@ __global__ void __launch_bounds__(128) fs_gamma_kernel(const FsParams p)
 
     const double *cc = p.colconst + (size_t)col * p.colStride;
     const double *zz = cc + p.off_z;
-    const double *bgchi = cc + p.off_bgchi, *bgeta = cc + p.off_bgeta, *bgsca = cc + p.off_bgsca;
+    const double *tab = cc + p.off_tab + td.recOff;   // this tile's record of depth row 0
+    const int lsC = valid ? ls : 0;
+    const int laneV = valid ? lane : 0;
     const double *npop = p.pops + (size_t)col * p.popStride;
     double *Jcol = p.J + (size_t)col * p.JStride;
     double *scr = p.scratch + (size_t)col * p.scratchStride;
@@ -359,16 +361,16 @@ __global__ void __launch_bounds__(128) fs_gamma_kernel(const FsParams p)
                 const int lt = laC - sd.Nblue;
                 const bool act = valid && lt >= 0 && lt < sd.Nlam;
                 const int ltC = act ? lt : 0;
+                const double *rec = tab + (size_t)k * p.rowStride;
                 double Vij, Vji, Uji;
                 if (sd.isLine) {
-                    const double phi =
-                        act ? __ldg(cc + sd.tabOff + ((size_t)(d * N + k) * sd.Nlam + ltC) * Nrays + muC) : 0.0;
+                    const double phi = act ? __ldg(rec + sd.vOff + d * kVRow + laneV) : 0.0;
                     Vij = phi;  // the table holds hc/4pi*Bij*phi (rh_method.py:279), folded in at upload
                     Vji = sd.c2 * Vij;
                     Uji = sd.c1 * Vji;
                 } else {
                     const double a = act ? __ldg(p.alpha + sd.toff + ltC) : 0.0;
-                    const double g = act ? __ldg(cc + sd.tabOff + (size_t)k * sd.Nlam + ltC) : 0.0;
+                    const double g = act ? __ldg(rec + sd.fOff + lsC) : 0.0;
                     Vij = a;
                     Vji = g * Vij;
                     Uji = __ldg(p.twohc + sd.toff + ltC) * Vji;
@@ -386,14 +388,15 @@ __global__ void __launch_bounds__(128) fs_gamma_kernel(const FsParams p)
                 etaTot += eta_t;
             }
             const size_t kl = (size_t)k * Nspect + laC;
-            chiTot += __ldg(bgchi + kl);
+            const double *bg = tab + (size_t)k * p.rowStride + td.bgOff + lsC;
+            chiTot += __ldg(bg);
             if (probe) {
                 chiProbe = chiTot;
                 continue;
             }
             const double Jdag = Jcol[kl];
             const double rchi = rcp_full(chiTot);
-            const double S = div_by(etaTot + __ldg(bgeta + kl) + __ldg(bgsca + kl) * Jdag, chiTot, rchi);
+            const double S = div_by(etaTot + __ldg(bg + p.Lw) + __ldg(bg + 2 * p.Lw) * Jdag, chiTot, rchi);
 
             // ---- (2) short characteristic: formal_solver.py
             const double zk = zz[k];
@@ -425,17 +428,17 @@ __global__ void __launch_bounds__(128) fs_gamma_kernel(const FsParams p)
                         const int lt = laC - sd.Nblue;
                         const bool act = valid && lt >= 0 && lt < sd.Nlam;
                         const int ltC = act ? lt : 0;
+                        const double *rec = tab + (size_t)k * p.rowStride;
                         double Vij, Vji, Uji, wla;
                         if (sd.isLine) {
-                            const double phi =
-                                act ? __ldg(cc + sd.tabOff + ((size_t)(d * N + k) * sd.Nlam + ltC) * Nrays + muC) : 0.0;
-                            Vij = phi;  // the table holds hc/4pi*Bij*phi (rh_method.py:279), folded in at upload
+                            const double phi = act ? __ldg(rec + sd.vOff + d * kVRow + laneV) : 0.0;
+                            Vij = phi;
                             Vji = sd.c2 * Vij;
                             Uji = sd.c1 * Vji;
-                            wla = act ? __ldg(cc + sd.wlaOff + (size_t)k * sd.Nlam + ltC) : 0.0;
+                            wla = act ? __ldg(rec + sd.fOff + lsC) : 0.0;
                         } else {
                             const double a = act ? __ldg(p.alpha + sd.toff + ltC) : 0.0;
-                            const double g = act ? __ldg(cc + sd.tabOff + (size_t)k * sd.Nlam + ltC) : 0.0;
+                            const double g = act ? __ldg(rec + sd.fOff + lsC) : 0.0;
                             Vij = a;
                             Vji = g * Vij;
                             Uji = __ldg(p.twohc + sd.toff + ltC) * Vji;
@@ -611,21 +614,21 @@ __global__ void sweep_hook_kernel(int N, int nray, const double *z, const double
 }
 
 // Test hook: ComputationalTransition.uv from the packed device tables of one column.
-__global__ void uv_hook_kernel(const FsParams p, int col, SlotDesc sd, int la, int mu, int d, double *Uji,
-                               double *Vij, double *Vji)
+__global__ void uv_hook_kernel(const FsParams p, int col, SlotDesc sd, int recOff, int la, int ls, int mu, int d,
+                               double *Uji, double *Vij, double *Vji)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= p.N) return;
-    const double *cc = p.colconst + (size_t)col * p.colStride;
+    const double *rec = p.colconst + (size_t)col * p.colStride + p.off_tab + (size_t)k * p.rowStride + recOff;
     const int lt = la - sd.Nblue;
     double vij, vji, uji;
     if (sd.isLine) {
-        vij = cc[sd.tabOff + ((size_t)(d * p.N + k) * sd.Nlam + lt) * p.Nrays + mu];  // hc/4pi*Bij*phi
+        vij = rec[sd.vOff + d * kVRow + ls * p.Nrays + mu];  // hc/4pi*Bij*phi
         vji = sd.c2 * vij;
         uji = sd.c1 * vji;
     } else {
         vij = p.alpha[sd.toff + lt];
-        vji = cc[sd.tabOff + (size_t)k * sd.Nlam + lt] * vij;
+        vji = rec[sd.fOff + ls] * vij;
         uji = p.twohc[sd.toff + lt] * vji;
     }
     Uji[k] = uji;
@@ -634,43 +637,78 @@ __global__ void uv_hook_kernel(const FsParams p, int col, SlotDesc sd, int la, i
 }
 
 // --------------------------------------------------------------------------------------------------------
-// Upload path: the host pack is a plain concatenation of the reference's depth-contiguous arrays; these kernels
-// turn it into the depth-major, wavelength-contiguous device layout.
-struct TransposeJob {
-    int64_t srcOff, dstOff;  // doubles, inside hostpack / colconst
-    int32_t R, C;            // src is [R][C], dst is [C][R]
-    int32_t tile0;           // first 32x32 tile of this job in the flat tile list
-    int32_t tilesC;          // tiles along C
-    double scale;            // dst = scale * src (1.0, or hc/4pi*Bij for a line's phi -> Vij table)
+// Upload path: the host pack is a plain concatenation of the reference's depth-contiguous arrays; pack_tiles_kernel
+// gathers it into the tile-major records (see mali_types.cuh).  32 x 32 tiles through shared memory: reads are
+// coalesced along depth (the source's contiguous axis), writes along the record (the destination's).
+struct PackSlot {
+    int32_t isLine, Nblue, Nlam, lineIdx, toff, pad;
+    int64_t srcOff;   // host pack: lines phi[Nlam][Nrays][2][N]; continua g_ij[Nlam][N]
+    int64_t wphiOff;  // host pack: wphi[N] of the line
+    double c0;        // hc/4pi*Bij
+};
+struct PackTile {
+    int32_t recOff, recSize, la0, nslot, slot0, sb, pad0, pad1;  // sb: record offset of bg chi
+};
+struct PackChunk {
+    int32_t tile, e0;  // 32 consecutive record elements of one tile
 };
 
-__global__ void pack_transpose_kernel(const TransposeJob *jobs, int njobs, const double *staging, int64_t hpStride,
-                                      double *colconst, int64_t colStride, int col0)
+__global__ void pack_tiles_kernel(const PackChunk *chunks, const PackTile *tiles, const PackSlot *slots,
+                                  const double *wlambda, int N, int Nrays, int Nspect, int Lw, const double *staging,
+                                  int64_t hpStride, int64_t hpBgChi, int64_t hpBgEta, int64_t hpBgSca, double *colconst,
+                                  int64_t colStride, int64_t offTab, int64_t rowStride, int col0)
 {
     __shared__ double tile[32][33];
-    const int flat = blockIdx.x;
-    int lo = 0, hi = njobs - 1;
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (jobs[mid].tile0 <= flat)
-            lo = mid;
-        else
-            hi = mid - 1;
-    }
-    const TransposeJob jb = jobs[lo];
-    const int tl = flat - jb.tile0;
-    const int tr = tl / jb.tilesC, tc = tl - tr * jb.tilesC;
-    const double *src = staging + (size_t)blockIdx.y * hpStride + jb.srcOff;
-    double *dst = colconst + (size_t)(col0 + blockIdx.y) * colStride + jb.dstOff;
+    const PackChunk ch = chunks[blockIdx.x];
+    const PackTile pt = tiles[ch.tile];
+    const double *src = staging + (size_t)blockIdx.z * hpStride;
+    double *dst = colconst + (size_t)(col0 + blockIdx.z) * colStride + offTab + pt.recOff;
     const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+    const int k = blockIdx.y * 32 + tx;
     for (int q = ty; q < 32; q += 8) {
-        const int r = tr * 32 + q, c = tc * 32 + tx;
-        if (r < jb.R && c < jb.C) tile[q][tx] = src[(size_t)r * jb.C + c];
+        const int e = ch.e0 + q;
+        double v = 0.0;
+        if (e < pt.recSize && k < N) {
+            if (e < pt.sb) {  // Vij rows
+                const int j = e / (2 * kVRow), d = (e / kVRow) & 1, idx = e % kVRow;
+                const int ls = idx / Nrays, mu = idx - ls * Nrays;
+                int sq = -1;
+                for (int u = 0; u < pt.nslot; ++u)
+                    if (slots[pt.slot0 + u].isLine && slots[pt.slot0 + u].lineIdx == j) sq = u;
+                if (sq >= 0 && ls < Lw) {
+                    const PackSlot ps = slots[pt.slot0 + sq];
+                    const int la = pt.la0 + ls, lt = la - ps.Nblue;
+                    if (la < Nspect && lt >= 0 && lt < ps.Nlam)
+                        v = ps.c0 * src[ps.srcOff + ((size_t)(lt * Nrays + mu) * 2 + d) * N + k];
+                }
+            } else {
+                const int f = (e - pt.sb) / Lw, ls = (e - pt.sb) - f * Lw;
+                const int la = pt.la0 + ls;
+                const int laClamp = la < Nspect ? la : Nspect - 1;
+                if (f == 0)
+                    v = src[hpBgChi + (size_t)laClamp * N + k];
+                else if (f == 1)
+                    v = src[hpBgEta + (size_t)laClamp * N + k];
+                else if (f == 2)
+                    v = src[hpBgSca + (size_t)laClamp * N + k];
+                else if (f - 3 < pt.nslot) {
+                    const PackSlot ps = slots[pt.slot0 + f - 3];
+                    const int lt = la - ps.Nblue;
+                    if (la < Nspect && lt >= 0 && lt < ps.Nlam) {
+                        if (ps.isLine)  // wla = wlambda(lt) * wphi[k] / HC   (rh_method.py:451)
+                            v = wlambda[ps.toff + lt] * src[ps.wphiOff + k] / kHC;
+                        else
+                            v = src[ps.srcOff + (size_t)lt * N + k];
+                    }
+                }
+            }
+        }
+        tile[q][tx] = v;
     }
     __syncthreads();
     for (int q = ty; q < 32; q += 8) {
-        const int c = tc * 32 + q, r = tr * 32 + tx;
-        if (r < jb.R && c < jb.C) dst[(size_t)c * jb.R + r] = jb.scale * tile[tx][q];
+        const int kk = blockIdx.y * 32 + q, e = ch.e0 + tx;
+        if (kk < N && e < pt.recSize) dst[(size_t)kk * rowStride + e] = tile[tx][q];
     }
 }
 
@@ -679,16 +717,9 @@ struct CopyJob {
     int32_t toPops;  // destination is the pops buffer instead of colconst
     int32_t pad;
 };
-struct WlaJob {
-    int64_t wphiOff;  // hostpack offset of wphi[t][N]
-    int64_t dstOff;   // colconst offset of wla[N][Nlam]
-    int32_t toff, Nlam;
-};
-
-__global__ void pack_misc_kernel(const CopyJob *copies, int ncopies, const WlaJob *wlas, int nwla,
-                                 const double *wlambda, int N, const double *staging, int64_t hpStride,
+__global__ void pack_misc_kernel(const CopyJob *copies, int ncopies, const double *staging, int64_t hpStride,
                                  double *colconst, int64_t colStride, double *pops, int64_t popStride, double *J,
-                                 int64_t JStride, int col0, int64_t offZero)
+                                 int64_t JStride, int col0)
 {
     const int col = col0 + blockIdx.y;
     const double *src = staging + (size_t)blockIdx.y * hpStride;
@@ -699,18 +730,8 @@ __global__ void pack_misc_kernel(const CopyJob *copies, int ncopies, const WlaJo
         double *dst = cj.toPops ? pops + (size_t)col * popStride + cj.dstOff : cc + cj.dstOff;
         for (int64_t q = tid; q < cj.len; q += nth) dst[q] = src[cj.srcOff + q];
     }
-    // wla[k][lt] = wlambda(lt) * wphi[k] / HC   (rh_method.py:451)
-    for (int w = 0; w < nwla; ++w) {
-        const WlaJob wj = wlas[w];
-        const int64_t tot = (int64_t)N * wj.Nlam;
-        for (int64_t q = tid; q < tot; q += nth) {
-            const int k = (int)(q / wj.Nlam), lt = (int)(q - (int64_t)k * wj.Nlam);
-            cc[wj.dstOff + q] = wlambda[wj.toff + lt] * src[wj.wphiOff + k] / kHC;
-        }
-    }
     double *Jc = J + (size_t)col * JStride;
     for (int64_t q = tid; q < JStride; q += nth) Jc[q] = 0.0;
-    if (tid < 16) cc[offZero + tid] = 0.0;
 }
 
 }  // namespace mali

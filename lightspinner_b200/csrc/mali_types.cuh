@@ -4,6 +4,15 @@
 // (wavelength la, angle mu) pair of a column, swept down (toFrom=0) then up (toFrom=1) over the
 // Nspace depth points; a *tile* is the group of Lw = 32 / Nrays consecutive wavelengths (all angles)
 // one warp owns; a *slot* is one radiative transition overlapping a tile's wavelength range.
+//
+// The iteration-invariant per-column tables are stored TILE-MAJOR: for every depth k one row of `rowStride` doubles
+// holding, tile after tile, one contiguous *record* with everything the tile's warp reads at that depth:
+//     [ Vij rows: per line slot, direction 0 then 1, each kVRow = 32 doubles = (wavelength, angle) in lane order ]
+//     [ bg chi[Lw] | bg eta[Lw] | bg sca[Lw] ]
+//     [ per slot: wla[Lw] (lines, rh_method.py:451) or g_ij[Lw] (continua, :453-454) ]      (padded to 16 doubles)
+// Entries for wavelengths on which a transition is not active are zero, so the kernels need no activity masks for
+// their loads; rows are 128-byte aligned, every warp load is a full-sector burst, and all streams of a warp advance
+// by the same stride per depth step.
 #pragma once
 #include <cstdint>
 
@@ -26,9 +35,9 @@ struct SlotDesc {
     int32_t lsI, lsJ;    // level-slot of the lower / upper level inside the tile
     int32_t toff;        // offset of this transition in the per-wavelength tables (alpha, twohc, wlacont)
     int32_t flags;       // bit 0 / 1: this slot is the first of its tile to touch level-slot lsI / lsJ
+    int32_t fOff;        // record offset of the slot's per-wavelength field: wla[Lw] (lines) or g_ij[Lw] (continua)
+    int32_t vOff;        // lines: record offset of the direction-0 Vij row (direction 1 follows at +kVRow); else -1
     int32_t pad;
-    int64_t tabOff;      // colconst offset: lines Vij[2][N][Nlam][Nrays] (= hc/4pi*Bij*phi); continua gij[N][Nlam]
-    int64_t wlaOff;      // colconst offset: lines wla[N][Nlam] = wlambda*wphi/HC   (rh_method.py:451)
     double c0, c1, c2;   // lines: hc/4pi*Bij (folded into the Vij table at upload), Aji/Bji, Bji/Bij  (rh_method.py:279-281,450)
 };
 
@@ -38,8 +47,12 @@ struct TileDesc {
     int32_t slot0;     // first SlotDesc of the tile
     int32_t nlevslot;  // distinct (atom, level) pairs touched by the tile's slots
     int32_t partRow0;  // first row of the tile's Gamma partials (2 rows per slot: [i,j] then [j,i])
-    int32_t pad[3];
+    int32_t recOff;    // offset of the tile's record inside a depth row
+    int32_t bgOff;     // record offset of bg chi[Lw] (eta, sca follow at +Lw, +2Lw)
+    int32_t pad;
 };
+
+constexpr int kVRow = 32;  // doubles per Vij row of a record (Lw * Nrays <= 32 lanes, zero padded)
 
 // Kernel parameters (passed by value -> constant bank).
 struct FsParams {
@@ -50,7 +63,7 @@ struct FsParams {
     // strides (doubles per column)
     int64_t colStride, popStride, JStride, IStride, scratchStride;
     // offsets inside one column's colconst block
-    int64_t off_z, off_bbc, off_bgchi, off_bgeta, off_bgsca;
+    int64_t off_z, off_bbc, off_tab, rowStride;
     // offsets inside one column's scratch block
     int64_t off_jpart, off_part;
     // model tables (device)

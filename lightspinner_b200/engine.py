@@ -166,6 +166,12 @@ class MaliEngine:
         _capi.check(self.lib.mali_profile_end(self._handle, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    def model_info(self):
+        out = (C.c_int32 * 8)()
+        _capi.check(self.lib.mali_model_info(self._handle, out))
+        keys = ('ntile', 'spec_tiles', 'generic_tiles', 'max_slots', 'max_levels', 'row_stride', 'smem_per_warp', 'tma')
+        return dict(zip(keys, list(out)))
+
     def launch_count(self):
         return int(self.lib.mali_launch_count(self._handle))
 
