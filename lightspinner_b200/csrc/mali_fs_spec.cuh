@@ -67,7 +67,7 @@ __host__ __device__ constexpr int spec_class_slots(int cls) { return cls == 0 ? 
 #define MALI_OCC1 12
 #endif
 #ifndef MALI_OCC2
-#define MALI_OCC2 8
+#define MALI_OCC2 12
 #endif
 __host__ __device__ constexpr int spec_class_warps(int cls) { return cls == 0 ? MALI_OCC0 : (cls == 1 ? MALI_OCC1 : MALI_OCC2); }
 // number of line slots among the first tt slots (tt == nslot: all of them) -> position of a line's Vij rows
