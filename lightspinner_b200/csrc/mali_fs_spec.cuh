@@ -294,6 +294,7 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
         Sweep sw;
         sw.r3 = r3;
         sw.stab = stab;
+#pragma unroll 2
         for (int s = 0; s < N; ++s) {
             const int k = kS + s * dk;
             double ld[NSA], wl[NSA];
