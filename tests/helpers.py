@@ -162,3 +162,64 @@ def fake_reference_objects(p):
     bg = _NS()
     bg.chi, bg.eta, bg.sca = np.array(p['bg_chi']), np.array(p['bg_eta']), np.array(p['bg_sca'])
     return atmos, spect, eqPops, bg
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Mutated fixtures: ragged / edge-case problems derived from a reference fixture.  They are not outputs of the
+# reference any more, so the checker for them is the oracle (which is pinned to the reference on the originals).
+def drop_depth(p, k):
+    """The same problem with depth point k removed (odd Nspace -> no TMA staging path, different tile tails)."""
+    N = int(p['Nspace'])
+    keep = np.array([q for q in range(N) if q != k])
+    q = dict(p)
+    q['Nspace'] = N - 1
+    for key in ('height', 'temperature', 'vlos', 'vturb'):
+        if key in p:
+            q[key] = np.array(p[key])[keep]
+    for key in ('bg_chi', 'bg_eta', 'bg_sca', 'nStar', 'nTotal', 'C', 'n', 'wphi', 'aDamp', 'vBroad'):
+        if key in p:
+            q[key] = np.ascontiguousarray(np.array(p[key])[..., keep])
+    phi = np.array(p['phi']).reshape(-1, N)[:, keep]
+    q['phi'] = np.ascontiguousarray(phi).reshape(-1)
+    q['phioff'] = (np.array(p['phioff'], dtype=np.int64) // N) * (N - 1)
+    return q
+
+
+def select_rays(p, rays):
+    """The same problem restricted to the given angle indices (e.g. a single ray: 32 wavelengths per warp)."""
+    N, R = int(p['Nspace']), int(p['Nrays'])
+    rays = list(rays)
+    q = dict(p)
+    q['Nrays'] = len(rays)
+    q['muz'] = np.array(p['muz'])[rays]
+    q['wmu'] = np.array(p['wmu'])[rays]
+    phi = np.array(p['phi']).reshape(-1, R, 2, N)[:, rays]
+    q['phi'] = np.ascontiguousarray(phi).reshape(-1)
+    q['phioff'] = (np.array(p['phioff'], dtype=np.int64) // R) * len(rays)
+    return q
+
+
+def only_transitions(p, keep):
+    """The same problem with only the listed transitions radiatively active (possibly none)."""
+    keep = list(keep)
+    tr = np.array(p['trans']).reshape(-1, 6)
+    N, R = int(p['Nspace']), int(p['Nrays'])
+    toff = np.concatenate([[0], np.cumsum(tr[:, 5])]).astype(int)
+    q = dict(p)
+    q['trans'] = tr[keep].reshape(-1, 6)
+    q['linepar'] = np.array(p['linepar']).reshape(-1, 4)[keep].reshape(-1, 4)
+    q['alpha'] = np.concatenate([np.array(p['alpha'])[toff[t]:toff[t + 1]] for t in keep]) if keep else np.zeros(0)
+    q['wphi'] = np.array(p['wphi'])[keep].reshape(-1, N)
+    phis, offs, o = [], [], 0
+    for t in keep:
+        if tr[t, 3]:
+            sz = int(tr[t, 5]) * R * 2 * N
+            po = int(p['phioff'][t])
+            phis.append(np.array(p['phi'])[po:po + sz])
+            offs.append(o)
+            o += sz
+        else:
+            offs.append(0)
+    q['phi'] = np.concatenate(phis) if phis else np.zeros(0)
+    q['phioff'] = np.array(offs, dtype=np.int64)
+    return q
