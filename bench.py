@@ -184,7 +184,7 @@ def main():
     ap.add_argument('--ncol', type=int, default=1024, help='columns per GPU')
     ap.add_argument('--iters', type=int, default=16, help='MALI iterations per solve (= per step)')
     ap.add_argument('--fixture', default='c2_falc_cah')
-    ap.add_argument('--chunk', type=int, default=128, help='columns per upload chunk in the e2e path')
+    ap.add_argument('--chunk', type=int, default=256, help='columns per upload chunk in the e2e path')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     args = ap.parse_args()
@@ -211,6 +211,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        os.environ['NCCL_DEBUG'] = os.environ.get('MALI_NCCL_DEBUG', 'WARN')   # keep stdout to the one JSON line
         dist.init_process_group('nccl', device_id=dev)
 
     def barrier():
@@ -281,8 +282,16 @@ def main():
     fs_ms_mean = fs_ms / max(fs_n, 1)
     alg_bytes = algorithmic_bytes_per_column(base) * ncol
     achieved = alg_bytes / (fs_ms_mean * 1e-3) / 1e9
-    roofline = {'kernel': 'fs_gamma_kernel', 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+    traffic = None
+    try:    # DRAM bytes per launch from the committed ncu capture of this very configuration (profiles/)
+        tj = json.load(open(os.path.join(ROOT, 'profiles', 'traffic_latest.json')))
+        if int(tj['ncol']) == ncol and tj['fixture'] == args.fixture:
+            traffic = float(tj['traffic_bytes_per_launch'])
+    except Exception:
+        pass
+    roofline = {'kernel': 'fs_gamma_kernel_m<0,1,2> (formal solution + Gamma stage: 3 launches)', 'bound': 'hbm',
+                'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': alg_bytes, 'mean_launch_ms': fs_ms_mean, 'launches_timed': fs_n,
                 'share_of_step': fs_ms / ms if ms > 0 else None,
                 'note': 'fp64 CUDA-core work binds before HBM on this path (SURVEY.md 7.3-2); see DESIGN.md'}
