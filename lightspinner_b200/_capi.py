@@ -43,18 +43,19 @@ EXPORTS = ['mali_last_error', 'mali_device_count', 'mali_model_create', 'mali_mo
            'mali_piecewise_linear_1d', 'mali_uv', 'mali_exp_hook', 'mali_div_hook', 'mali_profile_begin',
            'mali_profile_end', 'mali_launch_count', 'mali_fp64_peak']
 
-_lib = None
+_libs = {}
 
 
-def load():
-    """Load the shared library (building it is the job of lightspinner_b200.build / __graft_entry__.build)."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.isfile(LIB_PATH):
+def load(path=None):
+    """Load the shared library (building it is the job of lightspinner_b200.build / __graft_entry__.build).
+    `path`: a model-specific variant built by lightspinner_b200.specialize (same ABI, other kernel instances)."""
+    path = LIB_PATH if path is None else path
+    if path in _libs:
+        return _libs[path]
+    if not os.path.isfile(path):
         raise ImportError('%s is missing: run `python -m lightspinner_b200.build` (nvcc, sm_100a). '
-                          'There is no CPU fallback for the MALI hot path.' % LIB_PATH)
-    L = C.CDLL(LIB_PATH)
+                          'There is no CPU fallback for the MALI hot path.' % path)
+    L = C.CDLL(path)
     L.mali_last_error.restype = C.c_char_p
     L.mali_device_count.restype = C.c_int
     L.mali_model_create.argtypes = [C.POINTER(ModelDesc), C.c_int, C.POINTER(C.c_void_p)]
@@ -78,7 +79,7 @@ def load():
     L.mali_fp64_peak.argtypes = [C.c_int32, C.c_void_p, C.POINTER(C.c_double)]
     L.mali_exp_hook.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.mali_uv.argtypes = [C.c_void_p, C.POINTER(Buffers)] + [C.c_int32] * 5 + [C.c_void_p] * 4
-    _lib = L
+    _libs[path] = L
     return L
 
 

@@ -37,20 +37,23 @@ def stale():
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS) or os.path.getmtime(__file__) > t
 
 
-def build(force=False, verbose=False):
-    if not force and not stale():
+def build(force=False, verbose=False, lib=None, spec_inc=None):
+    """Build libmali_b200.so, or (lib, spec_inc given) a model-specific variant with other kernel instances."""
+    lib = LIB if lib is None else lib
+    if lib == LIB and not force and not stale():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
-    cmd = [nvcc_path()] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + \
+    extra = ['-DMALI_SPEC_INC="%s"' % spec_inc] if spec_inc else []
+    cmd = [nvcc_path()] + NVCC_FLAGS + extra + (['-Xptxas', '-v'] if verbose else []) + \
         ['-ccbin', '/usr/bin/g++' if os.path.isfile('/usr/bin/g++') else 'g++'] + \
-        ['-o', LIB + '.tmp'] + [os.path.join(CSRC, s) for s in SOURCES]
+        ['-o', lib + '.tmp'] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
-        raise RuntimeError('nvcc failed building libmali_b200.so')
-    os.replace(LIB + '.tmp', LIB)
-    return LIB
+        raise RuntimeError('nvcc failed building %s' % os.path.basename(lib))
+    os.replace(lib + '.tmp', lib)
+    return lib
 
 
 if __name__ == '__main__':

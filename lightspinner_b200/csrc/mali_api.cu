@@ -83,16 +83,20 @@ __global__ void iterate_ctl_kernel(int phase, double *dJ, double *dPops, int32_t
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------
-// Ahead-of-time instances of the structure-specialised kernel (generated: tools/gen_spec_instances.py)
+// Ahead-of-time instances of the structure-specialised kernel (generated: tools/gen_spec_instances.py; a
+// model-specific library is built with -DMALI_SPEC_INC=\"<file>\" by lightspinner_b200/specialize.py)
+#ifndef MALI_SPEC_INC
+#define MALI_SPEC_INC "spec_instances.inc"
+#endif
 #define MALI_SPEC(ID, KEY, ...)                          \
     struct SpecTag##ID {                                 \
         static constexpr TileStruct S = {__VA_ARGS__};   \
     };
-#include "spec_instances.inc"
+#include MALI_SPEC_INC
 #undef MALI_SPEC
 #define MALI_SPEC(ID, KEY, ...) {KEY, SpecTag##ID::S.nslot, ID},
 static const SpecEntry kSpecRegistry[] = {
-#include "spec_instances.inc"
+#include MALI_SPEC_INC
     {nullptr, 0, 0}};
 #undef MALI_SPEC
 
@@ -110,7 +114,7 @@ __global__ void __launch_bounds__(32, spec_class_warps(CLS)) fs_gamma_kernel_m(c
     case ID:                                                                                           \
         if constexpr (spec_class(SpecTag##ID::S.nslot) == CLS) fs_body<SpecTag##ID>(P.c, T, smem_raw); \
         break;
-#include "spec_instances.inc"
+#include MALI_SPEC_INC
 #undef MALI_SPEC
         default:
             break;

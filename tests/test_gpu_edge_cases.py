@@ -140,3 +140,27 @@ def test_singular_system_raises_linalgerror():
     with pytest.raises(np.linalg.LinAlgError):
         eng.stat_equil()
     eng.close()
+
+
+def test_runtime_specialisation_builds_model_specific_kernels(oracle):
+    """A model whose tile structures have no ahead-of-time instance (2 rays) gets a model-specific library built
+    with nvcc (lightspinner_b200.specialize) and then runs entirely on specialised kernels, same results."""
+    from lightspinner_b200 import specialize
+    from lightspinner_b200.engine import MaliEngine
+    p, _ = load_golden('c1_falc_ca')
+    q = select_rays(p, [0, 4])
+    assert set(specialize.tile_structures(q)) - set(specialize.stock_keys())
+    eng = MaliEngine(q, 1, specialize=True)
+    info = eng.model_info()
+    assert info['generic_tiles'] == 0 and info['spec_tiles'] == info['ntile'], info
+    eng.upload([q])
+    oc = oracle.OracleContext(q)
+    for it in range(1, 6):
+        eng.set_n(0, oc.n)
+        eng.formal_sol_gamma_matrices()
+        oc.formal_sol_gamma_matrices()
+        if it > 3:
+            eng.stat_equil()
+            oc.stat_equil(use_scipy=True)
+    assert relerr(eng.J(0), oc.J) < 1e-13 and relerr(eng.I(0), oc.I) < 1e-13 and relerr(eng.n(0), oc.n) < 1e-9
+    eng.close()

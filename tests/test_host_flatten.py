@@ -72,3 +72,15 @@ def test_context_host_mirror_against_live_reference():
     ctx = Context(atmos, spect, eq2, bg, _host_only=True)
     for k in KEYS:
         assert np.array_equal(np.asarray(ctx._problem[k]), np.asarray(pr[k])), k
+
+
+def test_stock_kernel_instances_cover_the_fixture_models():
+    """tools/gen_spec_instances.py and mali_api.cu must agree on the structure keys: every tile of the fixture
+    models has an ahead-of-time instance (the GPU twin checks model_info()['generic_tiles'] == 0)."""
+    from lightspinner_b200 import specialize
+    have = set(specialize.stock_keys())
+    assert len(have) >= 40
+    for name in ['c1_falc_ca', 'c2_falc_cah', 'c1v_jitter_ca3', 'rf_k40p']:
+        p, _ = load_golden(name)
+        assert set(specialize.tile_structures(p)) <= have, name
+        assert specialize.library_for(p) is None
