@@ -175,6 +175,7 @@ struct mali_model {
     int64_t off_z = 0, off_bbc = 0, off_C = 0, off_nTotal = 0, off_tab = 0, rowStride = 0;
     int64_t off_jpart = 0, off_part = 0;
     int smemPopDoubles = 0, smemZOff = 0, smemLvlOff = 0, smemMbarOff = 0, smemExpOff = 0, smemBytesPerWarp = 0, useBulk = 0;
+    int ringStage[3] = {16, 16, 16};
     std::vector<CopyJob> cjobs;
     int packChunks = 0;
     // device copies
@@ -351,7 +352,7 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
             s.flags = 0;
             s.lsI = slot_of(tr[1], 1);
             s.lsJ = slot_of(tr[2], 2);
-            if (s.isLine) s.vOff = 2 * kVRow * nLine++;
+            if (s.isLine) s.vOff = kVRow * nLine++;
             trRows[t].push_back(partRow);
             partRow += 2;
             m->slots.push_back(s);
@@ -384,6 +385,7 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
         ptiles.push_back(pt);
         td.recOff = pt.recOff;
         td.bgOff = sb;
+        td.vDir = kVRow * nLine;
         td.nlevslot = (int)lev.size();
         rowOff += pt.recSize;
         m->Dmax = std::max(m->Dmax, td.nlevslot);
@@ -496,8 +498,17 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
         m->smemZOff = even(m->smemPopDoubles);
         m->smemLvlOff = m->smemZOff + even(N);
         m->smemMbarOff = (m->smemLvlOff + std::max(std::max(m->Dmax, 1) * 64 + d->Natom * 32, 16 * 36)) * 8;
-        m->smemExpOff = (int)align_up(m->smemMbarOff + 16, 16);
-        m->smemBytesPerWarp = m->smemExpOff + 128 * 16;
+        m->smemExpOff = (int)align_up(m->smemMbarOff + 32, 16);  // staging barrier + three ring barriers
+        m->smemBytesPerWarp = m->smemExpOff + 128 * 16;   // generic kernel / upper bound without the TMA ring
+        // TMA ring of the specialised kernels, per register class: 3 stages of the largest record part one sweep
+        // direction needs (its Vij rows + the per-wavelength fields)
+        for (int c = 0; c < 3; ++c) m->ringStage[c] = 16;
+        for (size_t ti = 0; ti < ptiles.size(); ++ti) {
+            const PackTile &pt = ptiles[ti];
+            if (pt.nslot > kSpecMaxSlots) continue;
+            int &st = m->ringStage[spec_class(pt.nslot)];
+            st = std::max(st, pt.recSize - pt.sb / 2);
+        }
         m->useBulk = (N % 2 == 0 && m->smemPopDoubles % 2 == 0) ? 1 : 0;  // cp.async.bulk: 16-byte sizes / addresses
     }
 
@@ -767,13 +778,24 @@ static int launch_fs(const mali_model *m, const mali_buffers *b, int col0, int n
         m->launches += 1;
     }
     if (m->specTiles > 0) {
-        const FsCommon c = make_fs_common(m, b, col0, ncol);
-        const size_t smem = (size_t)m->smemBytesPerWarp;
-        if (smem > 227 * 1024) return fail(MALI_ELIMIT, "column needs %zu B of shared memory per warp", smem);
+        // per-warp shared memory of a class: populations | heights | reduce scratch | barriers | exp table | TMA ring
+        FsCommon cc[3];
+        size_t smem[3];
+        for (int cls = 0; cls < 3; ++cls) {
+            FsCommon &c = cc[cls];
+            c = make_fs_common(m, b, col0, ncol);
+            const int red = spec_pow2(2 * spec_class_slots(cls)) * 36;
+            c.mbarOffBytes = (c.lvlOffDoubles + red) * 8;
+            c.expTabOffBytes = (int)align_up(c.mbarOffBytes + 32, 16);
+            c.ringOffDoubles = (c.expTabOffBytes + 128 * 16) / 8;
+            c.smemBytesPerWarp = (c.ringOffDoubles + 3 * m->ringStage[cls]) * 8;
+            smem[cls] = (size_t)c.smemBytesPerWarp;
+            if (smem[cls] > 227 * 1024) return fail(MALI_ELIMIT, "column needs %zu B of shared memory per warp", smem[cls]);
+        }
         cudaError_t e = cudaSuccess;
-        if (!m->spec2.empty()) e = launch_mega<2>(c, m->spec2, ncol, smem, st, &m->launches);
-        if (e == cudaSuccess && !m->spec1.empty()) e = launch_mega<1>(c, m->spec1, ncol, smem, st, &m->launches);
-        if (e == cudaSuccess && !m->spec0.empty()) e = launch_mega<0>(c, m->spec0, ncol, smem, st, &m->launches);
+        if (!m->spec2.empty()) e = launch_mega<2>(cc[2], m->spec2, ncol, smem[2], st, &m->launches);
+        if (e == cudaSuccess && !m->spec1.empty()) e = launch_mega<1>(cc[1], m->spec1, ncol, smem[1], st, &m->launches);
+        if (e == cudaSuccess && !m->spec0.empty()) e = launch_mega<0>(cc[0], m->spec0, ncol, smem[0], st, &m->launches);
         if (e != cudaSuccess) return fail((int)e, "fs_gamma_kernel_m: %s", cudaGetErrorString(e));
     }
     if (rec) {
@@ -944,8 +966,8 @@ int mali_uv(const mali_model *m, const mali_buffers *b, int32_t col, int32_t t, 
         if (m->slots[td.slot0 + q].t == t) sd = &m->slots[td.slot0 + q];
     if (!sd) return fail(MALI_EINVAL, "mali_uv: internal error, transition %d missing from tile %d", t, ti);
     FsParams p = make_fs_params(m, b, col, 1, 1);
-    uv_hook_kernel<<<(m->N + 63) / 64, 64, 0, (cudaStream_t)stream>>>(p, col, *sd, td.recOff, la, la - td.la0, mu,
-                                                                      toFrom ? 1 : 0, Uji, Vij, Vji);
+    uv_hook_kernel<<<(m->N + 63) / 64, 64, 0, (cudaStream_t)stream>>>(p, col, *sd, td.recOff, td.vDir, la, la - td.la0,
+                                                                      mu, toFrom ? 1 : 0, Uji, Vij, Vji);
     CU(cudaGetLastError());
     return MALI_OK;
 }

@@ -26,6 +26,7 @@ struct FsCommon {  // launch-invariant parameters of the specialised kernels (co
     int32_t N, Nrays, Nspect, Lw;
     int32_t col0, ncol, warpsPerBlock, useBulk;
     int32_t smemBytesPerWarp, popDoubles, zOffDoubles, lvlOffDoubles, mbarOffBytes, expTabOffBytes;
+    int32_t ringOffDoubles, pad1;
     int64_t colStride, popStride, JStride, IStride, scratchStride;
     int64_t off_z, off_bbc, off_tab, rowStride;
     int64_t off_jpart, off_part;
@@ -215,18 +216,53 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
     const double fourPi = 4.0 * kPi;
     const double r3 = rcp_full(3.0);
 
-    // ---- compile-time record geometry (see mali_types.cuh): Vij rows, then bg chi/eta/sca, then one field per slot
+    // ---- compile-time record geometry (mali_types.cuh): [Vij rows dir 0][Vij rows dir 1][bg chi|eta|sca][slot fields]
     constexpr int LW = S.lw;
     constexpr int NLINE = spec_line_index(S, S.nslot);
-    constexpr int SB = 2 * NLINE * kVRow;  // record offset of bg chi
+    constexpr int VBLK = NLINE * kVRow;                                    // one direction's Vij rows
+    constexpr int SMALL = ((3 + NS) * LW + 15) / 16 * 16;                  // bg + slot fields, padded as packed
+    constexpr int STAGE = VBLK + SMALL;                                    // doubles of one ring stage
+    constexpr int NST = 3;                                                 // ring depth: two steps in flight
 #define line_index(tt) spec_line_index(S, (tt))
     // idle lanes (lane >= Lw * Nrays) read the zero padding of the Vij rows and the last wavelength's fields; lanes
     // past the end of the spectrum read the zero / clamped entries packed for them.  Their weights are zero.
     const int lsC = ls < p.Lw ? ls : p.Lw - 1;
-    const int laneV = lane;
     const double hwG = valid ? hw : 0.0;
-    const long long rowBytesStep = p.rowStride;  // doubles per depth row
-    const double *tab0 = cc + p.off_tab + T.recOff;
+    const double *tab0 = cc + p.off_tab + T.recOff;   // this tile's record in depth row 0
+
+    // ---- TMA ring: the record of depth step g+2 streams into shared memory while step g is computed.
+    // One elected lane issues two bulk copies per step (this direction's Vij rows; the per-wavelength fields) onto
+    // the stage's mbarrier; everybody waits on it before reading.  No per-lane global loads, no prefetch registers.
+    double *ring = sN + p.ringOffDoubles;
+    const uint32_t ringAddr = smem_u32(ring);
+    const uint32_t barAddr = smem_u32(wbase + p.mbarOffBytes) + 8;  // three ring barriers after the staging barrier
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < NST; ++q) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(barAddr + 8 * q) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    auto issue = [&](int g) {  // lane 0 only: fetch the record of global step g (direction g / N) into stage g % NST
+        const int d = g >= N ? 1 : 0;
+        const int s = g - d * N;
+        const int k = d ? N - 1 - s : s;
+        const int st = g % NST;
+        const double *rec = tab0 + (size_t)k * p.rowStride;
+        const uint32_t dst = ringAddr + (uint32_t)(st * STAGE) * 8u, bar = barAddr + 8u * st;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(STAGE * 8)) : "memory");
+        if (VBLK > 0)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                         "l"(rec + d * VBLK), "r"((uint32_t)(VBLK * 8)), "r"(bar)
+                         : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         dst + (uint32_t)VBLK * 8u),
+                     "l"(rec + 2 * VBLK), "r"((uint32_t)(SMALL * 8)), "r"(bar)
+                     : "memory");
+    };
+    if (lane == 0) {
+        issue(0);
+        issue(1);
+    }
 
     // ---- depth-invariant per-lane constants of the continuum slots (alpha, 2hc/lambda^3, wlamu)
     double ca[NSA], cb[NSA], cw[NSA];
@@ -245,13 +281,10 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
         }
     }
 
+    int g = 0;  // global step over both directions
     for (int d = 0; d < 2; ++d) {
         const int dk = d ? -1 : 1;
         const int kS = d ? N - 1 : 0;
-        // one running pointer per access pattern; every table offset below is a compile-time immediate
-        const double *pV = tab0 + (size_t)kS * rowBytesStep + d * kVRow + laneV;  // Vij rows: lane order
-        const double *pS = tab0 + (size_t)kS * rowBytesStep + SB + lsC;           // per-wavelength fields
-        const long long step = dk * rowBytesStep;
         int kl = kS * Nspect + laC;
         const int dkl = dk * Nspect;
 
@@ -259,51 +292,33 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
         double chiProbe = 0.0;
         if (d) {
             const int k = kS + dk;
+            const double *rec = tab0 + (size_t)k * p.rowStride;
             double chiTot = 0.0;
 #pragma unroll
             for (int tt = 0; tt < NS; ++tt) {
                 const double ni = sN[S.rowI[tt] * N + k], nj = sN[S.rowJ[tt] * N + k];
                 if (S.kind[tt]) {
-                    const double ld = __ldg(pV + step + 2 * line_index(tt) * kVRow);
+                    const double ld = __ldg(rec + VBLK + line_index(tt) * kVRow + lane);
                     chiTot += ni * ld - nj * (T.s[tt].cA * ld);
                 } else {
-                    const double ld = __ldg(pS + step + (3 + tt) * LW);
+                    const double ld = __ldg(rec + 2 * VBLK + (3 + tt) * LW + lsC);
                     chiTot += ni * ca[tt] - nj * (ld * ca[tt]);
                 }
             }
-            chiProbe = chiTot + __ldg(pS + step);
+            chiProbe = chiTot + __ldg(rec + 2 * VBLK + lsC);
         }
-
-        // software prefetch: the streams of step s+1 are in flight while step s is computed
-        double ldN[NSA], wlN[NSA], bgcN, bgeN, bgsN, JdN;
-#pragma unroll
-        for (int tt = 0; tt < NS; ++tt) {
-            wlN[tt] = 0.0;
-            if (S.kind[tt]) {
-                ldN[tt] = ld_stream(pV + 2 * line_index(tt) * kVRow);
-                wlN[tt] = __ldg(pS + (3 + tt) * LW);
-            } else {
-                ldN[tt] = __ldg(pS + (3 + tt) * LW);
-            }
-        }
-        bgcN = __ldg(pS);
-        bgeN = __ldg(pS + LW);
-        bgsN = __ldg(pS + 2 * LW);
-        JdN = Jcol[kl];
+        double JdN = Jcol[kl];
 
         Sweep sw;
         sw.r3 = r3;
         sw.stab = stab;
-#pragma unroll 2
-        for (int s = 0; s < N; ++s) {
+#pragma unroll 1
+        for (int s = 0; s < N; ++s, ++g) {
             const int k = kS + s * dk;
-            double ld[NSA], wl[NSA];
-#pragma unroll
-            for (int tt = 0; tt < NS; ++tt) {
-                ld[tt] = ldN[tt];
-                wl[tt] = wlN[tt];
-            }
-            const double bgc = bgcN, bge = bgeN, bgs = bgsN, Jdag = JdN;
+            const int st = g % NST;
+            const double *sV = ring + st * STAGE + lane;       // this direction's Vij rows, lane order
+            const double *sS = ring + st * STAGE + VBLK + lsC;  // per-wavelength fields
+            const double Jdag = JdN;
             const int klc = kl;
             // partial sums written by the down sweep (read early: consumed at the end of the step)
             double jOld = 0.0, gOld = 0.0;
@@ -316,21 +331,20 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
             }
             if (s + 1 < N) {
                 kl += dkl;
-                pV += step;
-                pS += step;
-#pragma unroll
-                for (int tt = 0; tt < NS; ++tt) {
-                    if (S.kind[tt]) {
-                        ldN[tt] = ld_stream(pV + 2 * line_index(tt) * kVRow);
-                        wlN[tt] = __ldg(pS + (3 + tt) * LW);
-                    } else {
-                        ldN[tt] = __ldg(pS + (3 + tt) * LW);
-                    }
-                }
-                bgcN = __ldg(pS);
-                bgeN = __ldg(pS + LW);
-                bgsN = __ldg(pS + 2 * LW);
                 JdN = Jcol[kl];
+            }
+            // the stage of step g+2 is the one step g-1 used: every lane has passed the __syncwarp of that step
+            if (lane == 0 && g + 2 < 2 * N) issue(g + 2);
+            {   // wait for this step's record
+                const uint32_t bar = barAddr + 8u * st, parity = (uint32_t)((g / NST) & 1);
+                uint32_t ok = 0;
+                do {
+                    asm volatile(
+                        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                        : "=r"(ok)
+                        : "r"(bar), "r"(parity)
+                        : "memory");
+                } while (!ok);
             }
 
             // ---- (1) opacity / emissivity, rh_method.py:601-632.  chiL / UL / etaA: compile-time indexed registers
@@ -347,12 +361,12 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
 #pragma unroll
             for (int tt = 0; tt < NS; ++tt) {
                 if (S.kind[tt]) {  // rh_method.py:278-281; the table holds hc/4pi*Bij*phi
-                    Vij[tt] = ld[tt];
+                    Vij[tt] = sV[line_index(tt) * kVRow];
                     Vji[tt] = T.s[tt].cA * Vij[tt];
                     Uji[tt] = T.s[tt].cB * Vji[tt];
                 } else {           // rh_method.py:284-286
                     Vij[tt] = ca[tt];
-                    Vji[tt] = ld[tt] * Vij[tt];
+                    Vji[tt] = sS[(3 + tt) * LW] * Vij[tt];
                     Uji[tt] = cb[tt] * Vji[tt];
                 }
                 const double ni = sN[S.rowI[tt] * N + k], nj = sN[S.rowJ[tt] * N + k];
@@ -372,9 +386,9 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
                 chiTot = (tt == 0) ? chi_t : chiTot + chi_t;
                 etaTot = (tt == 0) ? eta_t : etaTot + eta_t;
             }
-            chiTot += bgc;
+            chiTot += sS[0];
             const double rchi = rcp_full(chiTot);
-            const double Ssrc = div_by(etaTot + bge + bgs * Jdag, chiTot, rchi);
+            const double Ssrc = div_by(etaTot + sS[LW] + sS[2 * LW] * Jdag, chiTot, rchi);
 
             // ---- (2) short characteristic
             const double zk = sZ[k];
@@ -411,7 +425,7 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
                 for (int a = 0; a < NA; ++a) Ieff[a] = Ik - Psi * etaA[a];
 #pragma unroll
                 for (int tt = 0; tt < NS; ++tt) {
-                    const double wlamu = S.kind[tt] ? (wl[tt] * hwG) * fourPi : cw[tt];  // rh_method.py:665
+                    const double wlamu = S.kind[tt] ? (sS[(3 + tt) * LW] * hwG) * fourPi : cw[tt];  // rh_method.py:665
                     const double Ie = Ieff[S.atom[tt]];
                     // Ulvl of a level no transition of the tile has as its upper level is exactly 0: the reference's
                     // (chi*Psi)*0.0 term is +-0 and drops out of the subtraction
@@ -429,6 +443,8 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
                 }
                 const double tot = reduce_transpose<M>(v, lane, red);
                 if (writer) __stcg(gdst, d == 0 ? tot : gOld + tot);
+            } else {
+                __syncwarp();  // ring reuse: every lane is done with this stage
             }
         }
         if (d == 1 && valid) p.I[(size_t)col * p.IStride + (size_t)la * Nrays + mu] = sw.Iupw;

@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(128) fs_gamma_kernel(const FsParams p)
                 const double *rec = tab + (size_t)k * p.rowStride;
                 double Vij, Vji, Uji;
                 if (sd.isLine) {
-                    const double phi = act ? __ldg(rec + sd.vOff + d * kVRow + laneV) : 0.0;
+                    const double phi = act ? __ldg(rec + sd.vOff + d * td.vDir + laneV) : 0.0;
                     Vij = phi;  // the table holds hc/4pi*Bij*phi (rh_method.py:279), folded in at upload
                     Vji = sd.c2 * Vij;
                     Uji = sd.c1 * Vji;
@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(128) fs_gamma_kernel(const FsParams p)
                         const double *rec = tab + (size_t)k * p.rowStride;
                         double Vij, Vji, Uji, wla;
                         if (sd.isLine) {
-                            const double phi = act ? __ldg(rec + sd.vOff + d * kVRow + laneV) : 0.0;
+                            const double phi = act ? __ldg(rec + sd.vOff + d * td.vDir + laneV) : 0.0;
                             Vij = phi;
                             Vji = sd.c2 * Vij;
                             Uji = sd.c1 * Vji;
@@ -614,7 +614,7 @@ __global__ void sweep_hook_kernel(int N, int nray, const double *z, const double
 }
 
 // Test hook: ComputationalTransition.uv from the packed device tables of one column.
-__global__ void uv_hook_kernel(const FsParams p, int col, SlotDesc sd, int recOff, int la, int ls, int mu, int d,
+__global__ void uv_hook_kernel(const FsParams p, int col, SlotDesc sd, int recOff, int vDir, int la, int ls, int mu, int d,
                                double *Uji, double *Vij, double *Vji)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -623,7 +623,7 @@ __global__ void uv_hook_kernel(const FsParams p, int col, SlotDesc sd, int recOf
     const int lt = la - sd.Nblue;
     double vij, vji, uji;
     if (sd.isLine) {
-        vij = rec[sd.vOff + d * kVRow + ls * p.Nrays + mu];  // hc/4pi*Bij*phi
+        vij = rec[sd.vOff + d * vDir + ls * p.Nrays + mu];  // hc/4pi*Bij*phi
         vji = sd.c2 * vij;
         uji = sd.c1 * vji;
     } else {
@@ -670,7 +670,8 @@ __global__ void pack_tiles_kernel(const PackChunk *chunks, const PackTile *tiles
         double v = 0.0;
         if (e < pt.recSize && k < N) {
             if (e < pt.sb) {  // Vij rows
-                const int j = e / (2 * kVRow), d = (e / kVRow) & 1, idx = e % kVRow;
+                const int nLine = pt.sb / (2 * kVRow);
+                const int d = e / (nLine * kVRow), j = (e / kVRow) - d * nLine, idx = e % kVRow;
                 const int ls = idx / Nrays, mu = idx - ls * Nrays;
                 int sq = -1;
                 for (int u = 0; u < pt.nslot; ++u)

@@ -7,7 +7,8 @@
 //
 // The iteration-invariant per-column tables are stored TILE-MAJOR: for every depth k one row of `rowStride` doubles
 // holding, tile after tile, one contiguous *record* with everything the tile's warp reads at that depth:
-//     [ Vij rows: per line slot, direction 0 then 1, each kVRow = 32 doubles = (wavelength, angle) in lane order ]
+//     [ Vij rows of direction 0: one per line slot, each kVRow = 32 doubles = (wavelength, angle) in lane order ]
+//     [ Vij rows of direction 1 ]
 //     [ bg chi[Lw] | bg eta[Lw] | bg sca[Lw] ]
 //     [ per slot: wla[Lw] (lines, rh_method.py:451) or g_ij[Lw] (continua, :453-454) ]      (padded to 16 doubles)
 // Entries for wavelengths on which a transition is not active are zero, so the kernels need no activity masks for
@@ -36,7 +37,7 @@ struct SlotDesc {
     int32_t toff;        // offset of this transition in the per-wavelength tables (alpha, twohc, wlacont)
     int32_t flags;       // bit 0 / 1: this slot is the first of its tile to touch level-slot lsI / lsJ
     int32_t fOff;        // record offset of the slot's per-wavelength field: wla[Lw] (lines) or g_ij[Lw] (continua)
-    int32_t vOff;        // lines: record offset of the direction-0 Vij row (direction 1 follows at +kVRow); else -1
+    int32_t vOff;        // lines: record offset of the direction-0 Vij row (direction 1: + TileDesc::vDir); else -1
     int32_t pad;
     double c0, c1, c2;   // lines: hc/4pi*Bij (folded into the Vij table at upload), Aji/Bji, Bji/Bij  (rh_method.py:279-281,450)
 };
@@ -49,7 +50,7 @@ struct TileDesc {
     int32_t partRow0;  // first row of the tile's Gamma partials (2 rows per slot: [i,j] then [j,i])
     int32_t recOff;    // offset of the tile's record inside a depth row
     int32_t bgOff;     // record offset of bg chi[Lw] (eta, sca follow at +Lw, +2Lw)
-    int32_t pad;
+    int32_t vDir;      // distance between the direction-0 and direction-1 Vij rows (number of line slots * kVRow)
 };
 
 constexpr int kVRow = 32;  // doubles per Vij row of a record (Lw * Nrays <= 32 lanes, zero padded)
