@@ -173,7 +173,7 @@ struct mali_model {
     int specTiles = 0;
     mali_layout lay{};
     int64_t off_z = 0, off_bbc = 0, off_C = 0, off_nTotal = 0, off_tab = 0, rowStride = 0;
-    int64_t off_jpart = 0, off_part = 0;
+    int64_t off_jpart = 0, off_part = 0, upOff = 0;
     int smemPopDoubles = 0, smemZOff = 0, smemLvlOff = 0, smemMbarOff = 0, smemExpOff = 0, smemBytesPerWarp = 0, useBulk = 0;
     int ringStage[3] = {16, 16, 16};
     std::vector<CopyJob> cjobs;
@@ -423,7 +423,8 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
     so = align_up(so + L.J, 16);
     m->off_part = so;
     so = align_up(so + (int64_t)std::max(partRow, 1) * N, 16);
-    L.scratch = so;
+    m->upOff = so;      // second copy of [Jpart | part] for the up sweep
+    L.scratch = 2 * so;
     if (m->Dmax > 255 || m->sumNlevel > 65535) {
         delete m;
         return fail(MALI_ELIMIT, "tile touches %d levels / model has %d levels: beyond the kernel's packed indices", m->Dmax, m->sumNlevel);
@@ -657,6 +658,7 @@ static FsParams make_fs_params(const mali_model *m, const mali_buffers *b, int c
     p.rowStride = m->rowStride;
     p.off_jpart = m->off_jpart;
     p.off_part = m->off_part;
+    p.upOff = m->upOff;
     p.tiles = m->d_tiles;
     p.slots = m->d_slots;
     p.classTiles = m->d_genericTiles;
@@ -705,6 +707,7 @@ static FsCommon make_fs_common(const mali_model *m, const mali_buffers *b, int c
     c.rowStride = m->rowStride;
     c.off_jpart = m->off_jpart;
     c.off_part = m->off_part;
+    c.upOff = m->upOff;
     c.alpha = m->d_alpha;
     c.twohc = m->d_twohc;
     c.wlacont = m->d_wlacont;
@@ -738,6 +741,7 @@ static FinishParams make_finish_params(const mali_model *m, const mali_buffers *
     p.off_C = m->off_C;
     p.off_nTotal = m->off_nTotal;
     p.off_part = m->off_part;
+    p.upOff = m->upOff;
     p.Nlevel = m->d_Nlevel;
     p.lvlOff = m->d_lvlOff;
     p.g2Off = m->d_g2Off;
@@ -784,6 +788,11 @@ static int launch_fs(const mali_model *m, const mali_buffers *b, int col0, int n
         for (int cls = 0; cls < 3; ++cls) {
             FsCommon &c = cc[cls];
             c = make_fs_common(m, b, col0, ncol);
+            // populations: only the level rows a tile of this class can touch, transposed to [depth][level-slot]
+            c.popDoubles = std::min(2 * spec_class_slots(cls), std::max(m->sumNlevel, 1)) * m->N;
+            c.zOffDoubles = (c.popDoubles + 1) & ~1;
+            c.lvlOffDoubles = c.zOffDoubles + ((m->N + 1) & ~1);
+            c.useBulk = (m->N % 2 == 0) ? 1 : 0;   // cp.async.bulk: 16-byte sizes / addresses
             const int red = spec_pow2(2 * spec_class_slots(cls)) * 36;
             c.mbarOffBytes = (c.lvlOffDoubles + red) * 8;
             c.expTabOffBytes = (int)align_up(c.mbarOffBytes + 32, 16);
@@ -807,7 +816,7 @@ static int launch_fs(const mali_model *m, const mali_buffers *b, int col0, int n
     gamma_finish_kernel<<<grid, 64, 0, st>>>(f);
     {
         const int nb = (int)std::min<int64_t>(16, (m->lay.J + 255) / 256);
-        j_finish_kernel<<<dim3(nb, ncol), 256, 0, st>>>(b->J, m->lay.J, b->scratch, m->lay.scratch, m->off_jpart,
+        j_finish_kernel<<<dim3(nb, ncol), 256, 0, st>>>(b->J, m->lay.J, b->scratch, m->lay.scratch, m->off_jpart, m->upOff,
                                                       reinterpret_cast<unsigned long long *>(b->dJ), b->done, col0);
     }
     m->launches += 2;

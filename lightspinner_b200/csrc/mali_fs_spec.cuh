@@ -29,7 +29,7 @@ struct FsCommon {  // launch-invariant parameters of the specialised kernels (co
     int32_t ringOffDoubles, pad1;
     int64_t colStride, popStride, JStride, IStride, scratchStride;
     int64_t off_z, off_bbc, off_tab, rowStride;
-    int64_t off_jpart, off_part;
+    int64_t off_jpart, off_part, upOff;
     const double *alpha, *twohc, *wlacont, *zmu, *hw;
     const double *colconst, *pops;
     double *J, *I, *scratch;
@@ -102,18 +102,21 @@ __device__ __forceinline__ double ld_stream(const double *p)
     return v;
 }
 
-// Warp reduce-scatter through shared memory: every lane stores its M values, then lane L sums 32/M... see below.
-// red: per-warp scratch of M rows x 36 doubles (lane l of a row sits at l + l/8: conflict-free stores and loads).
-// After the call the lane holds the total over the 32 lanes of value index L / (32/M).  Fixed order -> deterministic.
+// Warp reduce-scatter through shared memory, split in two so that the second half can run one depth step later
+// (its latency then overlaps the next step's arithmetic): reduce_store puts the lane's M values into the per-warp
+// scratch (M rows x 36 doubles; lane l of a row sits at l + l/8: conflict-free stores and loads); reduce_load sums
+// them: afterwards the lane holds the total over the 32 lanes of value index L / (32/M).  Fixed order -> deterministic.
 template <int M>
-__device__ __forceinline__ double reduce_transpose(const double (&v)[M], int lane, double *red)
+__device__ __forceinline__ void reduce_store(const double (&v)[M], int lane, double *red)
+{
+#pragma unroll
+    for (int q = 0; q < M; ++q) red[q * 36 + lane + (lane >> 3)] = v[q];
+}
+template <int M>
+__device__ __forceinline__ double reduce_load(int lane, const double *red)
 {
     constexpr int G = 32 / M;      // lanes that share one value after the reduction
     constexpr int SEG = 32 / G;    // source lanes each of them sums
-    __syncwarp();
-#pragma unroll
-    for (int q = 0; q < M; ++q) red[q * 36 + lane + (lane >> 3)] = v[q];
-    __syncwarp();
     const int e = lane / G, part = lane % G;
     const double *row = red + e * 36;
     double acc = 0.0, acc1 = 0.0;   // two interleaved partial sums halve the dependent-add chain
@@ -132,6 +135,128 @@ __device__ __forceinline__ double reduce_transpose(const double (&v)[M], int lan
     return acc;
 }
 
+// row of n[sumNlevel][N] that holds level-slot lv of the tile
+__host__ __device__ constexpr int spec_level_row(const TileStruct &S, int lv)
+{
+    for (int u = 0; u < S.nslot; ++u) {
+        if (S.lvI[u] == lv) return S.rowI[u];
+        if (S.lvJ[u] == lv) return S.rowJ[u];
+    }
+    return 0;
+}
+
+#ifndef MALI_NT
+#define MALI_NT 0
+#endif
+// populations of the levels a tile touches, transposed into shared memory as [depth][level-slot]
+template <class SPEC, int LV>
+__device__ __forceinline__ void stage_levels(double *sN, const double *gN, int N, int lane)
+{
+    constexpr TileStruct S = SPEC::S;
+    if constexpr (LV < S.nlev) {
+        constexpr int row = spec_level_row(S, LV);   // constant-evaluated: S never materialises in local memory
+        const double *src = gN + (size_t)row * N;
+        for (int k = lane; k < N; k += 32) sN[MALI_NT ? k * S.nlev + LV : LV * N + k] = src[k];
+        stage_levels<SPEC, LV + 1>(sN, gN, N, lane);
+    }
+}
+
+#if MALI_NT
+#define NIDX(k, lv) ((k) * NLV + (lv))
+#define NSTEP NLV
+#else
+#define NIDX(k, lv) ((lv) * N + (k))
+#define NSTEP 1
+#endif
+// one TMA bulk copy per level row the tile touches -> sN[level-slot][depth]
+template <class SPEC, int LV>
+__device__ __forceinline__ void stage_levels_bulk(double *sN, const double *gN, int N, uint32_t mbar)
+{
+    constexpr TileStruct S = SPEC::S;
+    if constexpr (LV < S.nlev) {
+        constexpr int row = spec_level_row(S, LV);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_u32(sN + (size_t)LV * N)),
+                     "l"(gN + (size_t)row * N), "r"((uint32_t)N * 8u), "r"(mbar)
+                     : "memory");
+        stage_levels_bulk<SPEC, LV + 1>(sN, gN, N, mbar);
+    }
+}
+
+// one lane of the (converged) warp
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{ .reg .pred p; elect.sync _|p, 0xffffffff; selp.u32 %0, 1, 0, p; }" : "=r"(pred));
+    return pred != 0;
+}
+
+// TMA ring producer step: one elected lane fetches the record of global step fetchG (both sweep directions:
+// 0 .. 2N-1) into the next ring stage -- this direction's Vij rows and the per-wavelength fields -- then the
+// (warp-uniform) bookkeeping advances.  A record: [Vij rows dir 0][Vij rows dir 1][fields]; VBLK / SMALL in doubles.
+template <int VBLK, int SMALL, int NST>
+__device__ __forceinline__ void ring_fetch(int &fetchG, uint32_t &fetchOff, uint32_t &fetchBar, const double *&fetchRec,
+                                           int N, int64_t rowStride, uint32_t ringAddr, uint32_t barAddr)
+{
+    constexpr int STAGE = VBLK + SMALL;
+    if (fetchG < 2 * N) {
+        const double *srcV = fetchRec + (fetchG >= N ? VBLK : 0);
+        const double *srcS = fetchRec + 2 * VBLK;
+        if (elect_one()) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fetchBar), "r"((uint32_t)(STAGE * 8))
+                         : "memory");
+            if (VBLK > 0)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 ringAddr + fetchOff),
+                             "l"(srcV), "r"((uint32_t)(VBLK * 8)), "r"(fetchBar)
+                             : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             ringAddr + fetchOff + (uint32_t)VBLK * 8u),
+                         "l"(srcS), "r"((uint32_t)(SMALL * 8)), "r"(fetchBar)
+                         : "memory");
+        }
+        ++fetchG;
+        const bool wrap = fetchOff == (uint32_t)((NST - 1) * STAGE * 8);
+        fetchOff = wrap ? 0u : fetchOff + (uint32_t)(STAGE * 8);
+        fetchBar = wrap ? barAddr : fetchBar + 8u;
+        if (fetchG < N)
+            fetchRec += rowStride;
+        else if (fetchG > N)
+            fetchRec -= rowStride;
+    }
+}
+
+// second half of a depth step's reductions (run during the next step): Gamma partial of the lane's matrix entry
+// and the mu-sum of J, rh_method.py:640.  The down and the up sweep write separate partials (no read-modify-write:
+// the depth loop holds no global loads); gamma_finish_kernel / j_finish_kernel add them.
+template <int M, int NS>
+__device__ __forceinline__ void finish_step(int lane, int Nrays, const double *red, bool writer, bool leader,
+                                            double *gdst, double *jdst, double x)
+{
+    if constexpr (NS > 0) {
+        const double tot = reduce_load<M>(lane, red);
+        if (writer) __stcg(gdst, tot);
+    }
+    double sum = x;
+    if (Nrays == 5) {
+#pragma unroll
+        for (int m = 1; m < 5; ++m) sum += __shfl_down_sync(0xffffffffu, x, m);
+    } else if (Nrays == 3) {
+#pragma unroll
+        for (int m = 1; m < 3; ++m) sum += __shfl_down_sync(0xffffffffu, x, m);
+    } else {
+        for (int m = 1; m < Nrays; ++m) sum += __shfl_down_sync(0xffffffffu, x, m);
+    }
+    if (leader) __stcg(jdst, sum);
+}
+
+#ifndef MALI_DEFER
+#define MALI_DEFER 1
+#endif
+#ifndef MALI_UNROLL
+#define MALI_UNROLL 2
+#endif
+
 // SPEC is a tag type with a `static constexpr TileStruct S` member (the structure travels inside a type).
 template <class SPEC, int NSP>
 __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, unsigned char *smem_raw)
@@ -142,8 +267,9 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
     constexpr int NLV = S.nlev > 0 ? S.nlev : 1;
     constexpr int NA = S.natom > 0 ? S.natom : 1;
     constexpr int M = spec_pow2(2 * NS);
+    constexpr int kUnroll = MALI_UNROLL;
     // one warp per block: the column (hence every base pointer) is block-uniform -> uniform-register addressing
-    const int warp = 0, lane = threadIdx.x;
+    const int lane = threadIdx.x;
     const int col = p.col0 + blockIdx.x;
     if (col >= p.col0 + p.ncol) return;
     if (p.done != nullptr && p.done[col] != 0) return;
@@ -162,34 +288,47 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
     double *Jpart = scr + p.off_jpart;
     double *part = scr + p.off_part + (size_t)T.partRow0 * N;
 
-    // ---- stage this column's depth profiles (populations, heights) into shared memory: TMA bulk copies
-    unsigned char *wbase = smem_raw + (size_t)warp * p.smemBytesPerWarp;
+    // ---- per-warp shared memory: populations | heights | Gamma reduce scratch | barriers | exp table | TMA ring
+    unsigned char *wbase = smem_raw;
     double *sN = reinterpret_cast<double *>(wbase);
     double *sZ = sN + p.zOffDoubles;
-    double *red = sN + p.lvlOffDoubles;  // Gamma reduce scratch (shares the level-array slot of the class kernels)
+    double *red = sN + p.lvlOffDoubles;
     {
+        // heights: one TMA bulk copy; populations of the levels this tile touches: transposed to [depth][level-slot]
+        // (one running pointer and compile-time offsets in the depth loop), overlapped with the bulk copy
         const double *gN = p.pops + (size_t)col * p.popStride;
         const double *gZ = cc + p.off_z;
+        const uint32_t mbar = smem_u32(wbase + p.mbarOffBytes);
         if (p.useBulk) {
-            const uint32_t mbar = smem_u32(wbase + p.mbarOffBytes);
             if (lane == 0) {
-                const uint32_t bytesN = (uint32_t)p.popDoubles * 8u, bytesZ = (uint32_t)N * 8u;
+                const uint32_t bytesZ = (uint32_t)N * 8u;
                 asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
                 asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytesN + bytesZ)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar),
+                             "r"(bytesZ * (uint32_t)(1 + (MALI_NT ? 0 : S.nlev)))
                              : "memory");
-                asm volatile(
-                    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                        smem_u32(sN)),
-                    "l"(gN), "r"(bytesN), "r"(mbar)
-                    : "memory");
                 asm volatile(
                     "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                         smem_u32(sZ)),
                     "l"(gZ), "r"(bytesZ), "r"(mbar)
                     : "memory");
             }
-            __syncwarp();
+        } else {
+            for (int q = lane; q < N; q += 32) sZ[q] = gZ[q];
+        }
+#if MALI_NT
+        if constexpr (NS > 0) stage_levels<SPEC, 0>(sN, gN, N, lane);
+#else
+        if constexpr (NS > 0) {
+            if (p.useBulk) {
+                if (lane == 0) stage_levels_bulk<SPEC, 0>(sN, gN, N, mbar);
+            } else {
+                stage_levels<SPEC, 0>(sN, gN, N, lane);
+            }
+        }
+#endif
+        __syncwarp();
+        if (p.useBulk) {
             uint32_t ok = 0;
             do {
                 asm volatile(
@@ -198,10 +337,6 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
                     : "r"(mbar)
                     : "memory");
             } while (!ok);
-        } else {
-            for (int q = lane; q < p.popDoubles; q += 32) sN[q] = gN[q];
-            for (int q = lane; q < N; q += 32) sZ[q] = gZ[q];
-            __syncwarp();
         }
     }
 
@@ -231,8 +366,9 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
     const double *tab0 = cc + p.off_tab + T.recOff;   // this tile's record in depth row 0
 
     // ---- TMA ring: the record of depth step g+2 streams into shared memory while step g is computed.
-    // One elected lane issues two bulk copies per step (this direction's Vij rows; the per-wavelength fields) onto
-    // the stage's mbarrier; everybody waits on it before reading.  No per-lane global loads, no prefetch registers.
+    // All ring bookkeeping is warp-uniform (uniform registers); one elected lane issues two bulk copies per step
+    // (this direction's Vij rows; the per-wavelength fields) onto the stage's mbarrier and every lane waits on it
+    // before reading.  No per-lane global loads, no prefetch registers.
     double *ring = sN + p.ringOffDoubles;
     const uint32_t ringAddr = smem_u32(ring);
     const uint32_t barAddr = smem_u32(wbase + p.mbarOffBytes) + 8;  // three ring barriers after the staging barrier
@@ -242,27 +378,15 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    auto issue = [&](int g) {  // lane 0 only: fetch the record of global step g (direction g / N) into stage g % NST
-        const int d = g >= N ? 1 : 0;
-        const int s = g - d * N;
-        const int k = d ? N - 1 - s : s;
-        const int st = g % NST;
-        const double *rec = tab0 + (size_t)k * p.rowStride;
-        const uint32_t dst = ringAddr + (uint32_t)(st * STAGE) * 8u, bar = barAddr + 8u * st;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(STAGE * 8)) : "memory");
-        if (VBLK > 0)
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                         "l"(rec + d * VBLK), "r"((uint32_t)(VBLK * 8)), "r"(bar)
-                         : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                         dst + (uint32_t)VBLK * 8u),
-                     "l"(rec + 2 * VBLK), "r"((uint32_t)(SMALL * 8)), "r"(bar)
-                     : "memory");
-    };
-    if (lane == 0) {
-        issue(0);
-        issue(1);
-    }
+    const int64_t rowStride = p.rowStride;
+    int fetchG = 0;                     // next global step (both directions: 0 .. 2N-1) to fetch
+    uint32_t fetchOff = 0;              // byte offset of its stage in the ring
+    uint32_t fetchBar = barAddr;        // its barrier
+    const double *fetchRec = tab0;      // its record
+#define fetch_next() ring_fetch<VBLK, SMALL, NST>(fetchG, fetchOff, fetchBar, fetchRec, N, rowStride, ringAddr, barAddr)
+    fetch_next();
+    fetch_next();
+    uint32_t useOff = 0, useBar = barAddr, phases = 0, useBit = 1;   // stage being consumed; parity bit per stage
 
     // ---- depth-invariant per-lane constants of the continuum slots (alpha, 2hc/lambda^3, wlamu)
     double ca[NSA], cb[NSA], cw[NSA];
@@ -281,7 +405,11 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
         }
     }
 
-    int g = 0;  // global step over both directions
+    // Gamma value owned by this lane after the reduce, and where its partial sums live
+    const int eOwn = lane / (32 / M);
+    const bool writer = (lane % (32 / M)) == 0 && eOwn < 2 * NS;
+    double *gbase = part + (size_t)eOwn * N;
+
     for (int d = 0; d < 2; ++d) {
         const int dk = d ? -1 : 1;
         const int kS = d ? N - 1 : 0;
@@ -296,7 +424,7 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
             double chiTot = 0.0;
 #pragma unroll
             for (int tt = 0; tt < NS; ++tt) {
-                const double ni = sN[S.rowI[tt] * N + k], nj = sN[S.rowJ[tt] * N + k];
+                const double ni = sN[NIDX(k, S.lvI[tt])], nj = sN[NIDX(k, S.lvJ[tt])];
                 if (S.kind[tt]) {
                     const double ld = __ldg(rec + VBLK + line_index(tt) * kVRow + lane);
                     chiTot += ni * ld - nj * (T.s[tt].cA * ld);
@@ -312,40 +440,43 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
         Sweep sw;
         sw.r3 = r3;
         sw.stab = stab;
-#pragma unroll 1
-        for (int s = 0; s < N; ++s, ++g) {
+
+        // the second half of a step's J / Gamma reductions runs during the NEXT step (its shuffle / shared-memory
+        // latency then overlaps that step's arithmetic); state carried for it:
+        double xP = 0.0;
+        int kP = kS, klP = kl;
+        double *gdir = gbase + (d ? p.upOff : 0), *jdir = Jpart + (d ? p.upOff : 0);
+#define finish_prev() finish_step<M, NS>(lane, Nrays, red, writer, leader, gdir + kP, jdir + klP, xP)
+
+        const double *nk = sN + kS * NSTEP;   // populations at the current depth
+#pragma unroll kUnroll
+        for (int s = 0; s < N; ++s) {
             const int k = kS + s * dk;
-            const int st = g % NST;
-            const double *sV = ring + st * STAGE + lane;       // this direction's Vij rows, lane order
-            const double *sS = ring + st * STAGE + VBLK + lsC;  // per-wavelength fields
+            const double *sV = ring + (useOff >> 3) + lane;          // this direction's Vij rows, lane order
+            const double *sS = ring + (useOff >> 3) + VBLK + lsC;    // per-wavelength fields
             const double Jdag = JdN;
             const int klc = kl;
-            // partial sums written by the down sweep (read early: consumed at the end of the step)
-            double jOld = 0.0, gOld = 0.0;
-            const int e = lane / (32 / M);                       // Gamma value owned by this lane after the reduce
-            const bool writer = (lane % (32 / M)) == 0 && e < 2 * NS;
-            double *gdst = part + (size_t)e * N + k;
-            if (d) {
-                if (leader) jOld = __ldcg(Jpart + klc);
-                if (writer) gOld = __ldcg(gdst);
-            }
             if (s + 1 < N) {
                 kl += dkl;
                 JdN = Jcol[kl];
             }
-            // the stage of step g+2 is the one step g-1 used: every lane has passed the __syncwarp of that step
-            if (lane == 0 && g + 2 < 2 * N) issue(g + 2);
+            // the stage refilled here (step g+2) is the one step g-1 used: every lane has passed that step's __syncwarp
+            fetch_next();
             {   // wait for this step's record
-                const uint32_t bar = barAddr + 8u * st, parity = (uint32_t)((g / NST) & 1);
+                const uint32_t parity = (phases & useBit) ? 1u : 0u;
                 uint32_t ok = 0;
                 do {
                     asm volatile(
                         "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                         : "=r"(ok)
-                        : "r"(bar), "r"(parity)
+                        : "r"(useBar), "r"(parity)
                         : "memory");
                 } while (!ok);
+                phases ^= useBit;
             }
+#if MALI_DEFER
+            if (s > 0) finish_prev();
+#endif
 
             // ---- (1) opacity / emissivity, rh_method.py:601-632.  chiL / UL / etaA: compile-time indexed registers
             double chiTot = 0.0, etaTot = 0.0;
@@ -369,7 +500,7 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
                     Vji[tt] = sS[(3 + tt) * LW] * Vij[tt];
                     Uji[tt] = cb[tt] * Vji[tt];
                 }
-                const double ni = sN[S.rowI[tt] * N + k], nj = sN[S.rowJ[tt] * N + k];
+                const double ni = nk[NIDX(0, S.lvI[tt])], nj = nk[NIDX(0, S.lvJ[tt])];
                 const double chi_t = ni * Vij[tt] - nj * Vji[tt];
                 const double eta_t = nj * Uji[tt];
                 // first touch of a level / atom: the reference's 0.0 + x (== x up to the sign of zero)
@@ -398,22 +529,9 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
             else
                 sw.step(s == N - 1, zmu, chiTot, rchi, Ssrc, zk, Ik, Psi);
 
-            // ---- (3) J, rh_method.py:640
-            {
-                const double x = valid ? hw * Ik : 0.0;
-                double sum = x;
-                if (Nrays == 5) {
-#pragma unroll
-                    for (int m = 1; m < 5; ++m) sum += __shfl_down_sync(0xffffffffu, x, m);
-                } else if (Nrays == 3) {
-#pragma unroll
-                    for (int m = 1; m < 3; ++m) sum += __shfl_down_sync(0xffffffffu, x, m);
-                } else {
-                    for (int m = 1; m < Nrays; ++m) sum += __shfl_down_sync(0xffffffffu, x, m);
-                }
-                // down: store the partial; up: complete it.  j_finish_kernel then forms dJ and moves Jpart -> J
-                if (leader) __stcg(Jpart + klc, d == 0 ? sum : jOld + sum);
-            }
+            // ---- (3) J, rh_method.py:640: the sum over the mu lanes is taken in finish_prev of the next step
+            xP = valid ? hw * Ik : 0.0;
+            klP = klc;
 
             // ---- (4) Gamma integrands, rh_method.py:643-681
             if constexpr (NS > 0) {
@@ -441,16 +559,36 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
                     v[2 * tt] = g1 * wlamu;  // wavelengths without this transition: wlamu == 0 (zero table entries)
                     v[2 * tt + 1] = g2 * wlamu;
                 }
-                const double tot = reduce_transpose<M>(v, lane, red);
-                if (writer) __stcg(gdst, d == 0 ? tot : gOld + tot);
-            } else {
-                __syncwarp();  // ring reuse: every lane is done with this stage
+                __syncwarp();                 // every lane has read the previous step's values (finish_prev)
+                reduce_store<M>(v, lane, red);
+                kP = k;
             }
+            __syncwarp();                     // values visible; ring stage of this step free for the next fetch
+#if !MALI_DEFER
+            finish_prev();
+#endif
+
+            // next stage / depth
+            {
+                const bool wrap = useOff == (uint32_t)((NST - 1) * STAGE * 8);
+                useOff = wrap ? 0u : useOff + (uint32_t)(STAGE * 8);
+                useBar = wrap ? barAddr : useBar + 8u;
+                useBit = wrap ? 1u : useBit << 1;
+            }
+            nk += dk * NSTEP;
         }
+#if MALI_DEFER
+        finish_prev();
+#endif
+        __syncwarp();
         if (d == 1 && valid) p.I[(size_t)col * p.IStride + (size_t)la * Nrays + mu] = sw.Iupw;
         if (valid && sw.bad && p.status != nullptr) atomicOr(p.status + col, 2);
     }
 #undef line_index
+#undef fetch_next
+#undef NIDX
+#undef NSTEP
+#undef finish_prev
 }
 
 // ---- registry of ahead-of-time instances -----------------------------------------------------------------

@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(128) fs_gamma_kernel(const FsParams p)
                 double sum = x;
                 for (int m = 1; m < Nrays; ++m) sum += __shfl_down_sync(0xffffffffu, x, m);
                 // down: store the partial; up: complete it.  j_finish_kernel then forms dJ and moves Jpart -> J
-                if (leader) __stcg(Jpart + kl, d == 0 ? sum : __ldcg(Jpart + kl) + sum);
+                if (leader) __stcg(Jpart + kl + (d ? p.upOff : 0), sum);
             }
 
             // ---- (4) Gamma integrands: rh_method.py:643-681
@@ -457,10 +457,7 @@ __global__ void __launch_bounds__(128) fs_gamma_kernel(const FsParams p)
                 const int tt = c0 + (e >> 1);
                 if ((lane & 3) == 0 && tt < nslot) {
                     double *dst = part + (size_t)(td.partRow0 + 2 * tt + (e & 1)) * N + k;
-                    if (d == 0)
-                        __stcg(dst, tot);
-                    else
-                        __stcg(dst, __ldcg(dst) + tot);
+                    __stcg(dst + (d ? p.upOff : 0), tot);  // down and up partials are summed by gamma_finish_kernel
                 }
             }
         }
@@ -478,7 +475,7 @@ __global__ void __launch_bounds__(128) fs_gamma_kernel(const FsParams p)
 // dJ = max |1 - JDag/J| (rh_method.py:705-706) and J <- the new mean intensity the sweeps accumulated in Jpart.
 // Elementwise over one column's [Nspace][Nspect] plane; block max -> one atomicMax per block.
 __global__ void j_finish_kernel(double *J, int64_t JStride, const double *scratch, int64_t scratchStride,
-                                int64_t offJpart, unsigned long long *dJbits, const int32_t *done, int col0)
+                                int64_t offJpart, int64_t upOff, unsigned long long *dJbits, const int32_t *done, int col0)
 {
     const int col = col0 + blockIdx.y;
     if (done != nullptr && done[col] != 0) return;
@@ -486,7 +483,7 @@ __global__ void j_finish_kernel(double *J, int64_t JStride, const double *scratc
     const double *Jn = scratch + (size_t)col * scratchStride + offJpart;
     unsigned long long b = 0ull;
     for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < JStride; q += (int64_t)gridDim.x * blockDim.x) {
-        const double jn = Jn[q];
+        const double jn = Jn[q] + Jn[q + upOff];  // down-sweep + up-sweep sums, rh_method.py:640
         const unsigned long long v = absbits(1.0 - Jc[q] / jn);
         b = v > b ? v : b;
         Jc[q] = jn;
@@ -529,8 +526,8 @@ __global__ void gamma_finish_kernel(const FinishParams p)
         double sij = 0.0, sji = 0.0;
         for (int r = p.trPartOff[t]; r < p.trPartOff[t + 1]; ++r) {
             const int row = p.trPartRows[r];
-            sij += part[(size_t)row * N + k];
-            sji += part[(size_t)(row + 1) * N + k];
+            sij += part[(size_t)row * N + k] + part[(size_t)row * N + k + p.upOff];
+            sji += part[(size_t)(row + 1) * N + k] + part[(size_t)(row + 1) * N + k + p.upOff];
         }
         G[((size_t)i * NL + j) * N + k] += sij;
         G[((size_t)j * NL + i) * N + k] += sji;

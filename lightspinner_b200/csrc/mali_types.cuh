@@ -67,6 +67,7 @@ struct FsParams {
     int64_t off_z, off_bbc, off_tab, rowStride;
     // offsets inside one column's scratch block
     int64_t off_jpart, off_part;
+    int64_t upOff;  // the up sweep writes its partial sums this many doubles further on (no read-modify-write)
     // model tables (device)
     const TileDesc *tiles;
     const SlotDesc *slots;
@@ -87,7 +88,7 @@ struct FinishParams {
     int32_t N, Natom, Ntrans, col0, ncol;
     int32_t sumNlevel, sumNlevel2;
     int64_t colStride, popStride, gammaStride, scratchStride;
-    int64_t off_C, off_nTotal, off_part;
+    int64_t off_C, off_nTotal, off_part, upOff;
     const int32_t *Nlevel;     // [Natom]
     const int32_t *lvlOff;     // [Natom+1]
     const int32_t *g2Off;      // [Natom+1]
