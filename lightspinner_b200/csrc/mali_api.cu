@@ -184,7 +184,7 @@ struct mali_model {
     double *d_alpha = nullptr, *d_twohc = nullptr, *d_wlacont = nullptr, *d_wlambda = nullptr, *d_zmu = nullptr,
            *d_hw = nullptr;
     int32_t *d_Nlevel = nullptr, *d_lvlOff = nullptr, *d_g2Off = nullptr, *d_trans = nullptr, *d_trPartOff = nullptr,
-            *d_trPartRows = nullptr, *d_genericTiles = nullptr;
+            *d_trPartRows = nullptr, *d_genericTiles = nullptr, *d_tileJOff = nullptr;
     CopyJob *d_cjobs = nullptr;
     PackChunk *d_pchunks = nullptr;
     PackTile *d_ptiles = nullptr;
@@ -324,6 +324,7 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
     // ---- tiles, slots and the tile-major record layout (mali_types.cuh)
     std::vector<std::vector<int32_t>> trRows(d->Ntrans);
     std::vector<PackTile> ptiles;
+    std::vector<int32_t> tileJOff;   // per tile: offset of the J-dagger field inside a depth row
     std::vector<PackSlot> pslots;
     std::vector<PackChunk> pchunks;
     int partRow = 0;
@@ -361,15 +362,20 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
         const int sb = 2 * kVRow * nLine;
         PackTile pt{};
         pt.recOff = (int32_t)rowOff;
-        pt.recSize = (int32_t)align_up(sb + (3 + td.nslot) * Lw, 16);
+        // after the Vij rows: the J-dagger field (written by j_finish_kernel; padded to whole 32-byte sectors), then
+        // the per-wavelength fields
+        const int jw = (Lw + 3) & ~3;
+        pt.recSize = (int32_t)align_up(sb + jw + (3 + td.nslot) * Lw, 16);
+        tileJOff.push_back((int32_t)rowOff + sb);
         pt.la0 = la0;
         pt.nslot = td.nslot;
         pt.slot0 = (int32_t)pslots.size();
         pt.sb = sb;
+        pt.pad0 = jw;
         int lineIdx = 0;
         for (int q = 0; q < td.nslot; ++q) {
             SlotDesc &s = m->slots[td.slot0 + q];
-            s.fOff = sb + (3 + q) * Lw;
+            s.fOff = sb + jw + (3 + q) * Lw;
             PackSlot ps{};
             ps.isLine = s.isLine;
             ps.Nblue = s.Nblue;
@@ -384,7 +390,7 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
         for (int e0 = 0; e0 < pt.recSize; e0 += 32) pchunks.push_back(PackChunk{ti, e0});
         ptiles.push_back(pt);
         td.recOff = pt.recOff;
-        td.bgOff = sb;
+        td.bgOff = sb + jw;
         td.vDir = kVRow * nLine;
         td.nlevslot = (int)lev.size();
         rowOff += pt.recSize;
@@ -552,6 +558,7 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
     up(to_device(m->trans, &m->d_trans));
     up(to_device(trPartOff, &m->d_trPartOff));
     up(to_device(trPartRows, &m->d_trPartRows));
+    up(to_device(tileJOff, &m->d_tileJOff));
     up(to_device(m->genericTiles, &m->d_genericTiles));
     up(to_device(m->cjobs, &m->d_cjobs));
     up(to_device(pchunks, &m->d_pchunks));
@@ -571,7 +578,7 @@ void mali_model_destroy(mali_model *m)
     cudaSetDevice(m->device);
     void *ptrs[] = {m->d_tiles, m->d_slots, m->d_alpha, m->d_twohc, m->d_wlacont, m->d_wlambda, m->d_zmu, m->d_hw,
                     m->d_Nlevel, m->d_lvlOff, m->d_g2Off, m->d_trans, m->d_trPartOff, m->d_trPartRows,
-                    m->d_genericTiles, m->d_cjobs, m->d_pchunks, m->d_ptiles, m->d_pslots};
+                    m->d_genericTiles, m->d_cjobs, m->d_pchunks, m->d_ptiles, m->d_pslots, m->d_tileJOff};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (cudaEvent_t e : m->profEvents) cudaEventDestroy(e);
@@ -815,8 +822,8 @@ static int launch_fs(const mali_model *m, const mali_buffers *b, int col0, int n
     dim3 grid((m->N + 63) / 64, m->Natom, ncol);
     gamma_finish_kernel<<<grid, 64, 0, st>>>(f);
     {
-        const int nb = (int)std::min<int64_t>(16, (m->lay.J + 255) / 256);
-        j_finish_kernel<<<dim3(nb, ncol), 256, 0, st>>>(b->J, m->lay.J, b->scratch, m->lay.scratch, m->off_jpart, m->upOff,
+        const int nb = std::min(m->N, 41);   // depth rows are dealt round-robin to the blocks of a column
+        j_finish_kernel<<<dim3(nb, ncol), 256, 0, st>>>(b->J, m->lay.J, b->scratch, m->lay.scratch, m->off_jpart, m->upOff, b->colconst, m->lay.colconst, m->off_tab, m->rowStride, m->d_tileJOff, m->Nspect, m->Lw,
                                                       reinterpret_cast<unsigned long long *>(b->dJ), b->done, col0);
     }
     m->launches += 2;

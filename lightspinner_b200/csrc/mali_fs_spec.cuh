@@ -283,7 +283,6 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
     const bool leader = valid && (mu == 0);
 
     const double *__restrict__ cc = p.colconst + (size_t)col * p.colStride;
-    double *Jcol = p.J + (size_t)col * p.JStride;
     double *scr = p.scratch + (size_t)col * p.scratchStride;
     double *Jpart = scr + p.off_jpart;
     double *part = scr + p.off_part + (size_t)T.partRow0 * N;
@@ -355,7 +354,8 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
     constexpr int LW = S.lw;
     constexpr int NLINE = spec_line_index(S, S.nslot);
     constexpr int VBLK = NLINE * kVRow;                                    // one direction's Vij rows
-    constexpr int SMALL = ((3 + NS) * LW + 15) / 16 * 16;                  // bg + slot fields, padded as packed
+    constexpr int JW = (LW + 3) / 4 * 4;                                   // J-dagger field (whole sectors)
+    constexpr int SMALL = (JW + (3 + NS) * LW + 15) / 16 * 16;             // J-dagger + bg + slot fields, padded as packed
     constexpr int STAGE = VBLK + SMALL;                                    // doubles of one ring stage
     constexpr int NST = 3;                                                 // ring depth: two steps in flight
 #define line_index(tt) spec_line_index(S, (tt))
@@ -429,13 +429,12 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
                     const double ld = __ldg(rec + VBLK + line_index(tt) * kVRow + lane);
                     chiTot += ni * ld - nj * (T.s[tt].cA * ld);
                 } else {
-                    const double ld = __ldg(rec + 2 * VBLK + (3 + tt) * LW + lsC);
+                    const double ld = __ldg(rec + 2 * VBLK + JW + (3 + tt) * LW + lsC);
                     chiTot += ni * ca[tt] - nj * (ld * ca[tt]);
                 }
             }
-            chiProbe = chiTot + __ldg(rec + 2 * VBLK + lsC);
+            chiProbe = chiTot + __ldg(rec + 2 * VBLK + JW + lsC);
         }
-        double JdN = Jcol[kl];
 
         Sweep sw;
         sw.r3 = r3;
@@ -453,13 +452,9 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
         for (int s = 0; s < N; ++s) {
             const int k = kS + s * dk;
             const double *sV = ring + (useOff >> 3) + lane;          // this direction's Vij rows, lane order
-            const double *sS = ring + (useOff >> 3) + VBLK + lsC;    // per-wavelength fields
-            const double Jdag = JdN;
+            const double *sS = ring + (useOff >> 3) + VBLK + JW + lsC;    // per-wavelength fields
             const int klc = kl;
-            if (s + 1 < N) {
-                kl += dkl;
-                JdN = Jcol[kl];
-            }
+            kl += dkl;
             // the stage refilled here (step g+2) is the one step g-1 used: every lane has passed that step's __syncwarp
             fetch_next();
             {   // wait for this step's record
@@ -519,6 +514,7 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
             }
             chiTot += sS[0];
             const double rchi = rcp_full(chiTot);
+            const double Jdag = sS[-JW];             // J-dagger: written into the record by j_finish_kernel
             const double Ssrc = div_by(etaTot + sS[LW] + sS[2 * LW] * Jdag, chiTot, rchi);
 
             // ---- (2) short characteristic

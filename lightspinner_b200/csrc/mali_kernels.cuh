@@ -475,18 +475,36 @@ __global__ void __launch_bounds__(128) fs_gamma_kernel(const FsParams p)
 // dJ = max |1 - JDag/J| (rh_method.py:705-706) and J <- the new mean intensity the sweeps accumulated in Jpart.
 // Elementwise over one column's [Nspace][Nspect] plane; block max -> one atomicMax per block.
 __global__ void j_finish_kernel(double *J, int64_t JStride, const double *scratch, int64_t scratchStride,
-                                int64_t offJpart, int64_t upOff, unsigned long long *dJbits, const int32_t *done, int col0)
+                                int64_t offJpart, int64_t upOff, double *colconst, int64_t colStride, int64_t offTab,
+                                int64_t rowStride, const int32_t *tileJOff, int Nspect, int Lw,
+                                unsigned long long *dJbits, const int32_t *done, int col0)
 {
     const int col = col0 + blockIdx.y;
     if (done != nullptr && done[col] != 0) return;
     double *Jc = J + (size_t)col * JStride;
+    double *tab = colconst + (size_t)col * colStride + offTab;
     const double *Jn = scratch + (size_t)col * scratchStride + offJpart;
     unsigned long long b = 0ull;
-    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < JStride; q += (int64_t)gridDim.x * blockDim.x) {
-        const double jn = Jn[q] + Jn[q + upOff];  // down-sweep + up-sweep sums, rh_method.py:640
-        const unsigned long long v = absbits(1.0 - Jc[q] / jn);
-        b = v > b ? v : b;
-        Jc[q] = jn;
+    const int N = (int)(JStride / Nspect);
+    const int jw = (Lw + 3) & ~3;                              // width of the J-dagger field of a record
+    const int ntile = (Nspect + Lw - 1) / Lw;
+    for (int k = blockIdx.x; k < N; k += gridDim.x) {          // one depth row at a time: no 64-bit divisions
+        const int64_t q0 = (int64_t)k * Nspect;
+        double *rec = tab + (size_t)k * rowStride;
+        for (int idx = threadIdx.x; idx < ntile * jw; idx += blockDim.x) {
+            const int ti = idx / jw, ls = idx - ti * jw;
+            const int la = ti * Lw + ls;
+            double jn = 0.0;
+            if (ls < Lw && la < Nspect) {
+                jn = Jn[q0 + la] + Jn[q0 + la + upOff];  // down-sweep + up-sweep sums, rh_method.py:640
+                const unsigned long long v = absbits(1.0 - Jc[q0 + la] / jn);
+                b = v > b ? v : b;
+                Jc[q0 + la] = jn;
+            }
+            // the copy the next formal solution reads (J-dagger): a field of the tile-major records, so that it
+            // arrives with the record's TMA and the depth loop holds no global loads; whole sectors are written
+            rec[tileJOff[ti] + ls] = jn;
+        }
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
@@ -644,7 +662,7 @@ struct PackSlot {
     double c0;        // hc/4pi*Bij
 };
 struct PackTile {
-    int32_t recOff, recSize, la0, nslot, slot0, sb, pad0, pad1;  // sb: record offset of bg chi
+    int32_t recOff, recSize, la0, nslot, slot0, sb, pad0, pad1;  // sb: size of the Vij rows; pad0: width of the J-dagger field
 };
 struct PackChunk {
     int32_t tile, e0;  // 32 consecutive record elements of one tile
@@ -679,8 +697,9 @@ __global__ void pack_tiles_kernel(const PackChunk *chunks, const PackTile *tiles
                     if (la < Nspect && lt >= 0 && lt < ps.Nlam)
                         v = ps.c0 * src[ps.srcOff + ((size_t)(lt * Nrays + mu) * 2 + d) * N + k];
                 }
-            } else {
-                const int f = (e - pt.sb) / Lw, ls = (e - pt.sb) - f * Lw;
+            } else if (e >= pt.sb + pt.pad0) {  // (the J-dagger field in between starts as zeros)
+                const int ef = e - pt.sb - pt.pad0;
+                const int f = ef / Lw, ls = ef - f * Lw;
                 const int la = pt.la0 + ls;
                 const int laClamp = la < Nspect ? la : Nspect - 1;
                 if (f == 0)
