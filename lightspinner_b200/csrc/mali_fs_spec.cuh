@@ -1,20 +1,27 @@
-// mali_fs_spec.cuh -- structure-specialised formal-solution / Gamma kernel: fs_gamma_kernel_s<S>.
+// mali_fs_spec.cuh -- structure-specialised formal-solution / Gamma kernel (fs_body<SPEC>, launched through the
+// three "mega" kernels fs_gamma_kernel_m<CLS> of mali_api.cu).
 //
-// Same mapping, memory layout and arithmetic as fs_gamma_kernel_c (mali_fs_kernel.cuh), but the STRUCTURE of the
-// tile -- how many transitions overlap it, which are lines, which atom and which lower / upper level each one
-// connects (i.e. which transitions share a level in the MALI cross terms, rh_method.py:619-622, 677-680) -- is a
-// compile-time constant (a C++20 class-type template parameter).  Consequences on sm_100a:
+// Same mapping and arithmetic as the generic fs_gamma_kernel (mali_kernels.cuh), but the STRUCTURE of the tile --
+// how many transitions overlap it, which are lines, which atom and which lower / upper level each one connects
+// (i.e. which transitions share a level in the MALI cross terms, rh_method.py:619-622, 677-680) -- is a
+// compile-time constant (a C++20 constexpr struct carried by a tag type).  Consequences on sm_100a:
 //   * the per-level sums chi[level], U[level] and the per-atom emissivity are plain registers with compile-time
 //     indices: no shared-memory read-modify-write, no first-touch branches, no address arithmetic;
 //   * slot loops unroll to the exact transition count; line / continuum code is selected at compile time;
-//   * the Gamma reduce-scatter is sized to the exact number of matrix entries of the tile (2, 4, 8 or 16 values);
-//   * register allocation is exact for the tile, so light tiles run at higher occupancy.
+//   * the Gamma reduce-scatter is sized to the exact number of matrix entries of the tile (2, 4, 8 or 16 values).
 // What stays run-time (warp-uniform, constant bank): where the tile sits (first wavelength, table offsets, Nblue,
 // Nlambda per transition, the lines' Einstein ratios) -- so one instance serves every tile with that structure.
 //
+// Data movement: the depth loop contains NO global loads.  A 3-stage TMA ring (cp.async.bulk + mbarrier, issued
+// by one elected lane from warp-uniform registers) streams each depth step's tile record -- this direction's Vij
+// rows, the per-wavelength fields and J-dagger -- into shared memory two steps ahead; the column's heights and the
+// level populations the tile touches are staged by TMA bulk copies before the sweep.  The down and the up sweep
+// store their J / Gamma partial sums to separate scratch copies (no read-modify-write); the second half of each
+// step's warp reductions runs during the following step so that its latency overlaps arithmetic.
+//
 // Instances for the structures of known models are generated ahead of time (tools/gen_spec_instances.py ->
-// spec_instances.inc, compiled by nvcc into libmali_b200.so); tiles whose structure has no instance fall back to
-// the class kernels of mali_fs_kernel.cuh.
+// spec_instances.inc, compiled by nvcc into libmali_b200.so); tiles whose structure has no instance run on the
+// generic kernel.
 #pragma once
 #include "mali_kernels.cuh"
 
@@ -65,7 +72,7 @@ __host__ __device__ constexpr int spec_class_slots(int cls) { return cls == 0 ? 
 #define MALI_OCC0 16
 #endif
 #ifndef MALI_OCC1
-#define MALI_OCC1 12
+#define MALI_OCC1 14
 #endif
 #ifndef MALI_OCC2
 #define MALI_OCC2 12
@@ -253,8 +260,15 @@ __device__ __forceinline__ void finish_step(int lane, int Nrays, const double *r
 #ifndef MALI_DEFER
 #define MALI_DEFER 1
 #endif
-#ifndef MALI_UNROLL
-#define MALI_UNROLL 2
+// depth-loop unroll factor per register class (<=2, <=4, <=8 transitions)
+#ifndef MALI_UNROLL0
+#define MALI_UNROLL0 2
+#endif
+#ifndef MALI_UNROLL1
+#define MALI_UNROLL1 2
+#endif
+#ifndef MALI_UNROLL2
+#define MALI_UNROLL2 1
 #endif
 
 // SPEC is a tag type with a `static constexpr TileStruct S` member (the structure travels inside a type).
@@ -267,7 +281,7 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
     constexpr int NLV = S.nlev > 0 ? S.nlev : 1;
     constexpr int NA = S.natom > 0 ? S.natom : 1;
     constexpr int M = spec_pow2(2 * NS);
-    constexpr int kUnroll = MALI_UNROLL;
+    constexpr int kUnroll = NS > 4 ? MALI_UNROLL2 : (NS > 2 ? MALI_UNROLL1 : MALI_UNROLL0);
     // one warp per block: the column (hence every base pointer) is block-uniform -> uniform-register addressing
     const int lane = threadIdx.x;
     const int col = p.col0 + blockIdx.x;

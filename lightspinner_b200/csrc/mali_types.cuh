@@ -5,10 +5,12 @@
 // Nspace depth points; a *tile* is the group of Lw = 32 / Nrays consecutive wavelengths (all angles)
 // one warp owns; a *slot* is one radiative transition overlapping a tile's wavelength range.
 //
-// The iteration-invariant per-column tables are stored TILE-MAJOR: for every depth k one row of `rowStride` doubles
-// holding, tile after tile, one contiguous *record* with everything the tile's warp reads at that depth:
+// The per-column tables are stored TILE-MAJOR: for every depth k one row of `rowStride` doubles holding, tile after
+// tile, one contiguous *record* with everything the tile's warp reads at that depth:
 //     [ Vij rows of direction 0: one per line slot, each kVRow = 32 doubles = (wavelength, angle) in lane order ]
 //     [ Vij rows of direction 1 ]
+//     [ J-dagger[Lw rounded up to 4]: the mean intensity of the previous iteration, rewritten by j_finish_kernel
+//       (the only part of a record that changes between iterations; zero after upload) ]
 //     [ bg chi[Lw] | bg eta[Lw] | bg sca[Lw] ]
 //     [ per slot: wla[Lw] (lines, rh_method.py:451) or g_ij[Lw] (continua, :453-454) ]      (padded to 16 doubles)
 // Entries for wavelengths on which a transition is not active are zero, so the kernels need no activity masks for
