@@ -393,13 +393,72 @@ def main():
         except Exception as ex:   # never let the side measurement break the main line
             single = {'error': repr(ex)}
 
+    # ---- BASELINE config 3 on the side: the response-function batch (164 perturbed CaII/FALC columns, warm-started
+    # from the converged base populations, response_fn.py:23-39), columns sharded over the ranks, each column run to
+    # the reference's convergence tolerance by the device-resident loop.  The columns cycle through the two
+    # response-function problems generated with the unmodified reference (tests/golden/rf_*.npz), so the iteration
+    # counts and emergent intensities can be checked against the reference's own.
+    rf = None
+    if not args.no_cpu:
+        try:
+            from helpers import load_golden
+            from lightspinner_b200.sharding import shard_range
+            gold = [load_golden(nm) for nm in ('rf_k40p', 'rf_k10m')]
+            n_rf = 164
+            lo, cnt = shard_range(n_rf, world, rank)
+            hi = lo + cnt
+            mine = [gold[c % 2] for c in range(lo, hi)]
+            e3 = MaliEngine(gold[0][0], max(len(mine), 1), device=local)
+            packs = [torch.from_numpy(pack_column(e3.mt, e3.lay, g[0])) for g in gold]
+            hp3 = int(e3.lay.hostpack)
+            host3 = torch.empty(max(len(mine), 1) * hp3, dtype=torch.float64, pin_memory=True)
+            for i in range(len(mine)):
+                host3[i * hp3:(i + 1) * hp3].copy_(packs[(lo + i) % 2])
+            times, its = [], None
+            for rep in range(3):
+                barrier()
+                t0 = time.perf_counter()
+                if mine:
+                    for c0 in range(0, len(mine), 64):      # H2D + re-layout + solve, as a user would run it
+                        nc = min(64, len(mine) - c0)
+                        e3.upload_packed(host3[c0 * hp3:(c0 + nc) * hp3], c0, nc)
+                    e3.reset_iteration_state()
+                    e3.iterate_async(64, ncol=len(mine))
+                barrier()
+                times.append(max_over_ranks(time.perf_counter() - t0))
+            ok = True
+            if mine:
+                its = e3.t_iter.cpu().numpy()[:len(mine)]
+                for i in range(len(mine)):
+                    g = mine[i][1]
+                    ok = ok and int(its[i]) == int(g['niter'])
+                    if i < 2:
+                        ref_I = np.asarray(g['final_I'])
+                        ok = ok and float(np.max(np.abs(e3.I(i) - ref_I) / np.abs(ref_I))) < 1e-10
+            okt = torch.tensor([1.0 if ok else 0.0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+            g0 = gold[0][0]
+            units_rf = sum(int(gold[c % 2][1]['niter']) for c in range(n_rf)) * int(g0['Nspect']) * int(g0['Nrays']) * int(g0['Nspace'])
+            rf = {'config': 'response-function batch: 164 perturbed CaII/FALC columns (T[k] +/- 25 K, warm start), '
+                            'to convergence, host buffers -> H2D -> solve (device-resident loop)',
+                  'columns': n_rf, 'columns_this_rank': len(mine), 'seconds_to_converge': min(times),
+                  'seconds_all_reps': times, 'updates_per_s': units_rf / min(times),
+                  'iterations': sorted(set(int(x) for x in its)) if its is not None else [],
+                  'matches_reference': bool(okt.item() > 0.5),
+                  'check': 'iteration count of every column == the reference\'s; I(lambda, mu) of the first two '
+                           'columns within 1e-10 of the reference\'s converged output (tests/golden/rf_*.npz)'}
+            e3.close()
+        except Exception as ex:
+            rf = {'error': repr(ex)}
+
     if rank == 0:
         cfg = workload_config(args, base)
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
                 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': cfg, 'clocks': clocks,
                 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu,
-                'single_column': single, 'results_finite': finite}
+                'single_column': single, 'response_function': rf, 'results_finite': finite}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
