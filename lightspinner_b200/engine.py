@@ -23,16 +23,17 @@ class MaliEngine:
     def __init__(self, model, ncol, device=None, max_upload_chunk=64, specialize=False):
         """specialize=True: if the model has wavelength tiles without a specialised kernel instance and nvcc is
         available, build (once, cached) a model-specific variant of the library; otherwise those tiles run on the
-        generic kernel."""
+        generic kernel.  specialize=<problem dict>: build / pick the variant that covers THAT model (e.g. the full
+        column when `model` is one wavelength shard of it, so that every rank loads the same library)."""
         if not torch.cuda.is_available():
             raise RuntimeError('lightspinner_b200 needs a CUDA device: the MALI hot path has no CPU fallback')
         self.mt = model if isinstance(model, ModelTables) else ModelTables(model)
         self.ncol = int(ncol)
         self.device = torch.device('cuda', torch.cuda.current_device() if device is None else device)
         lib_path = None
-        if specialize and not isinstance(model, ModelTables):
+        if isinstance(specialize, dict) or (specialize and not isinstance(model, ModelTables)):
             from . import specialize as _spec
-            lib_path = _spec.library_for(model)
+            lib_path = _spec.library_for(specialize if isinstance(specialize, dict) else model)
         self.lib = _capi.load(lib_path)
         self._handle = C.c_void_p()
         desc = self.mt.desc()

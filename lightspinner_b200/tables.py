@@ -17,6 +17,9 @@ column part
     C [sum Nlevel^2, Nspace]   C[i, j, k] per atom, flattened                               (rh_method.py:474-487)
     phi  1-D concat of each line's phi[Nlambda, Nrays, 2, Nspace], phioff [Ntrans]           (rh_method.py:224)
     wphi [Ntrans, Nspace]      (rows of continua unused)
+optional
+    wlambda_table [sum Nlambda]  the wavelength weights, when a transition's grid here is only a slice of the
+                                 grid they were formed on (wavelength-sharded single column, lambda_shard.py)
 
 Everything here is iteration-invariant set-up.  The tables that the reference evaluates with numpy
 transcendental code (not numba) are evaluated here with the same scalar/vector numpy expressions so that
@@ -73,6 +76,11 @@ class ModelTables:
         self.twohc_l3 = np.zeros(ntab)
         self.wlacont = np.zeros(ntab)
         hc_4pi = 0.25 * HC / np.pi                                   # rh_method.py:268
+        w_given = p.get('wlambda_table')
+        if w_given is not None:
+            w_given = _f64(w_given)
+            if w_given.shape[0] != ntab:
+                raise ValueError('wlambda_table must hold sum(Nlambda) = %d entries' % ntab)
         for t in range(self.Ntrans):
             atom, i, j, isLine, Nblue, Nlam = (int(v) for v in self.trans[t])
             wl = self.wavelength[Nblue:Nblue + Nlam]
@@ -85,10 +93,13 @@ class ModelTables:
                 dopplerWidth = CLight / lambda0                      # :179
             else:
                 dopplerWidth = 1.0
-            w = np.empty(Nlam)
-            w[0] = 0.5 * (wl[1] - wl[0]) * dopplerWidth              # :185
-            w[-1] = 0.5 * (wl[-1] - wl[-2]) * dopplerWidth           # :187
-            w[1:-1] = 0.5 * (wl[2:] - wl[:-2]) * dopplerWidth        # :189
+            if w_given is not None:
+                w = w_given[o:o + Nlam]
+            else:
+                w = np.empty(Nlam)
+                w[0] = 0.5 * (wl[1] - wl[0]) * dopplerWidth          # :185
+                w[-1] = 0.5 * (wl[-1] - wl[-2]) * dopplerWidth       # :187
+                w[1:-1] = 0.5 * (wl[2:] - wl[:-2]) * dopplerWidth    # :189
             self.wlambda[o:o + Nlam] = w
             if not isLine:
                 for lt in range(Nlam):                               # scalar numpy power / divide, as the reference

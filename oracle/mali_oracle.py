@@ -145,6 +145,7 @@ def model_tables(p):
     twohc = np.zeros(ntot)
     wlacont = np.zeros(ntot)
     hc_4pi = 0.25 * HC / np.pi
+    w_given = p.get('wlambda_table')   # weights formed on a larger grid (wavelength-sharded column)
     for t, (atom, i, j, isLine, Nblue, Nlam) in enumerate(trans):
         wl = wavelength[Nblue:Nblue + Nlam]
         if isLine:
@@ -154,7 +155,9 @@ def model_tables(p):
         else:
             dopplerWidth = 1.0
         for lt in range(Nlam):
-            if lt == 0:
+            if w_given is not None:
+                w = np.float64(w_given[toff[t] + lt])
+            elif lt == 0:
                 w = 0.5 * (wl[1] - wl[0]) * dopplerWidth
             elif lt == Nlam - 1:
                 w = 0.5 * (wl[-1] - wl[-2]) * dopplerWidth
