@@ -101,14 +101,6 @@ struct MegaParams {
     TileR<NSP> tiles[kMaxTiles];
 };
 
-// streaming read (each element is used by exactly one lane, once per direction): do not allocate in L1
-__device__ __forceinline__ double ld_stream(const double *p)
-{
-    double v;
-    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
-    return v;
-}
-
 // Warp reduce-scatter through shared memory, split in two so that the second half can run one depth step later
 // (its latency then overlaps the next step's arithmetic): reduce_store puts the lane's M values into the per-warp
 // scratch (M rows x 36 doubles; lane l of a row sits at l + l/8: conflict-free stores and loads); reduce_load sums
@@ -152,10 +144,7 @@ __host__ __device__ constexpr int spec_level_row(const TileStruct &S, int lv)
     return 0;
 }
 
-#ifndef MALI_NT
-#define MALI_NT 0
-#endif
-// populations of the levels a tile touches, transposed into shared memory as [depth][level-slot]
+// populations of the levels a tile touches -> sN[level-slot][depth] (plain loads: N odd, no bulk copy possible)
 template <class SPEC, int LV>
 __device__ __forceinline__ void stage_levels(double *sN, const double *gN, int N, int lane)
 {
@@ -163,18 +152,12 @@ __device__ __forceinline__ void stage_levels(double *sN, const double *gN, int N
     if constexpr (LV < S.nlev) {
         constexpr int row = spec_level_row(S, LV);   // constant-evaluated: S never materialises in local memory
         const double *src = gN + (size_t)row * N;
-        for (int k = lane; k < N; k += 32) sN[MALI_NT ? k * S.nlev + LV : LV * N + k] = src[k];
+        for (int k = lane; k < N; k += 32) sN[LV * N + k] = src[k];
         stage_levels<SPEC, LV + 1>(sN, gN, N, lane);
     }
 }
 
-#if MALI_NT
-#define NIDX(k, lv) ((k) * NLV + (lv))
-#define NSTEP NLV
-#else
-#define NIDX(k, lv) ((lv) * N + (k))
-#define NSTEP 1
-#endif
+#define NIDX(k, lv) ((lv) * N + (k))   // populations in shared memory: [level-slot][depth]
 // one TMA bulk copy per level row the tile touches -> sN[level-slot][depth]
 template <class SPEC, int LV>
 __device__ __forceinline__ void stage_levels_bulk(double *sN, const double *gN, int N, uint32_t mbar)
@@ -257,9 +240,6 @@ __device__ __forceinline__ void finish_step(int lane, int Nrays, const double *r
     if (leader) __stcg(jdst, sum);
 }
 
-#ifndef MALI_DEFER
-#define MALI_DEFER 1
-#endif
 // depth-loop unroll factor per register class (<=2, <=4, <=8 transitions)
 #ifndef MALI_UNROLL0
 #define MALI_UNROLL0 2
@@ -318,7 +298,7 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
                 asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
                 asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar),
-                             "r"(bytesZ * (uint32_t)(1 + (MALI_NT ? 0 : S.nlev)))
+                             "r"(bytesZ * (uint32_t)(1 + S.nlev))
                              : "memory");
                 asm volatile(
                     "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -329,9 +309,6 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
         } else {
             for (int q = lane; q < N; q += 32) sZ[q] = gZ[q];
         }
-#if MALI_NT
-        if constexpr (NS > 0) stage_levels<SPEC, 0>(sN, gN, N, lane);
-#else
         if constexpr (NS > 0) {
             if (p.useBulk) {
                 if (lane == 0) stage_levels_bulk<SPEC, 0>(sN, gN, N, mbar);
@@ -339,7 +316,6 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
                 stage_levels<SPEC, 0>(sN, gN, N, lane);
             }
         }
-#endif
         __syncwarp();
         if (p.useBulk) {
             uint32_t ok = 0;
@@ -461,7 +437,7 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
         double *gdir = gbase + (d ? p.upOff : 0), *jdir = Jpart + (d ? p.upOff : 0);
 #define finish_prev() finish_step<M, NS>(lane, Nrays, red, writer, leader, gdir + kP, jdir + klP, xP)
 
-        const double *nk = sN + kS * NSTEP;   // populations at the current depth
+        const double *nk = sN + kS;   // populations at the current depth
 #pragma unroll kUnroll
         for (int s = 0; s < N; ++s) {
             const int k = kS + s * dk;
@@ -483,9 +459,7 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
                 } while (!ok);
                 phases ^= useBit;
             }
-#if MALI_DEFER
             if (s > 0) finish_prev();
-#endif
 
             // ---- (1) opacity / emissivity, rh_method.py:601-632.  chiL / UL / etaA: compile-time indexed registers
             double chiTot = 0.0, etaTot = 0.0;
@@ -574,9 +548,6 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
                 kP = k;
             }
             __syncwarp();                     // values visible; ring stage of this step free for the next fetch
-#if !MALI_DEFER
-            finish_prev();
-#endif
 
             // next stage / depth
             {
@@ -585,11 +556,9 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
                 useBar = wrap ? barAddr : useBar + 8u;
                 useBit = wrap ? 1u : useBit << 1;
             }
-            nk += dk * NSTEP;
+            nk += dk;
         }
-#if MALI_DEFER
         finish_prev();
-#endif
         __syncwarp();
         if (d == 1 && valid) p.I[(size_t)col * p.IStride + (size_t)la * Nrays + mu] = sw.Iupw;
         if (valid && sw.bad && p.status != nullptr) atomicOr(p.status + col, 2);
@@ -597,7 +566,6 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
 #undef line_index
 #undef fetch_next
 #undef NIDX
-#undef NSTEP
 #undef finish_prev
 }
 
