@@ -241,13 +241,16 @@ def main():
     staging = [torch.empty(chunk * hp, dtype=torch.float64, device=dev) for _ in range(2)]
     want_e2e = not args.no_e2e
     host_in = torch.empty(ncol * hp, dtype=torch.float64, pin_memory=True) if want_e2e else None
-    for c0 in range(0, ncol, chunk):
-        nc = min(chunk, ncol - c0)
-        synth.jitter_staging(staging[0], lay, mt, base_pack, [col_global0 + c for c in range(c0, c0 + nc)])
-        eng.repack_from_staging(staging[0], c0, nc)
-        if want_e2e:
-            host_in[c0 * hp:(c0 + nc) * hp].copy_(staging[0][:nc * hp])
-    torch.cuda.synchronize(dev)
+    def fill_batch(keep_host_copy):
+        for c0 in range(0, ncol, chunk):
+            nc = min(chunk, ncol - c0)
+            synth.jitter_staging(staging[0], lay, mt, base_pack, [col_global0 + c for c in range(c0, c0 + nc)])
+            eng.repack_from_staging(staging[0], c0, nc)
+            if keep_host_copy:
+                host_in[c0 * hp:(c0 + nc) * hp].copy_(staging[0][:nc * hp])
+        torch.cuda.synchronize(dev)
+
+    fill_batch(want_e2e)
 
     def solve_resident():
         for _ in range(iters):
@@ -393,6 +396,40 @@ def main():
         except Exception as ex:   # never let the side measurement break the main line
             single = {'error': repr(ex)}
 
+    # ---- second half of BASELINE's metric: seconds to converge.  The same batch, from its start populations, run
+    # by the device-resident loop until every column meets the reference's tolerances (test.py:20: dJ <= 2e-3 and
+    # dPops <= 1e-3, statistical equilibrium from the 4th iteration on); converged columns drop out of the launches.
+    conv = None
+    if not args.no_cpu:
+        try:
+            fill_batch(False)
+            eng.reset_iteration_state()
+            barrier()
+            t0 = time.perf_counter()
+            n_it = 0
+            while n_it < 400:          # 16 iterations per host round trip; converged columns skip their work
+                eng.iterate_async(16)
+                n_it += 16
+                if bool((eng.t_done != 0).all().item()):
+                    break
+            barrier()
+            dt = max_over_ranks(time.perf_counter() - t0)
+            its = eng.t_iter.cpu().numpy().astype(np.int64)
+            tot = torch.tensor([float(its.sum()), float(its.max()), float(-its.min()),
+                                float((eng.t_done.cpu().numpy() != 0).sum())], dtype=torch.float64, device=dev)
+            if world > 1:
+                s2 = tot.clone()
+                dist.all_reduce(s2, op=dist.ReduceOp.SUM)
+                dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+                tot[0], tot[3] = s2[0], s2[3]
+            conv = {'config': 'the %d-column batch to convergence (dJ <= 2e-3, dPops <= 1e-3), device-resident loop' % (world * ncol),
+                    'seconds_to_converge': dt, 'columns': world * ncol, 'columns_converged': int(tot[3].item()),
+                    'iterations_max': int(tot[1].item()), 'iterations_min': int(-tot[2].item()),
+                    'iterations_mean': float(tot[0].item()) / (world * ncol),
+                    'updates_per_s': float(tot[0].item()) * units_per_col_iter / dt}
+        except Exception as ex:
+            conv = {'error': repr(ex)}
+
     # ---- BASELINE config 3 on the side: the response-function batch (164 perturbed CaII/FALC columns, warm-started
     # from the converged base populations, response_fn.py:23-39), columns sharded over the ranks, each column run to
     # the reference's convergence tolerance by the device-resident loop.  The columns cycle through the two
@@ -458,7 +495,7 @@ def main():
                 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
                 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': cfg, 'clocks': clocks,
                 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu,
-                'single_column': single, 'response_function': rf, 'results_finite': finite}
+                'single_column': single, 'to_convergence': conv, 'response_function': rf, 'results_finite': finite}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
