@@ -191,6 +191,10 @@ struct mali_model {
     PackSlot *d_pslots = nullptr;
     // optional per-launch timing of the formal-solution stage (mali_profile_begin / mali_profile_end)
     mutable std::vector<cudaEvent_t> profEvents;
+    // the three register-class kernels of one formal solution are independent: they run on the caller's stream
+    // and two side streams (fork / join by events), so that one kernel's tail overlaps the others
+    cudaStream_t sideStream[2] = {nullptr, nullptr};
+    cudaEvent_t forkEvent = nullptr, joinEvent[2] = {nullptr, nullptr};
     mutable int profUsed = 0;
     mutable bool profOn = false;
     mutable long long launches = 0;  // kernels launched through this model since creation
@@ -568,6 +572,17 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
         mali_model_destroy(m);
         return fail((int)e, "mali_model_create: %s", cudaGetErrorString(e));
     }
+    if (!getenv("MALI_SERIAL_CLASSES")) {   // side streams of launch_fs (MALI_SERIAL_CLASSES=1: one stream, for profiling)
+        for (int q = 0; q < 2 && e == cudaSuccess; ++q) {
+            e = cudaStreamCreateWithFlags(&m->sideStream[q], cudaStreamNonBlocking);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->joinEvent[q], cudaEventDisableTiming);
+        }
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->forkEvent, cudaEventDisableTiming);
+        if (e != cudaSuccess) {
+            mali_model_destroy(m);
+            return fail((int)e, "mali_model_create: %s", cudaGetErrorString(e));
+        }
+    }
     *out = m;
     return MALI_OK;
 }
@@ -582,6 +597,11 @@ void mali_model_destroy(mali_model *m)
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (cudaEvent_t e : m->profEvents) cudaEventDestroy(e);
+    for (int q = 0; q < 2; ++q) {
+        if (m->sideStream[q]) cudaStreamDestroy(m->sideStream[q]);
+        if (m->joinEvent[q]) cudaEventDestroy(m->joinEvent[q]);
+    }
+    if (m->forkEvent) cudaEventDestroy(m->forkEvent);
     delete m;
 }
 
@@ -808,11 +828,35 @@ static int launch_fs(const mali_model *m, const mali_buffers *b, int col0, int n
             smem[cls] = (size_t)c.smemBytesPerWarp;
             if (smem[cls] > 227 * 1024) return fail(MALI_ELIMIT, "column needs %zu B of shared memory per warp", smem[cls]);
         }
+        // fork: class 2 (heaviest warps) stays on the caller's stream, classes 1 and 0 go to the side streams
+        // -- only for small launches (a few waves of warps: single columns, response-function batches), where the
+        // serial tails are a large share; big batches fill the machine anyway and keep to one stream
+        const bool small = (int64_t)ncol * m->specTiles <= 16384;
+        const bool side1 = small && m->sideStream[0] && !m->spec1.empty() && (!m->spec2.empty());
+        const bool side0 = small && m->sideStream[1] && !m->spec0.empty() && (!m->spec2.empty() || !m->spec1.empty());
+        if (side1 || side0) CU(cudaEventRecord(m->forkEvent, st));
+        cudaStream_t s1 = st, s0 = st;
+        if (side1) {
+            s1 = m->sideStream[0];
+            CU(cudaStreamWaitEvent(s1, m->forkEvent, 0));
+        }
+        if (side0) {
+            s0 = m->sideStream[1];
+            CU(cudaStreamWaitEvent(s0, m->forkEvent, 0));
+        }
         cudaError_t e = cudaSuccess;
         if (!m->spec2.empty()) e = launch_mega<2>(cc[2], m->spec2, ncol, smem[2], st, &m->launches);
-        if (e == cudaSuccess && !m->spec1.empty()) e = launch_mega<1>(cc[1], m->spec1, ncol, smem[1], st, &m->launches);
-        if (e == cudaSuccess && !m->spec0.empty()) e = launch_mega<0>(cc[0], m->spec0, ncol, smem[0], st, &m->launches);
+        if (e == cudaSuccess && !m->spec1.empty()) e = launch_mega<1>(cc[1], m->spec1, ncol, smem[1], s1, &m->launches);
+        if (e == cudaSuccess && !m->spec0.empty()) e = launch_mega<0>(cc[0], m->spec0, ncol, smem[0], s0, &m->launches);
         if (e != cudaSuccess) return fail((int)e, "fs_gamma_kernel_m: %s", cudaGetErrorString(e));
+        if (side1) {   // join
+            CU(cudaEventRecord(m->joinEvent[0], s1));
+            CU(cudaStreamWaitEvent(st, m->joinEvent[0], 0));
+        }
+        if (side0) {
+            CU(cudaEventRecord(m->joinEvent[1], s0));
+            CU(cudaStreamWaitEvent(st, m->joinEvent[1], 0));
+        }
     }
     if (rec) {
         cudaEventRecord(m->profEvents[m->profUsed + 1], st);
