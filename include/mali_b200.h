@@ -61,16 +61,19 @@ typedef struct {
     const double *alpha;       /* concat: continuum cross-sections */
     const double *twohc_l3;    /* concat: 2hc/(NM_TO_M lambda)^3 (continua) */
     const double *wlacont;     /* concat: wlambda/lambda/h (continua) */
+    const double *lambda0;     /* [Ntrans] line-centre wavelength in nm (lines; only read by mali_compute_phi), may be NULL */
 } mali_model_desc;
 
 /* Sizes (in doubles, per column) of every caller-owned array, and the offsets of the reference-layout
  * arrays inside one column's host staging block ("host pack": plain concatenation, no transposition). */
 typedef struct {
     int64_t hostpack;  /* staging block: what mali_upload_columns copies host->device */
-    int64_t colconst;  /* packed iteration-invariant device block: z, planck BC, C, nTotal, then the tile-major
-                          table [Nspace][tile records] (see csrc/mali_types.cuh) */
+    int64_t colconst;  /* packed per-column device block: z, planck BC, C, nTotal, then the tile-major table
+                          [Nspace][tile records] (see csrc/mali_types.cuh).  Written by mali_upload_columns; the only
+                          part that changes afterwards is the J-dagger field of the records, which
+                          mali_formal_sol_gamma rewrites (it is the copy of J the next formal solution reads) */
     int64_t pops;      /* sumNlevel * Nspace        n[level][k]            (in/out) */
-    int64_t J;         /* Nspace * Nspect           J[k][la]  (depth-major) (in/out) */
+    int64_t J;         /* Nspace * Nspect           J[k][la]  (depth-major) (out; zeroed by upload) */
     int64_t I;         /* Nspect * Nrays            I[la][mu]               (out) */
     int64_t Gamma;     /* sum Nlevel^2 * Nspace     Gamma[i][j][k] per atom (out) */
     int64_t scratch;   /* library scratch per column */
@@ -80,10 +83,12 @@ typedef struct {
     int64_t hp_bg_chi, hp_bg_eta, hp_bg_sca; /* [Nspect][Nspace] */
     int64_t hp_C;        /* concat atoms [Nlevel][Nlevel][Nspace] */
     int64_t hp_nTotal;   /* [Natom][Nspace] */
-    int64_t hp_phi;      /* concat lines, each [Nlambda][Nrays][2][Nspace] (rh_method.py:224) */
-    int64_t hp_wphi;     /* [Ntrans][Nspace] */
     int64_t hp_gijcont;  /* concat [offset+lt][Nspace], continua rows only (rh_method.py:453-454) */
     int64_t hp_n;        /* [sumNlevel][Nspace] starting populations */
+    /* the line profiles come last, so that a caller who lets the device compute them (mali_compute_phi) uploads
+     * only the first hp_phi doubles of every block (mali_upload_columns_nophi): */
+    int64_t hp_phi;      /* concat lines, each [Nlambda][Nrays][2][Nspace] (rh_method.py:224) */
+    int64_t hp_wphi;     /* [Ntrans][Nspace] */
     int32_t sumNlevel, sumNlevel2, ntile, lambda_per_warp;
 } mali_layout;
 
@@ -123,8 +128,26 @@ int mali_planck_bc(const double *wavelength, int32_t Nspect, double Tm2, double 
 int mali_upload_columns(const mali_model *m, const mali_buffers *bufs, int32_t col0, int32_t ncol,
                         const double *host_pack, double *staging_dev, void *stream);
 
-/* Context.formal_sol_gamma_matrices for columns [col0, col0+ncol): updates J (J-dagger is read from the
- * same buffer), I, Gamma and dJ. */
+/* Same, for callers that do not hold the line profiles: host_pack_prefix holds [ncol][layout.hp_phi] doubles (the
+ * blocks without their phi / wphi tail; may be NULL when staging_dev already holds them at stride layout.hostpack).
+ * The profile entries of the device tables are zeroed; call mali_compute_phi before the first formal solution. */
+int mali_upload_columns_nophi(const mali_model *m, const mali_buffers *bufs, int32_t col0, int32_t ncol,
+                              const double *host_pack_prefix, double *staging_dev, void *stream);
+
+/* ComputationalTransition.compute_phi (rh_method.py:198-243) on the device, for columns [col0, col0+ncol): Voigt
+ * profiles phi[la][mu][toFrom][k] = H(aDamp, v -+ mu vlos / vBroad) / (sqrt(pi) vBroad) of every line and their
+ * normalisation wphi, written straight into the device tables (Vij rows and wavelength-weight fields).
+ *   aDamp  [ncol][Ntrans][Nspace] device (rows of continua are not read; atomic_model.py:491-502)
+ *   vBroad [ncol][Natom][Nspace]  device (atomic_model.py:241-245)      vlos [ncol][Nspace] device
+ * Needs mali_model_desc.lambda0.  H comes from csrc/mali_voigt.h (a few ulp; scipy's wofz, which the reference
+ * calls, is good to ~1e-13, so profiles agree with the reference's to that level, not bit for bit). */
+int mali_compute_phi(const mali_model *m, const mali_buffers *bufs, int32_t col0, int32_t ncol, const double *aDamp,
+                     const double *vBroad, const double *vlos, void *stream);
+
+/* Context.formal_sol_gamma_matrices for columns [col0, col0+ncol): updates J, I, Gamma and dJ.  J-dagger (the
+ * previous call's J; zero after an upload, rh_method.py:541) is kept by the library inside colconst.  Work is
+ * enqueued on `stream`; small launches also use two library-owned side streams, forked from and joined back into
+ * `stream` with events, so the call is stream-ordered like any other. */
 int mali_formal_sol_gamma(const mali_model *m, const mali_buffers *bufs, int32_t col0, int32_t ncol, void *stream);
 
 /* Context.stat_equil for columns [col0, col0+ncol): updates pops in place, writes dPops and status. */

@@ -22,13 +22,13 @@ class ModelDesc(C.Structure):
     _fields_ = [('Nspace', C.c_int32), ('Nrays', C.c_int32), ('Nspect', C.c_int32), ('Natom', C.c_int32),
                 ('Ntrans', C.c_int32), ('Nlevel', _ip), ('trans', _ip), ('wavelength', _dp), ('muz', _dp),
                 ('wmu', _dp), ('lineconst', _dp), ('wlambda', _dp), ('alpha', _dp), ('twohc_l3', _dp),
-                ('wlacont', _dp)]
+                ('wlacont', _dp), ('lambda0', _dp)]
 
 
 class Layout(C.Structure):
     _fields_ = [(n, C.c_int64) for n in (
         'hostpack', 'colconst', 'pops', 'J', 'I', 'Gamma', 'scratch', 'hp_height', 'hp_bbc', 'hp_bg_chi',
-        'hp_bg_eta', 'hp_bg_sca', 'hp_C', 'hp_nTotal', 'hp_phi', 'hp_wphi', 'hp_gijcont', 'hp_n')] + \
+        'hp_bg_eta', 'hp_bg_sca', 'hp_C', 'hp_nTotal', 'hp_gijcont', 'hp_n', 'hp_phi', 'hp_wphi')] + \
         [(n, C.c_int32) for n in ('sumNlevel', 'sumNlevel2', 'ntile', 'lambda_per_warp')]
 
 
@@ -39,7 +39,7 @@ class Buffers(C.Structure):
 
 
 EXPORTS = ['mali_last_error', 'mali_device_count', 'mali_model_create', 'mali_model_destroy', 'mali_model_layout', 'mali_model_info',
-           'mali_planck_bc', 'mali_upload_columns', 'mali_formal_sol_gamma', 'mali_stat_equil', 'mali_iterate',
+           'mali_planck_bc', 'mali_upload_columns', 'mali_upload_columns_nophi', 'mali_compute_phi', 'mali_formal_sol_gamma', 'mali_stat_equil', 'mali_iterate',
            'mali_piecewise_linear_1d', 'mali_uv', 'mali_exp_hook', 'mali_div_hook', 'mali_profile_begin',
            'mali_profile_end', 'mali_launch_count', 'mali_fp64_peak']
 
@@ -66,6 +66,9 @@ def load(path=None):
     L.mali_planck_bc.argtypes = [_dp, C.c_int32, C.c_double, C.c_double, _dp]
     L.mali_upload_columns.argtypes = [C.c_void_p, C.POINTER(Buffers), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                       C.c_void_p]
+    L.mali_upload_columns_nophi.argtypes = L.mali_upload_columns.argtypes
+    L.mali_compute_phi.argtypes = [C.c_void_p, C.POINTER(Buffers), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p]
     for name in ('mali_formal_sol_gamma', 'mali_stat_equil'):
         getattr(L, name).argtypes = [C.c_void_p, C.POINTER(Buffers), C.c_int32, C.c_int32, C.c_void_p]
     L.mali_iterate.argtypes = [C.c_void_p, C.POINTER(Buffers), C.c_int32, C.c_int32, C.c_int32, C.c_double,

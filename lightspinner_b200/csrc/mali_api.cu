@@ -184,7 +184,12 @@ struct mali_model {
     double *d_alpha = nullptr, *d_twohc = nullptr, *d_wlacont = nullptr, *d_wlambda = nullptr, *d_zmu = nullptr,
            *d_hw = nullptr;
     int32_t *d_Nlevel = nullptr, *d_lvlOff = nullptr, *d_g2Off = nullptr, *d_trans = nullptr, *d_trPartOff = nullptr,
-            *d_trPartRows = nullptr, *d_genericTiles = nullptr, *d_tileJOff = nullptr;
+            *d_trPartRows = nullptr, *d_genericTiles = nullptr, *d_tileJOff = nullptr, *d_phiTileV = nullptr,
+            *d_phiTileDir = nullptr, *d_phiTileF = nullptr;
+    PhiLine *d_phiLines = nullptr;
+    double *d_wavelength = nullptr, *d_muz = nullptr, *d_wmu = nullptr;
+    int nPhiLines = 0;
+    bool haveLambda0 = false;
     CopyJob *d_cjobs = nullptr;
     PackChunk *d_pchunks = nullptr;
     PackTile *d_ptiles = nullptr;
@@ -294,15 +299,15 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
     L.hp_bg_sca = htake((int64_t)d->Nspect * N);
     L.hp_C = htake((int64_t)m->sumNlevel2 * N);
     L.hp_nTotal = htake((int64_t)d->Natom * N);
-    L.hp_phi = h;
     std::vector<int64_t> hpPhi(d->Ntrans, 0), hpGij(d->Ntrans, 0);
-    for (int t = 0; t < d->Ntrans; ++t)
-        if (m->trans[(size_t)t * 6 + 3]) hpPhi[t] = htake((int64_t)m->trans[(size_t)t * 6 + 5] * d->Nrays * 2 * N);
-    L.hp_wphi = htake((int64_t)d->Ntrans * N);
     L.hp_gijcont = h;
     for (int t = 0; t < d->Ntrans; ++t)
         if (!m->trans[(size_t)t * 6 + 3]) hpGij[t] = htake((int64_t)m->trans[(size_t)t * 6 + 5] * N);
     L.hp_n = htake((int64_t)m->sumNlevel * N);
+    L.hp_phi = h;     // the profiles come last: a caller using mali_compute_phi uploads only [0, hp_phi)
+    for (int t = 0; t < d->Ntrans; ++t)
+        if (m->trans[(size_t)t * 6 + 3]) hpPhi[t] = htake((int64_t)m->trans[(size_t)t * 6 + 5] * d->Nrays * 2 * N);
+    L.hp_wphi = htake((int64_t)d->Ntrans * N);
     L.hostpack = h;
 
     // ---- per-transition descriptors
@@ -329,6 +334,8 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
     std::vector<std::vector<int32_t>> trRows(d->Ntrans);
     std::vector<PackTile> ptiles;
     std::vector<int32_t> tileJOff;   // per tile: offset of the J-dagger field inside a depth row
+    std::vector<std::vector<int32_t>> phiV(d->Ntrans), phiDir(d->Ntrans), phiF(d->Ntrans);
+    std::vector<int32_t> phiTile0(d->Ntrans, -1);
     std::vector<PackSlot> pslots;
     std::vector<PackChunk> pchunks;
     int partRow = 0;
@@ -390,6 +397,12 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
             ps.wphiOff = L.hp_wphi + (int64_t)s.t * N;
             ps.c0 = s.c0;
             pslots.push_back(ps);
+            if (s.isLine) {   // where compute_phi_kernel finds this line's entries of this tile
+                phiV[s.t].push_back((int32_t)rowOff + s.vOff);
+                phiDir[s.t].push_back(sb / 2);
+                phiF[s.t].push_back((int32_t)rowOff + s.fOff);
+                if (phiTile0[s.t] < 0) phiTile0[s.t] = ti;
+            }
         }
         for (int e0 = 0; e0 < pt.recSize; e0 += 32) pchunks.push_back(PackChunk{ti, e0});
         ptiles.push_back(pt);
@@ -563,6 +576,39 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
     up(to_device(trPartOff, &m->d_trPartOff));
     up(to_device(trPartRows, &m->d_trPartRows));
     up(to_device(tileJOff, &m->d_tileJOff));
+    {   // tables of the device compute_phi
+        std::vector<PhiLine> lines;
+        std::vector<int32_t> tv, td2, tf;
+        for (int t = 0; t < d->Ntrans; ++t) {
+            const int32_t *tr = &m->trans[(size_t)t * 6];
+            if (!tr[3]) continue;
+            PhiLine ln{};
+            ln.t = t;
+            ln.atom = tr[0];
+            ln.Nblue = tr[4];
+            ln.Nlam = tr[5];
+            ln.toff = m->toff[t];
+            ln.tile0 = phiTile0[t];
+            ln.tab0 = (int32_t)tv.size();
+            ln.lambda0 = d->lambda0 ? d->lambda0[t] : 0.0;
+            ln.c0 = d->lineconst[3 * t + 0];
+            lines.push_back(ln);
+            tv.insert(tv.end(), phiV[t].begin(), phiV[t].end());
+            td2.insert(td2.end(), phiDir[t].begin(), phiDir[t].end());
+            tf.insert(tf.end(), phiF[t].begin(), phiF[t].end());
+        }
+        m->nPhiLines = (int)lines.size();
+        m->haveLambda0 = d->lambda0 != nullptr;
+        up(to_device(lines, &m->d_phiLines));
+        up(to_device(tv, &m->d_phiTileV));
+        up(to_device(td2, &m->d_phiTileDir));
+        up(to_device(tf, &m->d_phiTileF));
+        std::vector<double> wl(d->wavelength, d->wavelength + d->Nspect), mz(d->muz, d->muz + d->Nrays),
+            wm(d->wmu, d->wmu + d->Nrays);
+        up(to_device(wl, &m->d_wavelength));
+        up(to_device(mz, &m->d_muz));
+        up(to_device(wm, &m->d_wmu));
+    }
     up(to_device(m->genericTiles, &m->d_genericTiles));
     up(to_device(m->cjobs, &m->d_cjobs));
     up(to_device(pchunks, &m->d_pchunks));
@@ -593,7 +639,8 @@ void mali_model_destroy(mali_model *m)
     cudaSetDevice(m->device);
     void *ptrs[] = {m->d_tiles, m->d_slots, m->d_alpha, m->d_twohc, m->d_wlacont, m->d_wlambda, m->d_zmu, m->d_hw,
                     m->d_Nlevel, m->d_lvlOff, m->d_g2Off, m->d_trans, m->d_trPartOff, m->d_trPartRows,
-                    m->d_genericTiles, m->d_cjobs, m->d_pchunks, m->d_ptiles, m->d_pslots, m->d_tileJOff};
+                    m->d_genericTiles, m->d_cjobs, m->d_pchunks, m->d_ptiles, m->d_pslots, m->d_tileJOff, m->d_phiTileV,
+                    m->d_phiTileDir, m->d_phiTileF, m->d_phiLines, m->d_wavelength, m->d_muz, m->d_wmu};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (cudaEvent_t e : m->profEvents) cudaEventDestroy(e);
@@ -633,20 +680,26 @@ static int check_range(const mali_model *m, const mali_buffers *b, int col0, int
     return MALI_OK;
 }
 
-int mali_upload_columns(const mali_model *m, const mali_buffers *b, int32_t col0, int32_t ncol, const double *host_pack,
-                        double *staging_dev, void *stream)
+static int upload_columns(const mali_model *m, const mali_buffers *b, int32_t col0, int32_t ncol, const double *host_pack,
+                          double *staging_dev, void *stream, bool nophi)
 {
     if (int r = check_range(m, b, col0, ncol, "mali_upload_columns")) return r;
     if (!staging_dev || !b->colconst || !b->pops || !b->J) return fail(MALI_EINVAL, "mali_upload_columns: null buffer");
     cudaStream_t st = (cudaStream_t)stream;
     const mali_layout &L = m->lay;
-    if (host_pack)
-        CU(cudaMemcpyAsync(staging_dev, host_pack, (size_t)ncol * L.hostpack * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (host_pack) {
+        if (!nophi)
+            CU(cudaMemcpyAsync(staging_dev, host_pack, (size_t)ncol * L.hostpack * sizeof(double), cudaMemcpyHostToDevice, st));
+        else   // only the blocks' prefix without the line profiles crosses the bus
+            CU(cudaMemcpy2DAsync(staging_dev, (size_t)L.hostpack * sizeof(double), host_pack, (size_t)L.hp_phi * sizeof(double),
+                                 (size_t)L.hp_phi * sizeof(double), (size_t)ncol, cudaMemcpyHostToDevice, st));
+    }
     if (m->packChunks > 0) {
         dim3 grid(m->packChunks, (m->N + 31) / 32, ncol), block(32, 8);
         pack_tiles_kernel<<<grid, block, 0, st>>>(m->d_pchunks, m->d_ptiles, m->d_pslots, m->d_wlambda, m->N, m->Nrays,
                                                   m->Nspect, m->Lw, staging_dev, L.hostpack, L.hp_bg_chi, L.hp_bg_eta,
-                                                  L.hp_bg_sca, b->colconst, L.colconst, m->off_tab, m->rowStride, col0);
+                                                  L.hp_bg_sca, b->colconst, L.colconst, m->off_tab, m->rowStride, col0,
+                                                  nophi ? 1 : 0);
     }
     {
         dim3 grid(32, ncol);
@@ -654,6 +707,35 @@ int mali_upload_columns(const mali_model *m, const mali_buffers *b, int32_t col0
                                                L.colconst, b->pops, L.pops, b->J, L.J, col0);
     }
     m->launches += 2;
+    CU(cudaGetLastError());
+    return MALI_OK;
+}
+
+int mali_upload_columns(const mali_model *m, const mali_buffers *b, int32_t col0, int32_t ncol, const double *host_pack,
+                        double *staging_dev, void *stream)
+{
+    return upload_columns(m, b, col0, ncol, host_pack, staging_dev, stream, false);
+}
+
+int mali_upload_columns_nophi(const mali_model *m, const mali_buffers *b, int32_t col0, int32_t ncol,
+                              const double *host_pack_prefix, double *staging_dev, void *stream)
+{
+    return upload_columns(m, b, col0, ncol, host_pack_prefix, staging_dev, stream, true);
+}
+
+int mali_compute_phi(const mali_model *m, const mali_buffers *b, int32_t col0, int32_t ncol, const double *aDamp,
+                     const double *vBroad, const double *vlos, void *stream)
+{
+    if (int r = check_range(m, b, col0, ncol, "mali_compute_phi")) return r;
+    if (!aDamp || !vBroad || !vlos || !b->colconst) return fail(MALI_EINVAL, "mali_compute_phi: null buffer");
+    if (!m->haveLambda0) return fail(MALI_EINVAL, "mali_compute_phi: the model was created without lambda0");
+    if (m->nPhiLines == 0) return MALI_OK;
+    dim3 grid((m->N + 63) / 64, m->nPhiLines, ncol);
+    compute_phi_kernel<<<grid, 64, 0, (cudaStream_t)stream>>>(
+        m->d_phiLines, m->d_phiTileV, m->d_phiTileDir, m->d_phiTileF, m->d_wavelength, m->d_wlambda, m->d_muz, m->d_wmu,
+        m->N, m->Nrays, m->Lw, m->Ntrans, m->Natom, aDamp, vBroad, vlos, b->colconst, m->lay.colconst, m->off_tab,
+        m->rowStride, col0);
+    m->launches += 1;
     CU(cudaGetLastError());
     return MALI_OK;
 }

@@ -12,6 +12,7 @@
 #include <cstdint>
 
 #include "mali_solve.h"
+#include "mali_voigt.h"
 #include "mali_types.cuh"
 
 namespace mali {
@@ -671,7 +672,7 @@ struct PackChunk {
 __global__ void pack_tiles_kernel(const PackChunk *chunks, const PackTile *tiles, const PackSlot *slots,
                                   const double *wlambda, int N, int Nrays, int Nspect, int Lw, const double *staging,
                                   int64_t hpStride, int64_t hpBgChi, int64_t hpBgEta, int64_t hpBgSca, double *colconst,
-                                  int64_t colStride, int64_t offTab, int64_t rowStride, int col0)
+                                  int64_t colStride, int64_t offTab, int64_t rowStride, int col0, int skipPhi)
 {
     __shared__ double tile[32][33];
     const PackChunk ch = chunks[blockIdx.x];
@@ -691,7 +692,7 @@ __global__ void pack_tiles_kernel(const PackChunk *chunks, const PackTile *tiles
                 int sq = -1;
                 for (int u = 0; u < pt.nslot; ++u)
                     if (slots[pt.slot0 + u].isLine && slots[pt.slot0 + u].lineIdx == j) sq = u;
-                if (sq >= 0 && ls < Lw) {
+                if (sq >= 0 && ls < Lw && !skipPhi) {   // skipPhi: compute_phi_kernel fills the line entries
                     const PackSlot ps = slots[pt.slot0 + sq];
                     const int la = pt.la0 + ls, lt = la - ps.Nblue;
                     if (la < Nspect && lt >= 0 && lt < ps.Nlam)
@@ -712,9 +713,9 @@ __global__ void pack_tiles_kernel(const PackChunk *chunks, const PackTile *tiles
                     const PackSlot ps = slots[pt.slot0 + f - 3];
                     const int lt = la - ps.Nblue;
                     if (la < Nspect && lt >= 0 && lt < ps.Nlam) {
-                        if (ps.isLine)  // wla = wlambda(lt) * wphi[k] / HC   (rh_method.py:451)
-                            v = wlambda[ps.toff + lt] * src[ps.wphiOff + k] / kHC;
-                        else
+                        if (ps.isLine) {  // wla = wlambda(lt) * wphi[k] / HC   (rh_method.py:451)
+                            if (!skipPhi) v = wlambda[ps.toff + lt] * src[ps.wphiOff + k] / kHC;
+                        } else
                             v = src[ps.srcOff + (size_t)lt * N + k];
                     }
                 }
@@ -726,6 +727,57 @@ __global__ void pack_tiles_kernel(const PackChunk *chunks, const PackTile *tiles
     for (int q = ty; q < 32; q += 8) {
         const int kk = blockIdx.y * 32 + q, e = ch.e0 + tx;
         if (kk < N && e < pt.recSize) dst[(size_t)kk * rowStride + e] = tile[tx][q];
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------
+// ComputationalTransition.compute_phi (rh_method.py:198-243) on the device: one thread per (column, line, depth)
+// walks the line's wavelengths, angles and directions in the reference's loop order, evaluates the Voigt profile
+// (mali_voigt.h), accumulates the normalisation wPhi (:233) and writes hc/4pi*Bij*phi into the Vij rows of the tile
+// records; afterwards it writes the wavelength-weight fields wlambda*wphi/HC (:451) of its depth row.
+struct PhiLine {
+    int32_t t, atom, Nblue, Nlam, toff, tile0, tab0, pad;   // tab0: first entry of the per-tile tables below
+    double lambda0, c0;                                      // line centre (nm); hc/4pi*Bij
+};
+__global__ void compute_phi_kernel(const PhiLine *lines, const int32_t *tileV, const int32_t *tileDir,
+                                   const int32_t *tileF, const double *wavelength, const double *wlambda,
+                                   const double *muz, const double *wmu, int N, int Nrays, int Lw, int Ntrans,
+                                   int Natom, const double *aDamp, const double *vBroad, const double *vlos,
+                                   double *colconst, int64_t colStride, int64_t offTab, int64_t rowStride, int col0)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= N) return;
+    const PhiLine ln = lines[blockIdx.y];
+    const int c = blockIdx.z;                      // column inside the call's inputs
+    const double ad = aDamp[((size_t)c * Ntrans + ln.t) * N + k];
+    const double vb = vBroad[((size_t)c * Natom + ln.atom) * N + k];
+    const double vl = vlos[(size_t)c * N + k];
+    double *row = colconst + (size_t)(col0 + c) * colStride + offTab + (size_t)k * rowStride;
+    const double sqrtPi = sqrt(kPi);
+    double wPhi = 0.0;
+    for (int lt = 0; lt < ln.Nlam; ++lt) {
+        const int la = ln.Nblue + lt;
+        const int ti = la / Lw, ls = la - ti * Lw, j = ln.tab0 + (ti - ln.tile0);
+        double *v0 = row + tileV[j] + ls * Nrays;      // direction 0; direction 1 is tileDir[j] further on
+        const int dir = tileDir[j];
+        const double v = (wavelength[la] - ln.lambda0) * kCLight / (vb * ln.lambda0);          // :225
+        const double wl = wlambda[ln.toff + lt] * 0.5;
+        for (int mu = 0; mu < Nrays; ++mu) {
+            const double vd = muz[mu] * vl / vb;                                                // :223
+            const double wlamu = wl * wmu[mu];                                                  // :227
+            for (int d = 0; d < 2; ++d) {
+                const double vk = d ? v + vd : v - vd;                                          // :229-230
+                const double ph = voigt_H(ad, vk) / (sqrtPi * vb);                              // :231
+                wPhi += ph * wlamu;                                                             // :233
+                v0[d * dir + mu] = ln.c0 * ph;
+            }
+        }
+    }
+    const double wphi = 1.0 / wPhi;                                                             // :235
+    for (int lt = 0; lt < ln.Nlam; ++lt) {
+        const int la = ln.Nblue + lt;
+        const int ti = la / Lw, ls = la - ti * Lw, j = ln.tab0 + (ti - ln.tile0);
+        row[tileF[j] + ls] = wlambda[ln.toff + lt] * wphi / kHC;                                // :451
     }
 }
 

@@ -72,6 +72,7 @@ class ModelTables:
         if self.alpha.shape[0] != ntab:
             raise ValueError('alpha must hold sum(Nlambda) = %d entries' % ntab)
         self.lineconst = np.zeros((self.Ntrans, 3))
+        self.lambda0 = np.ascontiguousarray(self.linepar[:, 3])      # line-centre wavelengths (device compute_phi)
         self.wlambda = np.zeros(ntab)
         self.twohc_l3 = np.zeros(ntab)
         self.wlacont = np.zeros(ntab)
@@ -112,7 +113,7 @@ class ModelTables:
         ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
         return _capi.ModelDesc(self.Nspace, self.Nrays, self.Nspect, self.Natom, self.Ntrans, ip(self.Nlevel),
                                ip(self.trans), dp(self.wavelength), dp(self.muz), dp(self.wmu), dp(self.lineconst),
-                               dp(self.wlambda), dp(self.alpha), dp(self.twohc_l3), dp(self.wlacont))
+                               dp(self.wlambda), dp(self.alpha), dp(self.twohc_l3), dp(self.wlacont), dp(self.lambda0))
 
 
 def gij_continuum(mt, nStar, temperature):
@@ -147,16 +148,19 @@ def planck_bc(wavelength, temperature):
     return out
 
 
-def pack_column(mt, lay, p, out=None):
+def pack_column(mt, lay, p, out=None, with_phi=True):
     """Concatenate one column's reference-layout arrays into the host staging block (`mali_layout.hp_*`).
 
     No transposition happens on the host: mali_upload_columns re-lays the data out on the device.
+    with_phi=False: only the first `lay.hp_phi` doubles (everything but the line profiles phi / wphi, which
+    mali_compute_phi then forms on the device).
     """
     N, Nspect = mt.Nspace, mt.Nspect
+    size = lay.hostpack if with_phi else lay.hp_phi
     if out is None:
-        out = np.empty(lay.hostpack)
-    if out.shape[0] != lay.hostpack:
-        raise ValueError('host pack must hold %d doubles' % lay.hostpack)
+        out = np.empty(size)
+    if out.shape[0] != size:
+        raise ValueError('host pack must hold %d doubles' % size)
 
     def put(off, arr, size):
         a = np.asarray(arr, dtype=np.float64)
@@ -171,16 +175,17 @@ def pack_column(mt, lay, p, out=None):
     put(lay.hp_bg_sca, p['bg_sca'], Nspect * N)
     put(lay.hp_C, p['C'], lay.sumNlevel2 * N)
     put(lay.hp_nTotal, p['nTotal'], mt.Natom * N)
-    phi = _f64(p['phi'])
-    o = lay.hp_phi
-    for t in range(mt.Ntrans):
-        atom, i, j, isLine, Nblue, Nlam = (int(v) for v in mt.trans[t])
-        if isLine:
-            sz = Nlam * mt.Nrays * 2 * N
-            po = int(p['phioff'][t])
-            out[o:o + sz] = phi[po:po + sz]
-            o += sz
-    put(lay.hp_wphi, p['wphi'], mt.Ntrans * N)
+    if with_phi:
+        phi = _f64(p['phi'])
+        o = lay.hp_phi
+        for t in range(mt.Ntrans):
+            atom, i, j, isLine, Nblue, Nlam = (int(v) for v in mt.trans[t])
+            if isLine:
+                sz = Nlam * mt.Nrays * 2 * N
+                po = int(p['phioff'][t])
+                out[o:o + sz] = phi[po:po + sz]
+                o += sz
+        put(lay.hp_wphi, p['wphi'], mt.Ntrans * N)
     g = gij_continuum(mt, p['nStar'], p['temperature'])
     put(lay.hp_gijcont, g, g.size)
     if lay.hp_gijcont + g.size != lay.hp_n:

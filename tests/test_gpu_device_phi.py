@@ -1,0 +1,50 @@
+"""Device compute_phi (rh_method.py:198-243 -> mali_compute_phi) against the profiles the
+unmodified reference produced (tests/golden: scipy.special.wofz on the host), and the MALI iteration run on them."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import load_golden, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def eng_mod():
+    assert torch.cuda.is_available(), 'GPU tests need a CUDA device'
+    from lightspinner_b200 import engine
+    return engine
+
+
+@pytest.mark.parametrize('name', ['c1_falc_ca', 'c2_falc_cah', 'c1v_jitter_ca3', 'rf_k40p'])
+def test_device_profiles_match_the_reference_tables(eng_mod, name):
+    """Every entry of the device tables (Vij rows, wavelength-weight fields) built from device profiles vs the same
+    tables built from the reference's phi / wphi: 1e-12 relative (wofz itself is good to ~1e-13)."""
+    p, _ = load_golden(name)
+    a = eng_mod.MaliEngine(p, 1)
+    a.upload([p])
+    ref = a.t_colconst.cpu().numpy().copy()
+    b = eng_mod.MaliEngine(p, 1)
+    b.upload_device_phi([p])
+    got = b.t_colconst.cpu().numpy()
+    off = int(a.lay.colconst) - int(a.mt.Nspace) * int(a.model_info()['row_stride'])   # start of the tile table
+    r, g = ref[off:], got[off:]
+    nz = r != 0
+    assert np.array_equal(g[~nz], r[~nz])                 # inactive / padding entries stay zero
+    assert float(np.max(np.abs(g[nz] - r[nz]) / np.abs(r[nz]))) < 1e-12     # measured: 2.5e-14
+    a.close()
+    b.close()
+
+
+def test_iteration_on_device_profiles_matches_the_reference(eng_mod):
+    """CaII/FALC to convergence on device-computed profiles: same iteration count, I and n within 1e-10."""
+    p, r = load_golden('c1_falc_ca')
+    e = eng_mod.MaliEngine(p, 1)
+    e.upload_device_phi([p])
+    e.reset_iteration_state()
+    e.iterate_async(64)
+    torch.cuda.synchronize()
+    assert int(e.t_iter.cpu()[0]) == int(r['niter'])
+    assert relerr(e.I(0), r['final_I']) < 1e-10
+    assert relerr(e.n(0), r['final_n']) < 1e-10
+    e.close()
