@@ -184,7 +184,9 @@ def main():
     ap.add_argument('--ncol', type=int, default=1024, help='columns per GPU')
     ap.add_argument('--iters', type=int, default=16, help='MALI iterations per solve (= per step)')
     ap.add_argument('--fixture', default='c2_falc_cah')
-    ap.add_argument('--chunk', type=int, default=256, help='columns per upload chunk in the e2e path')
+    ap.add_argument('--chunk', type=int, default=512, help='columns per upload chunk in the e2e path')
+    ap.add_argument('--first-chunk', type=int, default=0,
+                    help='e2e path: size of a smaller first chunk (shortens the exposed first host->device copy)')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     args = ap.parse_args()
@@ -234,6 +236,14 @@ def main():
     lay, mt = eng.lay, eng.mt
     hp = int(lay.hostpack)
     chunk = min(args.chunk, ncol)
+    # e2e schedule: [(first column, count)]; an optional small first chunk, then `chunk`-sized ones
+    sched, c0 = [], 0
+    if 0 < args.first_chunk < chunk and args.first_chunk < ncol:
+        sched.append((0, args.first_chunk))
+        c0 = args.first_chunk
+    while c0 < ncol:
+        sched.append((c0, min(chunk, ncol - c0)))
+        c0 += chunk
     col_global0 = rank * ncol        # this rank's slice of the global batch
 
     # ---- build the resident batch: base host pack -> device, jitter on the device, re-layout
@@ -317,12 +327,18 @@ def main():
         out_d = torch.empty(2 * ncol, dtype=torch.float64, pin_memory=True)
         gathered = torch.empty(world * ncol * lay.I, dtype=torch.float64, device=dev) if world > 1 else None
 
+        chunk_done = [None] * len(sched)    # per chunk: its previous solve + read-back finished (buffers are reused)
+
         def solve_from_host():
-            for ci, c0 in enumerate(range(0, ncol, chunk)):
-                nc = min(chunk, ncol - c0)
-                st = streams[ci & 1]
-                with torch.cuda.stream(st):
+            for ci, (c0, nc) in enumerate(sched):
+                with torch.cuda.stream(streams[0]):      # copy stream: H2D + re-layout, runs ahead of the solves
+                    if chunk_done[ci] is not None:
+                        streams[0].wait_event(chunk_done[ci])
                     eng.upload_packed(host_in[c0 * hp:(c0 + nc) * hp], c0, nc, staging=staging[ci & 1])
+                    ready = torch.cuda.Event()
+                    ready.record()
+                with torch.cuda.stream(streams[1]):      # compute stream: the solves, one chunk after the other
+                    streams[1].wait_event(ready)
                     for _ in range(iters):
                         eng.formal_sol_gamma_async(c0, nc)
                         eng.stat_equil_async(c0, nc)
@@ -331,6 +347,8 @@ def main():
                                                                   non_blocking=True)
                     out_d[c0:c0 + nc].copy_(eng.t_dJ[c0:c0 + nc], non_blocking=True)
                     out_d[ncol + c0:ncol + c0 + nc].copy_(eng.t_dPops[c0:c0 + nc], non_blocking=True)
+                    chunk_done[ci] = torch.cuda.Event()
+                    chunk_done[ci].record()
             for st in streams:
                 torch.cuda.current_stream(dev).wait_stream(st)
             if world > 1:     # the path's only exchange: final gather of the emergent intensities
@@ -352,9 +370,82 @@ def main():
                'd2h_bytes_per_step': world * (ncol * (lay.I + lay.pops) + 2 * ncol) * 8, 'steps': k_e2e,
                'ms_per_step': ms_e / k_e2e, 'gpu_launches': launches_e2e,
                'finite': bool(np.isfinite(out_I.numpy()).all() and np.isfinite(out_n.numpy()).all()),
-               'pipeline': '%d-column chunks, 2 streams (H2D of chunk c+1 overlaps the iterations of chunk c)' % chunk}
+               'pipeline': 'column chunks %s; a copy stream (H2D + re-layout) runs ahead of the compute stream' % [n for _, n in sched]}
         if world > 1:
             e2e['gather_bytes_per_step'] = world * ncol * lay.I * 8
+
+    # ---- e2e with the line profiles formed on the device (mali_compute_phi): the host hands over
+    # what ComputationalTransition.compute_phi consumes (damping parameters, Doppler widths, vlos) instead of phi, so
+    # 60 % fewer bytes cross PCIe and the Voigt evaluation happens inside the timed region.  Columns: same jittered
+    # backgrounds / rates; the up/down asymmetry now comes from vlos = 2 km/s * g3 (BASELINE config 4's recipe).
+    e2e_dev = None
+    if want_e2e and all(k in base for k in ('aDamp', 'vBroad')):
+        try:
+            hpp = int(lay.hp_phi)
+            host_pre = torch.empty(ncol * hpp, dtype=torch.float64, pin_memory=True)
+            host_pre.view(ncol, hpp).copy_(host_in.view(ncol, hp)[:, :hpp])
+            nT, nA = mt.Ntrans, mt.Natom
+            aux_np = np.empty((ncol, nT + nA + 1, N))
+            aux_np[:, :nT] = np.asarray(base['aDamp'], dtype=np.float64).reshape(1, nT, N)
+            aux_np[:, nT:nT + nA] = np.asarray(base['vBroad'], dtype=np.float64).reshape(1, nA, N)
+            for c in range(ncol):
+                fv = synth.jitter_factors(col_global0 + c, N)[2]
+                aux_np[c, nT + nA] = 2.0e3 * (fv - 1.0) / 0.02
+            host_aux = torch.from_numpy(aux_np).pin_memory()
+            dev_aux = [torch.empty((chunk, nT + nA + 1, N), dtype=torch.float64, device=dev) for _ in range(2)]
+            dev_split = [(torch.empty((chunk, nT, N), dtype=torch.float64, device=dev),
+                          torch.empty((chunk, nA, N), dtype=torch.float64, device=dev),
+                          torch.empty((chunk, 1, N), dtype=torch.float64, device=dev)) for _ in range(2)]
+
+            def solve_from_host_device_phi():
+                for ci, (c0, nc) in enumerate(sched):
+                    with torch.cuda.stream(streams[0]):
+                        if chunk_done[ci] is not None:
+                            streams[0].wait_event(chunk_done[ci])
+                        dev_aux[ci & 1][:nc].copy_(host_aux[c0:c0 + nc], non_blocking=True)
+                        aD, vB, vL = dev_split[ci & 1]
+                        aD[:nc].copy_(dev_aux[ci & 1][:nc, :nT])
+                        vB[:nc].copy_(dev_aux[ci & 1][:nc, nT:nT + nA])
+                        vL[:nc].copy_(dev_aux[ci & 1][:nc, nT + nA:])
+                        eng.upload_packed_device_phi(host_pre[c0 * hpp:(c0 + nc) * hpp], aD, vB, vL, c0, nc,
+                                                     staging=staging[ci & 1])
+                        ready = torch.cuda.Event()
+                        ready.record()
+                    with torch.cuda.stream(streams[1]):
+                        streams[1].wait_event(ready)
+                        for _ in range(iters):
+                            eng.formal_sol_gamma_async(c0, nc)
+                            eng.stat_equil_async(c0, nc)
+                        out_I[c0 * lay.I:(c0 + nc) * lay.I].copy_(eng.t_I[c0 * lay.I:(c0 + nc) * lay.I], non_blocking=True)
+                        out_n[c0 * lay.pops:(c0 + nc) * lay.pops].copy_(eng.t_pops[c0 * lay.pops:(c0 + nc) * lay.pops],
+                                                                      non_blocking=True)
+                        out_d[c0:c0 + nc].copy_(eng.t_dJ[c0:c0 + nc], non_blocking=True)
+                        out_d[ncol + c0:ncol + c0 + nc].copy_(eng.t_dPops[c0:c0 + nc], non_blocking=True)
+                        chunk_done[ci] = torch.cuda.Event()
+                        chunk_done[ci].record()
+                for st in streams:
+                    torch.cuda.current_stream(dev).wait_stream(st)
+                if world > 1:
+                    dist.all_gather_into_tensor(gathered, eng.t_I)
+
+            solve_from_host_device_phi()
+            barrier()
+            l0 = eng.launch_count()
+            e0.record()
+            for _ in range(k_e2e):
+                solve_from_host_device_phi()
+            e1.record()
+            barrier()
+            ms_d = max_over_ranks(e0.elapsed_time(e1))
+            e2e_dev = {'value': e_units / (ms_d * 1e-3), 'unit': UNIT,
+                       'h2d_bytes_per_step': world * ncol * (hpp + (nT + nA + 1) * N) * 8,
+                       'd2h_bytes_per_step': e2e['d2h_bytes_per_step'], 'steps': k_e2e, 'ms_per_step': ms_d / k_e2e,
+                       'gpu_launches': eng.launch_count() - l0,
+                       'finite': bool(np.isfinite(out_I.numpy()).all() and np.isfinite(out_n.numpy()).all()),
+                       'pipeline': e2e['pipeline'] + '; line profiles computed on the device (mali_compute_phi) '
+                                   'from aDamp / vBroad / vlos'}
+        except Exception as ex:
+            e2e_dev = {'error': repr(ex)}
 
     # ---- CPU baseline on the host cores (rank 0, N = 1)
     cpu = None
@@ -494,7 +585,7 @@ def main():
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
                 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': cfg, 'clocks': clocks,
-                'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu,
+                'e2e': e2e, 'e2e_device_phi': e2e_dev, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu,
                 'single_column': single, 'to_convergence': conv, 'response_function': rf, 'results_finite': finite}
         print(json.dumps(line))
     if world > 1:

@@ -590,6 +590,7 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
             ln.toff = m->toff[t];
             ln.tile0 = phiTile0[t];
             ln.tab0 = (int32_t)tv.size();
+            ln.ntile = (int32_t)phiV[t].size();
             ln.lambda0 = d->lambda0 ? d->lambda0[t] : 0.0;
             ln.c0 = d->lineconst[3 * t + 0];
             lines.push_back(ln);
@@ -730,10 +731,10 @@ int mali_compute_phi(const mali_model *m, const mali_buffers *b, int32_t col0, i
     if (!aDamp || !vBroad || !vlos || !b->colconst) return fail(MALI_EINVAL, "mali_compute_phi: null buffer");
     if (!m->haveLambda0) return fail(MALI_EINVAL, "mali_compute_phi: the model was created without lambda0");
     if (m->nPhiLines == 0) return MALI_OK;
-    dim3 grid((m->N + 63) / 64, m->nPhiLines, ncol);
-    compute_phi_kernel<<<grid, 64, 0, (cudaStream_t)stream>>>(
+    dim3 grid((m->N + 3) / 4, m->nPhiLines, ncol);     // 4 warps per block, one depth point each
+    compute_phi_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(
         m->d_phiLines, m->d_phiTileV, m->d_phiTileDir, m->d_phiTileF, m->d_wavelength, m->d_wlambda, m->d_muz, m->d_wmu,
-        m->N, m->Nrays, m->Lw, m->Ntrans, m->Natom, aDamp, vBroad, vlos, b->colconst, m->lay.colconst, m->off_tab,
+        m->N, m->Nrays, m->Nspect, m->Lw, m->Ntrans, m->Natom, aDamp, vBroad, vlos, b->colconst, m->lay.colconst, m->off_tab,
         m->rowStride, col0);
     m->launches += 1;
     CU(cudaGetLastError());
@@ -913,7 +914,8 @@ static int launch_fs(const mali_model *m, const mali_buffers *b, int col0, int n
         // fork: class 2 (heaviest warps) stays on the caller's stream, classes 1 and 0 go to the side streams
         // -- only for small launches (a few waves of warps: single columns, response-function batches), where the
         // serial tails are a large share; big batches fill the machine anyway and keep to one stream
-        const bool small = (int64_t)ncol * m->specTiles <= 16384;
+        static const int64_t forkMax = getenv("MALI_FORK_MAX") ? atoll(getenv("MALI_FORK_MAX")) : 16384;
+        const bool small = (int64_t)ncol * m->specTiles <= forkMax;
         const bool side1 = small && m->sideStream[0] && !m->spec1.empty() && (!m->spec2.empty());
         const bool side0 = small && m->sideStream[1] && !m->spec0.empty() && (!m->spec2.empty() || !m->spec1.empty());
         if (side1 || side0) CU(cudaEventRecord(m->forkEvent, st));

@@ -731,21 +731,24 @@ __global__ void pack_tiles_kernel(const PackChunk *chunks, const PackTile *tiles
 }
 
 // --------------------------------------------------------------------------------------------------------
-// ComputationalTransition.compute_phi (rh_method.py:198-243) on the device: one thread per (column, line, depth)
-// walks the line's wavelengths, angles and directions in the reference's loop order, evaluates the Voigt profile
-// (mali_voigt.h), accumulates the normalisation wPhi (:233) and writes hc/4pi*Bij*phi into the Vij rows of the tile
-// records; afterwards it writes the wavelength-weight fields wlambda*wphi/HC (:451) of its depth row.
+// ComputationalTransition.compute_phi (rh_method.py:198-243) on the device.  One warp per (column, line, depth);
+// the lanes are the (wavelength, angle) pairs of one tile in the record's own lane order, so each tile's two Vij
+// rows (down / up direction) are written as whole 256-byte rows.  The warp walks the tiles the line spans,
+// evaluates the Voigt profile (mali_voigt.h) for both directions, accumulates the normalisation wPhi (:233; a fixed
+// shuffle tree instead of the reference's sequential sum) and finally writes the wavelength-weight fields
+// wlambda*wphi/HC (:451) of its depth row.
 struct PhiLine {
-    int32_t t, atom, Nblue, Nlam, toff, tile0, tab0, pad;   // tab0: first entry of the per-tile tables below
+    int32_t t, atom, Nblue, Nlam, toff, tile0, tab0, ntile;  // tab0: first entry of the per-tile tables below
     double lambda0, c0;                                      // line centre (nm); hc/4pi*Bij
 };
 __global__ void compute_phi_kernel(const PhiLine *lines, const int32_t *tileV, const int32_t *tileDir,
                                    const int32_t *tileF, const double *wavelength, const double *wlambda,
-                                   const double *muz, const double *wmu, int N, int Nrays, int Lw, int Ntrans,
+                                   const double *muz, const double *wmu, int N, int Nrays, int Nspect, int Lw, int Ntrans,
                                    int Natom, const double *aDamp, const double *vBroad, const double *vlos,
                                    double *colconst, int64_t colStride, int64_t offTab, int64_t rowStride, int col0)
 {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (k >= N) return;
     const PhiLine ln = lines[blockIdx.y];
     const int c = blockIdx.z;                      // column inside the call's inputs
@@ -753,31 +756,36 @@ __global__ void compute_phi_kernel(const PhiLine *lines, const int32_t *tileV, c
     const double vb = vBroad[((size_t)c * Natom + ln.atom) * N + k];
     const double vl = vlos[(size_t)c * N + k];
     double *row = colconst + (size_t)(col0 + c) * colStride + offTab + (size_t)k * rowStride;
+    const int ls = lane / Nrays, mu = lane - ls * Nrays;
+    const bool lane_on = ls < Lw;
     const double sqrtPi = sqrt(kPi);
+    const double rnorm = 1.0 / (sqrtPi * vb);
+    const double vd = lane_on ? muz[mu] * vl / vb : 0.0;                                        // :223
+    const double wm = lane_on ? wmu[mu] : 0.0;
     double wPhi = 0.0;
-    for (int lt = 0; lt < ln.Nlam; ++lt) {
-        const int la = ln.Nblue + lt;
-        const int ti = la / Lw, ls = la - ti * Lw, j = ln.tab0 + (ti - ln.tile0);
-        double *v0 = row + tileV[j] + ls * Nrays;      // direction 0; direction 1 is tileDir[j] further on
-        const int dir = tileDir[j];
-        const double v = (wavelength[la] - ln.lambda0) * kCLight / (vb * ln.lambda0);          // :225
-        const double wl = wlambda[ln.toff + lt] * 0.5;
-        for (int mu = 0; mu < Nrays; ++mu) {
-            const double vd = muz[mu] * vl / vb;                                                // :223
-            const double wlamu = wl * wmu[mu];                                                  // :227
-            for (int d = 0; d < 2; ++d) {
-                const double vk = d ? v + vd : v - vd;                                          // :229-230
-                const double ph = voigt_H(ad, vk) / (sqrtPi * vb);                              // :231
-                wPhi += ph * wlamu;                                                             // :233
-                v0[d * dir + mu] = ln.c0 * ph;
-            }
+    for (int j = 0; j < ln.ntile; ++j) {
+        const int la = (ln.tile0 + j) * Lw + ls, lt = la - ln.Nblue;
+        const bool on = lane_on && lt >= 0 && lt < ln.Nlam && la < Nspect;
+        double p0 = 0.0, p1 = 0.0;
+        if (on) {
+            const double v = (wavelength[la] - ln.lambda0) * kCLight / (vb * ln.lambda0);      // :225
+            p0 = voigt_H(ad, v - vd) * rnorm;                                                   // :229-231
+            p1 = voigt_H(ad, v + vd) * rnorm;
+            wPhi += (p0 + p1) * ((wlambda[ln.toff + lt] * 0.5) * wm);                           // :227, :233
         }
+        double *v0 = row + tileV[ln.tab0 + j];
+        v0[lane] = ln.c0 * p0;                         // whole rows, zero where the line is not active
+        v0[tileDir[ln.tab0 + j] + lane] = ln.c0 * p1;
     }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) wPhi += __shfl_xor_sync(0xffffffffu, wPhi, off);
     const double wphi = 1.0 / wPhi;                                                             // :235
-    for (int lt = 0; lt < ln.Nlam; ++lt) {
-        const int la = ln.Nblue + lt;
-        const int ti = la / Lw, ls = la - ti * Lw, j = ln.tab0 + (ti - ln.tile0);
-        row[tileF[j] + ls] = wlambda[ln.toff + lt] * wphi / kHC;                                // :451
+    for (int j = 0; j < ln.ntile; ++j) {
+        if (lane < Lw) {
+            const int la = (ln.tile0 + j) * Lw + lane, lt = la - ln.Nblue;
+            const bool on = lt >= 0 && lt < ln.Nlam && la < Nspect;
+            row[tileF[ln.tab0 + j] + lane] = on ? wlambda[ln.toff + lt] * wphi / kHC : 0.0;     // :451
+        }
     }
 }
 

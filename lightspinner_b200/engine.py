@@ -127,6 +127,21 @@ class MaliEngine:
                                                       *(C.c_void_p(t.data_ptr()) for t in dev), self._stream()))
             torch.cuda.current_stream(self.device).synchronize()
 
+    def upload_packed_device_phi(self, host_prefix_pinned, aDamp, vBroad, vlos, col0, ncol, staging=None):
+        """Asynchronous form of upload_device_phi: `host_prefix_pinned` holds [ncol][lay.hp_phi] doubles (pinned),
+        aDamp / vBroad / vlos are device tensors [ncol][Ntrans|Natom|1][Nspace]."""
+        if staging is None:
+            staging, _ = self._staging_bufs()
+        if ncol * self.lay.hostpack > staging.numel():
+            raise ValueError('staging buffer too small for %d columns' % ncol)
+        with torch.cuda.device(self.device):
+            _capi.check(self.lib.mali_upload_columns_nophi(self._handle, C.byref(self.bufs), col0, ncol,
+                                                           C.c_void_p(host_prefix_pinned.data_ptr()),
+                                                           C.c_void_p(staging.data_ptr()), self._stream()))
+            _capi.check(self.lib.mali_compute_phi(self._handle, C.byref(self.bufs), col0, ncol,
+                                                  C.c_void_p(aDamp.data_ptr()), C.c_void_p(vBroad.data_ptr()),
+                                                  C.c_void_p(vlos.data_ptr()), self._stream()))
+
     def upload_packed(self, host_pinned, col0, ncol, staging=None):
         """H2D copy of `ncol` host-pack blocks (a pinned torch tensor) + device re-layout; asynchronous."""
         if staging is None:
