@@ -62,7 +62,16 @@ class ComputationalTransition:
         self.i = trans.i
         self.j = trans.j
         self.Nblue = int(np.searchsorted(spect.wavelength, self.wavelength[0]))     # rh_method.py:122
-        self.compute_phi(atmos)
+        self._phi = None
+        self._wphi = None
+        self._atmos = atmos
+        self.aDamp = None
+        if getattr(compAtom.ctx, 'device_phi', False):
+            # the profiles are formed on the device (mali_compute_phi); the host only evaluates the damping parameter
+            if self.isLine:
+                self.aDamp = trans.damping(atmos, compAtom.vBroad, compAtom.hPops.n[0])[0]
+        else:
+            self.compute_phi(atmos)
         self.active = np.zeros(spect.wavelength.shape[0], bool)
         for i, s in enumerate(spect.activeSet):                                     # rh_method.py:125-127
             if trans in s:
@@ -112,8 +121,23 @@ class ComputationalTransition:
                     vk = v + sign * vlosDop[mu]
                     phi[la, mu, toFrom, :] = voigt_H(aDamp, vk) / (sqrtPi * self.atom.vBroad)
                     wPhi[:] += phi[la, mu, toFrom, :] * wlamu[la]
-        self.wphi = 1.0 / wPhi
-        self.phi = phi
+        self.aDamp = aDamp
+        self._wphi = 1.0 / wPhi
+        self._phi = phi
+
+    @property
+    def phi(self):
+        """[Nlambda, Nrays, 2, Nspace] (rh_method.py:224); evaluated on first use when the Context forms its
+        profiles on the device."""
+        if self.isLine and self._phi is None:
+            self.compute_phi(self._atmos)
+        return self._phi
+
+    @property
+    def wphi(self):
+        if self.isLine and self._wphi is None:
+            self.compute_phi(self._atmos)
+        return self._wphi
 
     def uv(self, la, mu, toFrom):
         """rh_method.py:245-288, evaluated by the GPU from the packed tables (mali_uv)."""
@@ -172,7 +196,12 @@ class Context:
     which run the same kernels over many columns per launch.
     """
 
-    def __init__(self, atmos, spect, eqPops, background, device=None, _host_only=False):
+    def __init__(self, atmos, spect, eqPops, background, device=None, _host_only=False, device_phi=False):
+        """device_phi=True: the Voigt line profiles (ComputationalTransition.compute_phi, rh_method.py:198-243) are
+        formed on the GPU from the damping parameters instead of by the host loops -- same results to ~1e-13 (the
+        accuracy of the reference's scipy wofz) and most of the constructor's time saved; `trans.phi` / `trans.wphi`
+        are then evaluated on the host only if somebody reads them."""
+        self.device_phi = bool(device_phi)
         self.atmos = atmos
         self.atmos.nondimensionalise()                                    # rh_method.py:553
         self.spect = spect
@@ -187,7 +216,10 @@ class Context:
         if _host_only:      # unit tests of the host-side flattening only; every compute method then fails
             return
         self._engine = MaliEngine(self._problem, 1, device=device)
-        self._engine.upload([self._problem])
+        if self.device_phi:
+            self._engine.upload_device_phi([self._problem])
+        else:
+            self._engine.upload([self._problem])
 
     # -- lazily fetched results (numpy, C order, the reference's shapes)
     def _get(self, key, fn):
@@ -236,9 +268,12 @@ def flatten_context(ctx):
     N = atmos.Nspace
     Nlevel, trans, linepar, alpha, phi, phioff, wphi = [], [], [], [], [], [], []
     nStar, nTotal, Cs, ns = [], [], [], []
+    aDamp, vBroad = [], []
+    dev_phi = bool(getattr(ctx, 'device_phi', False))
     off = 0
     it = 0
     for ia, atom in enumerate(ctx.activeAtoms):
+        vBroad.append(np.asarray(atom.vBroad, dtype=np.float64))
         atom.index = ia
         atom.compute_collisions()
         Nlevel.append(atom.Nlevel)
@@ -261,14 +296,19 @@ def flatten_context(ctx):
                 linepar.append([t.Aji, t.Bji, t.Bij, t.lambda0])
                 alpha.append(np.zeros(Nlam))
                 phioff.append(off)
-                phi.append(np.ascontiguousarray(t.phi).ravel())
-                off += t.phi.size
-                wphi.append(np.asarray(t.wphi, dtype=np.float64))
+                if not dev_phi:
+                    phi.append(np.ascontiguousarray(t.phi).ravel())
+                    off += t.phi.size
+                    wphi.append(np.asarray(t.wphi, dtype=np.float64))
+                else:
+                    wphi.append(np.zeros(N))
+                aDamp.append(np.asarray(t.aDamp, dtype=np.float64))
             else:
                 linepar.append([0.0, 0.0, 0.0, 0.0])
                 alpha.append(np.asarray(t.alpha, dtype=np.float64))
                 phioff.append(0)
                 wphi.append(np.zeros(N))
+                aDamp.append(np.zeros(N))
     return dict(
         Nspace=N, Nrays=atmos.Nrays, Nspect=int(spect.wavelength.shape[0]),
         wavelength=np.asarray(spect.wavelength, dtype=np.float64), muz=np.asarray(atmos.muz, dtype=np.float64),
@@ -279,7 +319,9 @@ def flatten_context(ctx):
         bg_chi=np.asarray(bg.chi), bg_eta=np.asarray(bg.eta), bg_sca=np.asarray(bg.sca),
         nStar=np.concatenate(nStar, axis=0), nTotal=np.stack(nTotal), C=np.concatenate(Cs, axis=0),
         n=np.concatenate(ns, axis=0), phi=np.concatenate(phi) if phi else np.zeros(0),
-        phioff=np.array(phioff, dtype=np.int64), wphi=np.stack(wphi) if wphi else np.zeros((0, N)))
+        phioff=np.array(phioff, dtype=np.int64), wphi=np.stack(wphi) if wphi else np.zeros((0, N)),
+        aDamp=np.stack(aDamp) if aDamp else np.zeros((0, N)), vBroad=np.stack(vBroad),
+        vlos=np.asarray(atmos.vlos, dtype=np.float64))
 
 
 @dataclass

@@ -48,3 +48,26 @@ def test_iteration_on_device_profiles_matches_the_reference(eng_mod):
     assert relerr(e.I(0), r['final_I']) < 1e-10
     assert relerr(e.n(0), r['final_n']) < 1e-10
     e.close()
+
+
+def test_dropin_context_with_device_profiles(eng_mod):
+    """Context(..., device_phi=True): the constructor skips the host Voigt loops; the test.py loop converges in the
+    reference's 46 iterations to the same I, J, n; trans.phi is still readable (evaluated on first use)."""
+    from helpers import fake_reference_objects
+    from lightspinner_b200 import Context
+    p, r = load_golden('c1_falc_ca')
+    atmos, spect, eqPops, bg = fake_reference_objects(p)
+    ctx = Context(atmos, spect, eqPops, bg, device_phi=True)
+    assert all(t._phi is None for t in ctx.activeAtoms[0].trans)
+    dJ, dPops, i = 1.0, 1.0, 0
+    while dJ > 2e-3 or dPops > 1e-3:
+        i += 1
+        dJ = ctx.formal_sol_gamma_matrices()
+        if i > 3:
+            dPops = ctx.stat_equil()
+    assert i == int(r['niter'])
+    assert relerr(ctx.I, r['final_I']) < 1e-10 and relerr(ctx.J, r['final_J']) < 1e-10
+    assert relerr(eqPops['CA'].n, r['final_n']) < 1e-10
+    t = ctx.activeAtoms[0].trans[0]
+    assert t.phi.shape == (int(p['trans'][0, 5]), 5, 2, 82)
+    ctx.close()
