@@ -102,17 +102,19 @@ static const SpecEntry kSpecRegistry[] = {
 
 namespace mali {
 // One kernel per register class; the structure id of the tile selects the specialised body (uniform switch).
-// blockIdx.x runs over columns, blockIdx.y over tiles: co-resident blocks share a structure, hence one instruction
-// stream per SM (each specialised body is ~40 KB of SASS).
+// blockIdx.x runs over columns, blockIdx.y over (tile, sweep direction): co-resident blocks share a structure, hence
+// one instruction stream per SM.  The down and the up sweep of a tile are independent warps (their partial sums go
+// to separate scratch copies), which doubles the parallelism of small launches and halves the tail of every wave.
 template <int CLS>
 __global__ void __launch_bounds__(32, spec_class_warps(CLS)) fs_gamma_kernel_m(const __grid_constant__ MegaParams<CLS> P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const TileR<MegaParams<CLS>::NSP> &T = P.tiles[blockIdx.y];
+    const TileR<MegaParams<CLS>::NSP> &T = P.tiles[blockIdx.y >> 1];
+    const int dir = blockIdx.y & 1;
     switch (T.spec) {
 #define MALI_SPEC(ID, KEY, ...)                                                                        \
     case ID:                                                                                           \
-        if constexpr (spec_class(SpecTag##ID::S.nslot) == CLS) fs_body<SpecTag##ID>(P.c, T, smem_raw); \
+        if constexpr (spec_class(SpecTag##ID::S.nslot) == CLS) fs_body<SpecTag##ID>(P.c, T, dir, smem_raw); \
         break;
 #include MALI_SPEC_INC
 #undef MALI_SPEC
@@ -150,7 +152,7 @@ static cudaError_t launch_mega(const FsCommon &c, const std::vector<TileR<spec_c
     for (int t0 = 0; t0 < nt; t0 += MP::kMaxTiles) {
         const int n = std::min(MP::kMaxTiles, nt - t0);
         memcpy(P->tiles, tiles.data() + t0, sizeof(tiles[0]) * n);
-        dim3 grid(ncol, n);
+        dim3 grid(ncol, 2 * n);
         kern<<<grid, 32, smem, st>>>(*P);
         if (launches) *launches += 1;
     }

@@ -12,6 +12,8 @@
 // What stays run-time (warp-uniform, constant bank): where the tile sits (first wavelength, table offsets, Nblue,
 // Nlambda per transition, the lines' Einstein ratios) -- so one instance serves every tile with that structure.
 //
+// Work split: one warp per (column, tile, sweep direction) -- the down and the up sweep of a tile are independent
+// until their partial sums are added by the finish kernels.
 // Data movement: the depth loop contains NO global loads.  A 3-stage TMA ring (cp.async.bulk + mbarrier, issued
 // by one elected lane from warp-uniform registers) streams each depth step's tile record -- this direction's Vij
 // rows, the per-wavelength fields and J-dagger -- into shared memory two steps ahead; the column's heights and the
@@ -181,16 +183,17 @@ __device__ __forceinline__ bool elect_one()
     return pred != 0;
 }
 
-// TMA ring producer step: one elected lane fetches the record of global step fetchG (both sweep directions:
-// 0 .. 2N-1) into the next ring stage -- this direction's Vij rows and the per-wavelength fields -- then the
-// (warp-uniform) bookkeeping advances.  A record: [Vij rows dir 0][Vij rows dir 1][fields]; VBLK / SMALL in doubles.
+// TMA ring producer step: one elected lane fetches the record of sweep step fetchS (0 .. N-1 in sweep order) into
+// the next ring stage -- this direction's Vij rows and the per-wavelength fields -- then the (warp-uniform)
+// bookkeeping advances.  A record: [Vij rows dir 0][Vij rows dir 1][fields]; VBLK / SMALL in doubles; dirOff selects
+// this direction's Vij rows, stepRec = +-rowStride moves to the next depth of the sweep.
 template <int VBLK, int SMALL, int NST>
-__device__ __forceinline__ void ring_fetch(int &fetchG, uint32_t &fetchOff, uint32_t &fetchBar, const double *&fetchRec,
-                                           int N, int64_t rowStride, uint32_t ringAddr, uint32_t barAddr)
+__device__ __forceinline__ void ring_fetch(int &fetchS, uint32_t &fetchOff, uint32_t &fetchBar, const double *&fetchRec,
+                                           int N, int64_t stepRec, int dirOff, uint32_t ringAddr, uint32_t barAddr)
 {
     constexpr int STAGE = VBLK + SMALL;
-    if (fetchG < 2 * N) {
-        const double *srcV = fetchRec + (fetchG >= N ? VBLK : 0);
+    if (fetchS < N) {
+        const double *srcV = fetchRec + dirOff;
         const double *srcS = fetchRec + 2 * VBLK;
         if (elect_one()) {
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fetchBar), "r"((uint32_t)(STAGE * 8))
@@ -205,14 +208,11 @@ __device__ __forceinline__ void ring_fetch(int &fetchG, uint32_t &fetchOff, uint
                          "l"(srcS), "r"((uint32_t)(SMALL * 8)), "r"(fetchBar)
                          : "memory");
         }
-        ++fetchG;
+        ++fetchS;
         const bool wrap = fetchOff == (uint32_t)((NST - 1) * STAGE * 8);
         fetchOff = wrap ? 0u : fetchOff + (uint32_t)(STAGE * 8);
         fetchBar = wrap ? barAddr : fetchBar + 8u;
-        if (fetchG < N)
-            fetchRec += rowStride;
-        else if (fetchG > N)
-            fetchRec -= rowStride;
+        fetchRec += stepRec;
     }
 }
 
@@ -253,7 +253,7 @@ __device__ __forceinline__ void finish_step(int lane, int Nrays, const double *r
 
 // SPEC is a tag type with a `static constexpr TileStruct S` member (the structure travels inside a type).
 template <class SPEC, int NSP>
-__device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, unsigned char *smem_raw)
+__device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, const int d, unsigned char *smem_raw)
 {
     constexpr TileStruct S = SPEC::S;
     constexpr int NS = S.nslot;
@@ -368,12 +368,15 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    const int64_t rowStride = p.rowStride;
-    int fetchG = 0;                     // next global step (both directions: 0 .. 2N-1) to fetch
+    // this warp's sweep: d == 0 downwards from the top (k = 0), d == 1 upwards from the bottom (k = N - 1)
+    const int dk = d ? -1 : 1;
+    const int kS = d ? N - 1 : 0;
+    const int64_t stepRec = d ? -p.rowStride : p.rowStride;
+    int fetchS = 0;                     // next sweep step to fetch
     uint32_t fetchOff = 0;              // byte offset of its stage in the ring
     uint32_t fetchBar = barAddr;        // its barrier
-    const double *fetchRec = tab0;      // its record
-#define fetch_next() ring_fetch<VBLK, SMALL, NST>(fetchG, fetchOff, fetchBar, fetchRec, N, rowStride, ringAddr, barAddr)
+    const double *fetchRec = tab0 + (size_t)kS * p.rowStride;      // its record
+#define fetch_next() ring_fetch<VBLK, SMALL, NST>(fetchS, fetchOff, fetchBar, fetchRec, N, stepRec, d * VBLK, ringAddr, barAddr)
     fetch_next();
     fetch_next();
     uint32_t useOff = 0, useBar = barAddr, phases = 0, useBit = 1;   // stage being consumed; parity bit per stage
@@ -400,9 +403,7 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
     const bool writer = (lane % (32 / M)) == 0 && eOwn < 2 * NS;
     double *gbase = part + (size_t)eOwn * N;
 
-    for (int d = 0; d < 2; ++d) {
-        const int dk = d ? -1 : 1;
-        const int kS = d ? N - 1 : 0;
+    {
         int kl = kS * Nspect + laC;
         const int dkl = dk * Nspect;
 
