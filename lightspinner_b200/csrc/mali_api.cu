@@ -474,7 +474,7 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
         };
         return "{" + std::to_string(Lw) + "," + std::to_string(td.nslot) + "," + std::to_string(d->Natom) + "," +
                std::to_string(td.nlevslot) + "," + arr(kind) + "," + arr(atom) + "," + arr(lvI) + "," + arr(lvJ) + "," +
-               arr(rowI) + "," + arr(rowJ) + "}";
+               arr(rowI) + "," + arr(rowJ) + "," + std::to_string(d->Nrays) + "}";
     };
     auto fill_tile = [&](auto &t, const TileDesc &td, int spec) {
         t.la0 = td.la0;

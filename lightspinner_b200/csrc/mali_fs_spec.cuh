@@ -58,6 +58,7 @@ struct TileStruct {
     int atom[kSpecMaxSlots];
     int lvI[kSpecMaxSlots], lvJ[kSpecMaxSlots];    // level-slot of the lower / upper level
     int rowI[kSpecMaxSlots], rowJ[kSpecMaxSlots];  // row of the level in n[sumNlevel][N]
+    int nrays;                    // angles per wavelength (the mu-sum of J unrolls exactly)
 };
 
 struct SlotR {  // run-time part of a slot, warp-uniform (constant bank), 32 B
@@ -219,24 +220,17 @@ __device__ __forceinline__ void ring_fetch(int &fetchS, uint32_t &fetchOff, uint
 // second half of a depth step's reductions (run during the next step): Gamma partial of the lane's matrix entry
 // and the mu-sum of J, rh_method.py:640.  The down and the up sweep write separate partials (no read-modify-write:
 // the depth loop holds no global loads); gamma_finish_kernel / j_finish_kernel add them.
-template <int M, int NS>
-__device__ __forceinline__ void finish_step(int lane, int Nrays, const double *red, bool writer, bool leader,
-                                            double *gdst, double *jdst, double x)
+template <int M, int NS, int NR>
+__device__ __forceinline__ void finish_step(int lane, const double *red, bool writer, bool leader, double *gdst,
+                                            double *jdst, double x)
 {
     if constexpr (NS > 0) {
         const double tot = reduce_load<M>(lane, red);
         if (writer) __stcg(gdst, tot);
     }
     double sum = x;
-    if (Nrays == 5) {
 #pragma unroll
-        for (int m = 1; m < 5; ++m) sum += __shfl_down_sync(0xffffffffu, x, m);
-    } else if (Nrays == 3) {
-#pragma unroll
-        for (int m = 1; m < 3; ++m) sum += __shfl_down_sync(0xffffffffu, x, m);
-    } else {
-        for (int m = 1; m < Nrays; ++m) sum += __shfl_down_sync(0xffffffffu, x, m);
-    }
+    for (int m = 1; m < NR; ++m) sum += __shfl_down_sync(0xffffffffu, x, m);   // the reference's order over mu
     if (leader) __stcg(jdst, sum);
 }
 
@@ -436,7 +430,7 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
         double xP = 0.0;
         int kP = kS, klP = kl;
         double *gdir = gbase + (d ? p.upOff : 0), *jdir = Jpart + (d ? p.upOff : 0);
-#define finish_prev() finish_step<M, NS>(lane, Nrays, red, writer, leader, gdir + kP, jdir + klP, xP)
+#define finish_prev() finish_step<M, NS, S.nrays>(lane, red, writer, leader, gdir + kP, jdir + klP, xP)
 
         const double *nk = sN + kS;   // populations at the current depth
 #pragma unroll kUnroll

@@ -45,8 +45,8 @@ def tile_structures(p):
             lvI[q], lvJ[q] = lev[(a, i)], lev[(a, j)]
             rowI[q], rowJ[q] = int(lvloff[a] + i), int(lvloff[a] + j)
         arr = lambda x: '{' + ','.join(str(v) for v in x) + '}'
-        keys.append('{%d,%d,%d,%d,%s,%s,%s,%s,%s,%s}' % (Lw, len(slots), natom, len(lev), arr(kind), arr(atom),
-                                                       arr(lvI), arr(lvJ), arr(rowI), arr(rowJ)))
+        keys.append('{%d,%d,%d,%d,%s,%s,%s,%s,%s,%s,%d}' % (Lw, len(slots), natom, len(lev), arr(kind), arr(atom),
+                                                          arr(lvI), arr(lvJ), arr(rowI), arr(rowJ), Nrays))
     return keys
 
 
