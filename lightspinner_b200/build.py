@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, 'csrc')
 LIBDIR = os.path.join(HERE, '_lib')
 LIB = os.path.join(LIBDIR, os.environ.get('MALI_LIB_NAME', 'libmali_b200.so'))
 SOURCES = ['mali_api.cu']
-DEPS = ['mali_api.cu', 'mali_kernels.cuh', 'mali_types.cuh', 'exp_table.inc', 'mali_solve.h', 'mali_fs_spec.cuh', 'spec_instances.inc', os.path.join('..', '..', 'include', 'mali_b200.h')]
+DEPS = ['mali_api.cu', 'mali_kernels.cuh', 'mali_types.cuh', 'exp_table.inc', 'mali_solve.h', 'mali_voigt.h', 'mali_fs_spec.cuh', 'mali_fs_step.inc', 'spec_instances.inc', os.path.join('..', '..', 'include', 'mali_b200.h')]
 
 EXTRA = os.environ.get('MALI_NVCC_EXTRA', '').split()
 NVCC_FLAGS = EXTRA + ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '--fmad=false', '-std=c++20',

@@ -433,125 +433,23 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
 #define finish_prev() finish_step<M, NS, S.nrays>(lane, red, writer, leader, gdir + kP, jdir + klP, xP)
 
         const double *nk = sN + kS;   // populations at the current depth
+        {   // first point
+            const int s = 0;
+#define STEP_KIND 0
+#include "mali_fs_step.inc"
+#undef STEP_KIND
+        }
 #pragma unroll kUnroll
-        for (int s = 0; s < N; ++s) {
-            const int k = kS + s * dk;
-            const double *sV = ring + (useOff >> 3) + lane;          // this direction's Vij rows, lane order
-            const double *sS = ring + (useOff >> 3) + VBLK + JW + lsC;    // per-wavelength fields
-            const int klc = kl;
-            kl += dkl;
-            // the stage refilled here (step g+2) is the one step g-1 used: every lane has passed that step's __syncwarp
-            fetch_next();
-            {   // wait for this step's record
-                const uint32_t parity = (phases & useBit) ? 1u : 0u;
-                uint32_t ok = 0;
-                do {
-                    asm volatile(
-                        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                        : "=r"(ok)
-                        : "r"(useBar), "r"(parity)
-                        : "memory");
-                } while (!ok);
-                phases ^= useBit;
-            }
-            if (s > 0) finish_prev();
-
-            // ---- (1) opacity / emissivity, rh_method.py:601-632.  chiL / UL / etaA: compile-time indexed registers
-            double chiTot = 0.0, etaTot = 0.0;
-            double chiL[NLV], UL[NLV], etaA[NA];
-            double Vij[NSA], Vji[NSA], Uji[NSA];
-#pragma unroll
-            for (int q = 0; q < NLV; ++q) {
-                chiL[q] = 0.0;
-                UL[q] = 0.0;
-            }
-#pragma unroll
-            for (int a = 0; a < NA; ++a) etaA[a] = 0.0;
-#pragma unroll
-            for (int tt = 0; tt < NS; ++tt) {
-                if (S.kind[tt]) {  // rh_method.py:278-281; the table holds hc/4pi*Bij*phi
-                    Vij[tt] = sV[line_index(tt) * kVRow];
-                    Vji[tt] = T.s[tt].cA * Vij[tt];
-                    Uji[tt] = T.s[tt].cB * Vji[tt];
-                } else {           // rh_method.py:284-286
-                    Vij[tt] = ca[tt];
-                    Vji[tt] = sS[(3 + tt) * LW] * Vij[tt];
-                    Uji[tt] = cb[tt] * Vji[tt];
-                }
-                const double ni = nk[NIDX(0, S.lvI[tt])], nj = nk[NIDX(0, S.lvJ[tt])];
-                const double chi_t = ni * Vij[tt] - nj * Vji[tt];
-                const double eta_t = nj * Uji[tt];
-                // first touch of a level / atom: the reference's 0.0 + x (== x up to the sign of zero)
-                bool firstI = true, firstJ = true, firstA = true;
-                for (int u = 0; u < tt; ++u) {
-                    if (S.lvI[u] == S.lvI[tt] || S.lvJ[u] == S.lvI[tt]) firstI = false;
-                    if (S.lvI[u] == S.lvJ[tt] || S.lvJ[u] == S.lvJ[tt]) firstJ = false;
-                    if (S.atom[u] == S.atom[tt]) firstA = false;
-                }
-                chiL[S.lvI[tt]] = firstI ? chi_t : chiL[S.lvI[tt]] + chi_t;
-                chiL[S.lvJ[tt]] = firstJ ? -chi_t : chiL[S.lvJ[tt]] - chi_t;
-                UL[S.lvJ[tt]] = firstJ ? Uji[tt] : UL[S.lvJ[tt]] + Uji[tt];
-                etaA[S.atom[tt]] = firstA ? eta_t : etaA[S.atom[tt]] + eta_t;
-                chiTot = (tt == 0) ? chi_t : chiTot + chi_t;
-                etaTot = (tt == 0) ? eta_t : etaTot + eta_t;
-            }
-            chiTot += sS[0];
-            const double rchi = rcp_full(chiTot);
-            const double Jdag = sS[-JW];             // J-dagger: written into the record by j_finish_kernel
-            const double Ssrc = div_by(etaTot + sS[LW] + sS[2 * LW] * Jdag, chiTot, rchi);
-
-            // ---- (2) short characteristic
-            const double zk = sZ[k];
-            double Ik, Psi;
-            if (s == 0)
-                sw.first(d != 0, zmu, chiTot, Ssrc, zk, chiProbe, sZ[kS + dk], bbc0, bbc1, Ik, Psi);
-            else
-                sw.step(s == N - 1, zmu, chiTot, rchi, Ssrc, zk, Ik, Psi);
-
-            // ---- (3) J, rh_method.py:640: the sum over the mu lanes is taken in finish_prev of the next step
-            xP = valid ? hw * Ik : 0.0;
-            klP = klc;
-
-            // ---- (4) Gamma integrands, rh_method.py:643-681
-            if constexpr (NS > 0) {
-                double v[M];
-#pragma unroll
-                for (int q = 0; q < M; ++q) v[q] = 0.0;
-                double Ieff[NA];
-#pragma unroll
-                for (int a = 0; a < NA; ++a) Ieff[a] = Ik - Psi * etaA[a];
-#pragma unroll
-                for (int tt = 0; tt < NS; ++tt) {
-                    const double wlamu = S.kind[tt] ? (sS[(3 + tt) * LW] * hwG) * fourPi : cw[tt];  // rh_method.py:665
-                    const double Ie = Ieff[S.atom[tt]];
-                    // Ulvl of a level no transition of the tile has as its upper level is exactly 0: the reference's
-                    // (chi*Psi)*0.0 term is +-0 and drops out of the subtraction
-                    bool uJ = false, uI = false;
-                    for (int u = 0; u < NS; ++u) {
-                        if (S.lvJ[u] == S.lvJ[tt]) uJ = true;
-                        if (S.lvJ[u] == S.lvI[tt]) uI = true;
-                    }
-                    double g1 = Uji[tt] + Vji[tt] * Ie;
-                    if (uJ) g1 = g1 - ((chiL[S.lvI[tt]] * Psi) * UL[S.lvJ[tt]]);
-                    double g2 = Vij[tt] * Ie;
-                    if (uI) g2 = g2 - ((chiL[S.lvJ[tt]] * Psi) * UL[S.lvI[tt]]);
-                    v[2 * tt] = g1 * wlamu;  // wavelengths without this transition: wlamu == 0 (zero table entries)
-                    v[2 * tt + 1] = g2 * wlamu;
-                }
-                __syncwarp();                 // every lane has read the previous step's values (finish_prev)
-                reduce_store<M>(v, lane, red);
-                kP = k;
-            }
-            __syncwarp();                     // values visible; ring stage of this step free for the next fetch
-
-            // next stage / depth
-            {
-                const bool wrap = useOff == (uint32_t)((NST - 1) * STAGE * 8);
-                useOff = wrap ? 0u : useOff + (uint32_t)(STAGE * 8);
-                useBar = wrap ? barAddr : useBar + 8u;
-                useBit = wrap ? 1u : useBit << 1;
-            }
-            nk += dk;
+        for (int s = 1; s < N - 1; ++s) {
+#define STEP_KIND 1
+#include "mali_fs_step.inc"
+#undef STEP_KIND
+        }
+        {   // last point (N >= 3 is checked at model creation)
+            const int s = N - 1;
+#define STEP_KIND 2
+#include "mali_fs_step.inc"
+#undef STEP_KIND
         }
         finish_prev();
         __syncwarp();
