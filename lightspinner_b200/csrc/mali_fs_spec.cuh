@@ -421,7 +421,7 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
             chiProbe = chiTot + __ldg(rec + 2 * VBLK + JW + lsC);
         }
 
-        Sweep sw;
+        SweepT<1> sw;
         sw.r3 = r3;
         sw.stab = stab;
 
