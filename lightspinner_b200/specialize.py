@@ -83,7 +83,8 @@ def library_for(problem, verbose=False):
     keys = sorted(need | have)
     tag = hashlib.sha1('\n'.join(keys).encode()).hexdigest()[:12]
     lib = os.path.join(_build.LIBDIR, 'libmali_b200_spec_%s.so' % tag)
-    if os.path.isfile(lib) and os.path.getmtime(lib) >= os.path.getmtime(os.path.join(_build.CSRC, 'mali_fs_spec.cuh')):
+    newest = max(os.path.getmtime(os.path.join(_build.CSRC, d)) for d in _build.DEPS if d != 'spec_instances.inc')
+    if os.path.isfile(lib) and os.path.getmtime(lib) >= newest:      # cached and not older than any kernel source
         return lib
     inc = os.path.join(_build.LIBDIR, 'spec_instances_%s.inc' % tag)
     os.makedirs(_build.LIBDIR, exist_ok=True)
