@@ -907,9 +907,9 @@ static int launch_fs(const mali_model *m, const mali_buffers *b, int col0, int n
             c.useBulk = (m->N % 2 == 0) ? 1 : 0;   // cp.async.bulk: 16-byte sizes / addresses
             const int red = spec_pow2(2 * spec_class_slots(cls)) * 36;
             c.mbarOffBytes = (c.lvlOffDoubles + red) * 8;
-            c.expTabOffBytes = (int)align_up(c.mbarOffBytes + 32, 16);
+            c.expTabOffBytes = (int)align_up(c.mbarOffBytes + 8 + 8 * kRingStages, 16);   // staging + ring barriers
             c.ringOffDoubles = (c.expTabOffBytes + 128 * 16) / 8;
-            c.smemBytesPerWarp = (c.ringOffDoubles + 3 * m->ringStage[cls]) * 8;
+            c.smemBytesPerWarp = (c.ringOffDoubles + kRingStages * m->ringStage[cls]) * 8;
             smem[cls] = (size_t)c.smemBytesPerWarp;
             if (smem[cls] > 227 * 1024) return fail(MALI_ELIMIT, "column needs %zu B of shared memory per warp", smem[cls]);
         }

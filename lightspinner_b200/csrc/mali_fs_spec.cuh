@@ -30,6 +30,10 @@
 namespace mali {
 
 constexpr int kSpecMaxSlots = 8;
+#ifndef MALI_NST
+#define MALI_NST 3
+#endif
+constexpr int kRingStages = MALI_NST;   // stages of the per-warp TMA ring (shared with the host's smem sizing)
 
 struct FsCommon {  // launch-invariant parameters of the specialised kernels (constant bank)
     int32_t N, Nrays, Nspect, Lw;
@@ -341,7 +345,7 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
     constexpr int JW = (LW + 3) / 4 * 4;                                   // J-dagger field (whole sectors)
     constexpr int SMALL = (JW + (3 + NS) * LW + 15) / 16 * 16;             // J-dagger + bg + slot fields, padded as packed
     constexpr int STAGE = VBLK + SMALL;                                    // doubles of one ring stage
-    constexpr int NST = 3;                                                 // ring depth: two steps in flight
+    constexpr int NST = kRingStages;                                       // ring depth: NST - 1 steps in flight
 #define line_index(tt) spec_line_index(S, (tt))
     // idle lanes (lane >= Lw * Nrays) read the zero padding of the Vij rows and the last wavelength's fields; lanes
     // past the end of the spectrum read the zero / clamped entries packed for them.  Their weights are zero.
@@ -355,7 +359,7 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
     // before reading.  No per-lane global loads, no prefetch registers.
     double *ring = sN + p.ringOffDoubles;
     const uint32_t ringAddr = smem_u32(ring);
-    const uint32_t barAddr = smem_u32(wbase + p.mbarOffBytes) + 8;  // three ring barriers after the staging barrier
+    const uint32_t barAddr = smem_u32(wbase + p.mbarOffBytes) + 8;  // the ring's barriers follow the staging barrier
     if (lane == 0) {
 #pragma unroll
         for (int q = 0; q < NST; ++q) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(barAddr + 8 * q) : "memory");
@@ -371,8 +375,8 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
     uint32_t fetchBar = barAddr;        // its barrier
     const double *fetchRec = tab0 + (size_t)kS * p.rowStride;      // its record
 #define fetch_next() ring_fetch<VBLK, SMALL, NST>(fetchS, fetchOff, fetchBar, fetchRec, N, stepRec, d * VBLK, ringAddr, barAddr)
-    fetch_next();
-    fetch_next();
+#pragma unroll
+    for (int q = 0; q < NST - 1; ++q) fetch_next();
     uint32_t useOff = 0, useBar = barAddr, phases = 0, useBit = 1;   // stage being consumed; parity bit per stage
 
     // ---- depth-invariant per-lane constants of the continuum slots (alpha, 2hc/lambda^3, wlamu)

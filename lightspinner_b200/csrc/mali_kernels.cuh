@@ -681,6 +681,7 @@ __global__ void pack_tiles_kernel(const PackChunk *chunks, const PackTile *tiles
     __shared__ double tile[32][33];
     const PackChunk ch = chunks[blockIdx.x];
     const PackTile pt = tiles[ch.tile];
+    if (skipPhi && ch.e0 + 32 <= pt.sb) return;   // a chunk of Vij rows only: compute_phi_kernel writes those rows whole
     const double *src = staging + (size_t)blockIdx.z * hpStride;
     double *dst = colconst + (size_t)(col0 + blockIdx.z) * colStride + offTab + pt.recOff;
     const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
