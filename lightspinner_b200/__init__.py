@@ -7,11 +7,11 @@ The compute lives in csrc/ (hand-written CUDA for sm_100a behind the C ABI of in
 fallback.  Importing the package does not touch the GPU; constructing a Context / MaliEngine does.
 """
 
-__all__ = ['Context', 'piecewise_linear_1d', 'IPsi', 'UV', 'MaliEngine']
+__all__ = ['Context', 'BatchContext', 'piecewise_linear_1d', 'IPsi', 'UV', 'MaliEngine']
 
 
 def __getattr__(name):
-    if name in ('Context', 'piecewise_linear_1d', 'IPsi', 'UV'):
+    if name in ('Context', 'BatchContext', 'piecewise_linear_1d', 'IPsi', 'UV'):
         from . import context
         return getattr(context, name)
     if name == 'MaliEngine':

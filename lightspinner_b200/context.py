@@ -141,7 +141,7 @@ class ComputationalTransition:
 
     def uv(self, la, mu, toFrom):
         """rh_method.py:245-288, evaluated by the GPU from the packed tables (mali_uv)."""
-        U, Vij, Vji = self.atom.ctx._engine.uv(0, self.index, int(la), int(mu), bool(toFrom))
+        U, Vij, Vji = self.atom.ctx._engine.uv(self.atom.ctx._col, self.index, int(la), int(mu), bool(toFrom))
         return UV(Uji=U, Vij=Vij, Vji=Vji)
 
 
@@ -192,8 +192,8 @@ class ComputationalAtom:
 class Context:
     """Drop-in for rh_method.Context (rh_method.py:490-745) -- one column on one GPU.
 
-    Batches of columns (response functions, 1.5D runs) go through lightspinner_b200.BatchContext / MaliEngine,
-    which run the same kernels over many columns per launch.
+    Batches of columns (response functions, 1.5D runs) go through BatchContext (below) / MaliEngine, which run the
+    same kernels over many columns per launch.
     """
 
     def __init__(self, atmos, spect, eqPops, background, device=None, _host_only=False, device_phi=False):
@@ -213,6 +213,7 @@ class Context:
         self._problem = flatten_context(self)
         self._cache = {}
         self._engine = None
+        self._col = 0       # column of the engine's batch this Context owns (BatchContext hands out others)
         if _host_only:      # unit tests of the host-side flattening only; every compute method then fails
             return
         self._engine = MaliEngine(self._problem, 1, device=device)
@@ -229,37 +230,122 @@ class Context:
 
     @property
     def J(self):
-        return self._get('J', lambda: self._engine.J(0))
+        return self._get('J', lambda: self._engine.J(self._col))
 
     @property
     def I(self):
-        return self._get('I', lambda: self._engine.I(0))
+        return self._get('I', lambda: self._engine.I(self._col))
 
     def _atom_Gamma(self, a):
-        return self._get(('G', a), lambda: self._engine.atom_Gamma(0, a))
+        return self._get(('G', a), lambda: self._engine.atom_Gamma(self._col, a))
 
     def _push_pops(self):
         # the reference reads atom.n afresh on every call: honour edits made through the eqPops alias
-        self._engine.set_n(0, np.concatenate([a.n for a in self.activeAtoms], axis=0))
+        self._engine.set_n(self._col, np.concatenate([a.n for a in self.activeAtoms], axis=0))
 
     def formal_sol_gamma_matrices(self):
         """rh_method.py:565-708.  Returns dJ = max |1 - JDag/J| as a float."""
         self._push_pops()
         self._cache = {}
-        return float(self._engine.formal_sol_gamma_matrices()[0])
+        return float(self._engine.formal_sol_gamma_matrices(self._col, 1)[0])
 
     def stat_equil(self):
         """rh_method.py:710-745.  Updates every atom.n IN PLACE; raises numpy.linalg.LinAlgError if singular."""
-        dPops = float(self._engine.stat_equil()[0])
-        n = self._engine.n(0)
+        dPops = float(self._engine.stat_equil(self._col, 1)[0])
+        self._pull_pops()
+        return dPops
+
+    def _pull_pops(self):
+        n = self._engine.n(self._col)
         mt = self._engine.mt
         for ia, atom in enumerate(self.activeAtoms):
             atom.n[...] = n[mt.lvloff[ia]:mt.lvloff[ia + 1]]
-        return dPops
 
     def close(self):
-        if self._engine is not None:
+        if self._engine is not None and self._col == 0 and not getattr(self, '_borrowed', False):
             self._engine.close()
+
+
+class BatchContext:
+    """Many columns that share one radiative model (same atoms, wavelength grid and angle quadrature) solved in one
+    batch -- the response-function / 1.5D use of the reference, which builds one Context per column and iterates
+    them one after the other (response_fn.py:23-39).
+
+        batch = BatchContext([(atmos_k, spect, eqPops_k, background_k) for k in columns])
+        its = batch.iterate()                       # test.py:20-29 for every column, on the device
+        I = batch[k].I ;  n = eqPops_k['Ca'].n      # per-column results through the usual Context attributes
+
+    `batch[k]` is a Context (host mirrors, results, the eqPops alias) bound to column k of the batch; the per-call
+    methods of the reference exist in batched form too: formal_sol_gamma_matrices() and stat_equil() return one
+    value per column."""
+
+    def __init__(self, columns, device=None, device_phi=False):
+        if not columns:
+            raise ValueError('BatchContext needs at least one column')
+        self.contexts = [Context(*c, _host_only=True, device_phi=device_phi) for c in columns]
+        problems = [c._problem for c in self.contexts]
+        p0 = problems[0]
+        for q in problems[1:]:
+            for key in ('Nspace', 'Nrays', 'Nspect'):
+                if int(q[key]) != int(p0[key]):
+                    raise ValueError('columns of a batch must share %s' % key)
+            for key in ('trans', 'wavelength', 'muz', 'wmu', 'Nlevel', 'linepar', 'alpha'):
+                if not np.array_equal(np.asarray(q[key]), np.asarray(p0[key])):
+                    raise ValueError('columns of a batch must share the radiative model (%s differs)' % key)
+        self._engine = MaliEngine(p0, len(problems), device=device)
+        if device_phi:
+            self._engine.upload_device_phi(problems)
+        else:
+            self._engine.upload(problems)
+        for k, c in enumerate(self.contexts):
+            c._engine, c._col, c._borrowed = self._engine, k, True
+
+    def __len__(self):
+        return len(self.contexts)
+
+    def __getitem__(self, k):
+        return self.contexts[k]
+
+    def _invalidate(self):
+        for c in self.contexts:
+            c._cache = {}
+
+    def formal_sol_gamma_matrices(self):
+        """rh_method.py:565-708 for every column: returns dJ[ncol]."""
+        for c in self.contexts:
+            c._push_pops()
+        self._invalidate()
+        return np.array(self._engine.formal_sol_gamma_matrices())
+
+    def stat_equil(self):
+        """rh_method.py:710-745 for every column: returns dPops[ncol]; every atom.n is updated in place."""
+        dPops = np.array(self._engine.stat_equil())
+        for c in self.contexts:
+            c._pull_pops()
+        return dPops
+
+    def iterate(self, max_iter=500, tolJ=2e-3, tolPops=1e-3):
+        """The loop of test.py:20-29 for every column, kept on the device (mali_iterate): returns the iteration
+        count of each column (a column stops as soon as it meets the tolerances)."""
+        import torch
+        for c in self.contexts:
+            c._push_pops()
+        self._invalidate()
+        self._engine.reset_iteration_state()
+        done = 0
+        while done < max_iter:
+            nit = min(16, max_iter - done)
+            self._engine.iterate_async(nit, tolJ, tolPops)
+            done += nit
+            if bool((self._engine.t_done != 0).all().item()):
+                break
+        torch.cuda.synchronize(self._engine.device)
+        for c in self.contexts:
+            c._pull_pops()
+        return self._engine.t_iter.cpu().numpy().copy()
+
+    def close(self):
+        self._engine.close()
 
 
 def flatten_context(ctx):

@@ -170,25 +170,28 @@ class MaliEngine:
         with torch.cuda.device(self.device):
             _capi.check(self.lib.mali_stat_equil(self._handle, C.byref(self.bufs), col0, ncol, self._stream()))
 
-    def formal_sol_gamma_matrices(self):
-        """One Lambda iteration for every column; returns dJ per column (device->host read of ncol doubles)."""
-        self.formal_sol_gamma_async()
-        dJ = self.t_dJ.cpu().numpy()
-        status = self.t_status.cpu().numpy()
+    def formal_sol_gamma_matrices(self, col0=0, ncol=None):
+        """One Lambda iteration for columns [col0, col0+ncol) (default: all); returns their dJ (device->host read)."""
+        ncol = self.ncol - col0 if ncol is None else ncol
+        self.formal_sol_gamma_async(col0, ncol)
+        dJ = self.t_dJ[col0:col0 + ncol].cpu().numpy()
+        status = self.t_status[col0:col0 + ncol].cpu().numpy()
         if (status & 2).any():
-            bad = np.nonzero(status & 2)[0]
-            self.t_status.bitwise_and_(~2)
+            bad = col0 + np.nonzero(status & 2)[0]
+            self.t_status[col0:col0 + ncol].bitwise_and_(~2)
             raise FloatingPointError('opacity or optical-depth step outside the formal solver\'s numeric domain '
                                      '(zero, subnormal, infinite or NaN) in column(s) %s' % bad[:8].tolist())
         return dJ
 
-    def stat_equil(self):
-        self.stat_equil_async()
-        dP = self.t_dPops.cpu().numpy()
-        status = self.t_status.cpu().numpy()
+    def stat_equil(self, col0=0, ncol=None):
+        """Statistical equilibrium for columns [col0, col0+ncol) (default: all); returns their dPops."""
+        ncol = self.ncol - col0 if ncol is None else ncol
+        self.stat_equil_async(col0, ncol)
+        dP = self.t_dPops[col0:col0 + ncol].cpu().numpy()
+        status = self.t_status[col0:col0 + ncol].cpu().numpy()
         if (status & 1).any():
-            bad = np.nonzero(status & 1)[0]
-            self.t_status.zero_()
+            bad = col0 + np.nonzero(status & 1)[0]
+            self.t_status[col0:col0 + ncol].zero_()
             raise np.linalg.LinAlgError('singular statistical-equilibrium system in column(s) %s' % bad[:8].tolist())
         return dP
 

@@ -71,3 +71,30 @@ def test_dropin_context_with_device_profiles(eng_mod):
     t = ctx.activeAtoms[0].trans[0]
     assert t.phi.shape == (int(p['trans'][0, 5]), 5, 2, 82)
     ctx.close()
+
+
+def test_batch_context_runs_the_response_function_columns(eng_mod):
+    """BatchContext: the base column and two response-function columns (different atmospheres, warm-started through
+    the eqPops alias) solved as one batch; every column converges in the reference's iteration count to the
+    reference's I and n, and the per-column Context views and eqPops aliases see the results."""
+    from helpers import fake_reference_objects
+    from lightspinner_b200 import BatchContext
+    names = ['c1_falc_ca', 'rf_k40p', 'rf_k10m']
+    gold = [load_golden(nm) for nm in names]
+    cols = [fake_reference_objects(g[0]) for g in gold]
+    batch = BatchContext(cols)
+    its = batch.iterate()
+    assert len(batch) == 3
+    for k, (p, r) in enumerate(gold):
+        assert int(its[k]) == int(r['niter']), (names[k], its[k])
+        assert relerr(batch[k].I, r['final_I']) < 1e-10
+        assert relerr(cols[k][2]['CA'].n, r['final_n']) < 1e-10          # the eqPops alias of column k
+        assert batch[k].J.shape == r['final_J'].shape
+    # the per-call forms, batched and per column
+    dJ = batch.formal_sol_gamma_matrices()
+    assert dJ.shape == (3,) and np.all(dJ < 2e-3)
+    dP = batch.stat_equil()
+    assert dP.shape == (3,) and np.all(dP < 1e-3)
+    d1 = batch[1].formal_sol_gamma_matrices()
+    assert isinstance(d1, float) and d1 < 2e-3
+    batch.close()
