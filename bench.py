@@ -323,7 +323,9 @@ def main():
     # ---- e2e: host buffers -> H2D -> re-layout -> iterate -> D2H, double-buffered over column chunks
     e2e = None
     if want_e2e:
-        streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+        # [0] copy stream (H2D, re-layout, line profiles), [1] compute stream (the solves), the latter at high priority so
+        # that the upload kernels of the next chunk only fill what the solve leaves idle
+        streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev, priority=-1)]
         out_I = torch.empty(ncol * lay.I, dtype=torch.float64, pin_memory=True)
         out_n = torch.empty(ncol * lay.pops, dtype=torch.float64, pin_memory=True)
         out_d = torch.empty(2 * ncol, dtype=torch.float64, pin_memory=True)
