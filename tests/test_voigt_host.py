@@ -59,8 +59,11 @@ def test_voigt_against_40_digit_arithmetic(shim):
     mp = pytest.importorskip('mpmath')
     mp.mp.dps = 40
     rng = np.random.default_rng(3)
-    a = np.concatenate([10.0**rng.uniform(-7, 1.4, 600), rng.uniform(0.09, 0.17, 150)])
-    v = np.concatenate([rng.uniform(0, 1, 600) * 10.0**rng.uniform(-3, 3.5, 600), rng.uniform(5.9, 6.2, 150)])
+    # random pairs, the region where wofz switches algorithm, and both sides of mali_voigt.h's |z| = 16 switch
+    a = np.concatenate([10.0**rng.uniform(-7, 1.4, 600), rng.uniform(0.09, 0.17, 150), 10.0**rng.uniform(-7, 1.2, 200),
+                        rng.uniform(15, 17, 100)])
+    v = np.concatenate([rng.uniform(0, 1, 600) * 10.0**rng.uniform(-3, 3.5, 600), rng.uniform(5.9, 6.2, 150),
+                        rng.uniform(15.9, 18, 200), rng.uniform(0, 6, 100)])
     got = voigt(shim, a, v)
 
     def exact(x, y):
