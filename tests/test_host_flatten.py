@@ -4,7 +4,7 @@ and the flattening / host-pack layout must reproduce what the reference computed
 import numpy as np
 import pytest
 
-from helpers import fake_reference_objects, load_golden
+from helpers import fake_reference_objects, load_golden, select_rays
 
 KEYS = ['wavelength', 'muz', 'wmu', 'Nlevel', 'trans', 'linepar', 'alpha', 'height', 'temperature', 'bg_chi', 'bg_eta',
         'bg_sca', 'nStar', 'nTotal', 'C', 'n', 'phi', 'phioff', 'wphi']
@@ -84,3 +84,14 @@ def test_stock_kernel_instances_cover_the_fixture_models():
         p, _ = load_golden(name)
         assert set(specialize.tile_structures(p)) <= have, name
         assert specialize.library_for(p) is None
+
+
+def test_batch_context_rejects_columns_of_different_models():
+    """BatchContext checks, before touching the GPU, that its columns share one radiative model."""
+    from lightspinner_b200.context import BatchContext
+    p, _ = load_golden('c1_falc_ca')
+    q = select_rays(p, [0, 2, 4])
+    with pytest.raises(ValueError, match='share'):
+        BatchContext([fake_reference_objects(p), fake_reference_objects(q)])
+    with pytest.raises(ValueError):
+        BatchContext([])
