@@ -949,8 +949,8 @@ static int launch_fs(const mali_model *m, const mali_buffers *b, int col0, int n
         m->profUsed += 2;
     }
     FinishParams f = make_finish_params(m, b, col0, ncol);
-    dim3 grid((m->N + 63) / 64, m->Natom, ncol);
-    gamma_finish_kernel<<<grid, 64, 0, st>>>(f);
+    dim3 grid((m->N + 31) / 32, m->Natom, ncol);
+    gamma_finish_kernel<<<grid, dim3(32, 8), 0, st>>>(f);
     {
         const int nb = std::min(m->N, 41);   // depth rows are dealt round-robin to the blocks of a column
         j_finish_kernel<<<dim3(nb, ncol), 256, 0, st>>>(b->J, m->lay.J, b->scratch, m->lay.scratch, m->off_jpart, m->upOff, b->colconst, m->lay.colconst, m->off_tab, m->rowStride, m->d_tileJOff, m->Nspect, m->Lw,

@@ -530,37 +530,46 @@ __global__ void j_finish_kernel(double *J, int64_t JStride, const double *scratc
 // 698-703).  One thread per (column, atom, depth); coalesced over depth.
 __global__ void gamma_finish_kernel(const FinishParams p)
 {
+    // block = 32 depth points x 8 "pair lanes": the transitions of an atom are dealt to the pair lanes by their
+    // (i, j) entry, so every Gamma entry has one owner (deterministic order) and the sums of different transitions
+    // run in parallel; the diagonal is formed after a block barrier
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = threadIdx.y, ny = blockDim.y;
     const int a = blockIdx.y;
     const int col = p.col0 + blockIdx.z;
-    if (k >= p.N) return;
     if (p.done != nullptr && p.done[col] != 0) return;
+    const bool on = k < p.N;
     const int N = p.N;
     const int NL = p.Nlevel[a];
     const double *C = p.colconst + (size_t)col * p.colStride + p.off_C + (size_t)p.g2Off[a] * N;
     double *G = p.Gamma + (size_t)col * p.gammaStride + (size_t)p.g2Off[a] * N;
     const double *part = p.scratch + (size_t)col * p.scratchStride + p.off_part;
 
-    for (int e = 0; e < NL * NL; ++e) G[(size_t)e * N + k] = 0.0 + C[(size_t)e * N + k];
-    for (int t = 0; t < p.Ntrans; ++t) {
-        const int32_t *tr = p.trans + 6 * t;
-        if (tr[0] != a) continue;
-        const int i = tr[1], j = tr[2];
-        double sij = 0.0, sji = 0.0;
-        for (int r = p.trPartOff[t]; r < p.trPartOff[t + 1]; ++r) {
-            const int row = p.trPartRows[r];
-            sij += part[(size_t)row * N + k] + part[(size_t)row * N + k + p.upOff];
-            sji += part[(size_t)(row + 1) * N + k] + part[(size_t)(row + 1) * N + k + p.upOff];
+    if (on)
+        for (int e = y; e < NL * NL; e += ny) G[(size_t)e * N + k] = 0.0 + C[(size_t)e * N + k];
+    __syncthreads();
+    if (on)
+        for (int t = 0; t < p.Ntrans; ++t) {
+            const int32_t *tr = p.trans + 6 * t;
+            if (tr[0] != a) continue;
+            const int i = tr[1], j = tr[2];
+            if ((i * NL + j) % ny != y) continue;
+            double sij = 0.0, sji = 0.0;
+            for (int r = p.trPartOff[t]; r < p.trPartOff[t + 1]; ++r) {
+                const int row = p.trPartRows[r];
+                sij += part[(size_t)row * N + k] + part[(size_t)row * N + k + p.upOff];
+                sji += part[(size_t)(row + 1) * N + k] + part[(size_t)(row + 1) * N + k + p.upOff];
+            }
+            G[((size_t)i * NL + j) * N + k] += sij;
+            G[((size_t)j * NL + i) * N + k] += sji;
         }
-        G[((size_t)i * NL + j) * N + k] += sij;
-        G[((size_t)j * NL + i) * N + k] += sji;
-    }
-    for (int i = 0; i < NL; ++i) G[((size_t)i * NL + i) * N + k] = 0.0;
-    for (int i = 0; i < NL; ++i) {
-        double GamDiag = 0.0;
-        for (int l = 0; l < NL; ++l) GamDiag += G[((size_t)l * NL + i) * N + k];
-        G[((size_t)i * NL + i) * N + k] = -GamDiag;
-    }
+    __syncthreads();
+    if (on)
+        for (int i = y; i < NL; i += ny) {   // rh_method.py:698-703: zero the diagonal, then minus the column sum
+            double GamDiag = 0.0;
+            for (int l = 0; l < NL; ++l) GamDiag += (l == i) ? 0.0 : G[((size_t)l * NL + i) * N + k];
+            G[((size_t)i * NL + i) * N + k] = -GamDiag;
+        }
 }
 
 // --------------------------------------------------------------------------------------------------------
