@@ -164,3 +164,59 @@ def test_runtime_specialisation_builds_model_specific_kernels(oracle):
             oc.stat_equil(use_scipy=True)
     assert relerr(eng.J(0), oc.J) < 1e-13 and relerr(eng.I(0), oc.I) < 1e-13 and relerr(eng.n(0), oc.n) < 1e-9
     eng.close()
+
+
+def test_synthetic_batch_properties_at_bench_scale(oracle):
+    """The bench workload (synthetic CaII+H columns, lightspinner_b200/synth.py) at a quarter of the per-GPU batch:
+    size-independent properties of the path plus a spot check of sampled columns against the oracle.
+      * rate conservation: every column of Gamma sums to zero (rh_method.py:698-703);
+      * a batch split in two launches gives bit-identical results to one launch;
+      * sampled columns agree with the oracle run on the same synthetic inputs;
+      * all populations stay positive and finite."""
+    import torch
+    from lightspinner_b200 import synth
+    from lightspinner_b200.engine import MaliEngine
+    from lightspinner_b200.tables import pack_column
+    p, _ = load_golden('c2_falc_cah')
+    ncol, iters = 256, 5
+    dev = torch.device('cuda', 0)
+
+    def run(splits):
+        eng = MaliEngine(p, ncol, max_upload_chunk=ncol)
+        hp = int(eng.lay.hostpack)
+        base_pack = torch.from_numpy(pack_column(eng.mt, eng.lay, p)).to(dev)
+        staging = torch.empty(ncol * hp, dtype=torch.float64, device=dev)
+        synth.jitter_staging(staging, eng.lay, eng.mt, base_pack, list(range(ncol)))
+        eng.repack_from_staging(staging, 0, ncol)
+        for it in range(1, iters + 1):
+            for c0, nc in splits:
+                eng.formal_sol_gamma_async(c0, nc)
+                if it > 3:
+                    eng.stat_equil_async(c0, nc)
+        torch.cuda.synchronize()
+        out = (eng.t_pops.cpu().numpy().copy(), eng.t_J.cpu().numpy().copy(), eng.t_I.cpu().numpy().copy(),
+               eng.t_Gamma.cpu().numpy().copy())
+        samples = {c: (eng.J(c), eng.I(c), eng.n(c)) for c in (0, 101, 255)}
+        lay, mt = eng.lay, eng.mt
+        eng.close()
+        return out, samples, lay, mt
+
+    (n1, J1, I1, G1), samples, lay, mt = run([(0, ncol)])
+    (n2, J2, I2, G2), _, _, _ = run([(0, 128), (128, 128)])
+    assert np.array_equal(n1, n2) and np.array_equal(J1, J2) and np.array_equal(I1, I2) and np.array_equal(G1, G2)
+    assert np.all(np.isfinite(n1)) and np.all(n1 > 0) and np.all(np.isfinite(I1))
+    # conservation, per atom: sum over the first index of Gamma[i][j][k] vanishes to rounding
+    N = mt.Nspace
+    G = G1.reshape(ncol, -1)
+    for a in range(mt.Natom):
+        NL = int(mt.Nlevel[a])
+        Ga = G[:, int(mt.g2off[a]) * N:int(mt.g2off[a + 1]) * N].reshape(ncol, NL, NL, N)
+        assert np.max(np.abs(Ga.sum(axis=1))) <= 1e-9 * np.max(np.abs(Ga))
+    # sampled columns against the oracle on the same synthetic inputs
+    for c, (J, I, n) in samples.items():
+        oc = oracle.OracleContext(synth.jitter_problem(p, c))
+        for it in range(1, iters + 1):
+            oc.formal_sol_gamma_matrices()
+            if it > 3:
+                oc.stat_equil(use_scipy=False)
+        assert relerr(I, oc.I) < 1e-9 and relerr(J, oc.J) < 1e-9 and relerr(n, oc.n) < 1e-8, c
