@@ -603,7 +603,7 @@ __global__ void stat_equil_kernel(const FinishParams p)
         }
     }
     double x[NLMAX];
-    if (!solve_stat_equil<NLMAX>(G, N, NL, iEl, nTot, x)) {
+    if (!solve_stat_equil_any<NLMAX>(G, N, NL, iEl, nTot, x)) {
         atomicOr(p.status + col, 1);  // the reference would raise LinAlgError here
         return;
     }

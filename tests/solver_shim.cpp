@@ -10,3 +10,7 @@ extern "C" int shim_solve16(const double *G, int NL, int iEl, double nTot, doubl
 {
     return mali::solve_stat_equil<16>(G, 1, NL, iEl, nTot, x) ? 0 : 1;
 }
+extern "C" int shim_solve_any(const double *G, int NL, int iEl, double nTot, double *x)
+{
+    return mali::solve_stat_equil_any<16>(G, 1, NL, iEl, nTot, x) ? 0 : 1;
+}

@@ -24,7 +24,7 @@ def shim(tmp_path_factory):
                            os.path.join(HERE, 'solver_shim.cpp')])
     L = C.CDLL(out)
     dp = C.POINTER(C.c_double)
-    for f in (L.shim_solve8, L.shim_solve16):
+    for f in (L.shim_solve8, L.shim_solve16, L.shim_solve_any):
         f.argtypes = [dp, C.c_int, C.c_int, C.c_double, dp]
     return L
 
@@ -104,3 +104,24 @@ def test_singular_system_is_reported(shim):
     G[2, :] = [2.0, 4.0, 6.0, 8.0]
     rc, x = solve_with(shim.shim_solve8, G, 0, 1.0)
     assert rc == 1
+
+
+def test_register_resident_form_returns_the_same_bits(shim):
+    """solve_stat_equil_fixed<NL> (what the kernel runs for 2..8 levels) against the general form: identical bits,
+    with and without row exchanges, and the same singular-system verdict."""
+    rng = np.random.default_rng(11)
+    for NL in (2, 3, 4, 5, 6, 7, 8):
+        for trial in range(40):
+            G = rng.normal(size=(NL, NL)) * np.exp(rng.normal(0, 4, size=(NL, NL)))
+            if trial % 4 == 0:      # diagonally dominant: no exchanges
+                G += np.diag(np.full(NL, 1e6))
+            iEl = int(rng.integers(0, NL))
+            nTot = float(np.exp(rng.normal(30, 5)))
+            rc0, x0 = solve_with(shim.shim_solve8, G, iEl, nTot)
+            rc1, x1 = solve_with(shim.shim_solve_any, G, iEl, nTot)
+            assert rc0 == rc1 == 0
+            assert np.array_equal(x0, x1), (NL, trial)
+    G = np.zeros((4, 4))
+    G[1, :] = [1.0, 2.0, 3.0, 4.0]
+    G[2, :] = [2.0, 4.0, 6.0, 8.0]
+    assert solve_with(shim.shim_solve_any, G, 0, 1.0)[0] == 1
