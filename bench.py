@@ -120,11 +120,20 @@ class ClockSampler:
                 'power_w_max': max(pw) if pw else None, 'samples': len(sm), 'reasons': sorted(reasons)}
 
 
+def host_threads():
+    """Host cores this process may use (launchers such as torchrun export OMP_NUM_THREADS=1: not a core count)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def cpu_oracle_rate(base, ncol_cpu, iters, col0=0):
     """Times the oracle's C restatement (OpenMP over columns) on synthetic columns [col0, col0+ncol_cpu)."""
     from oracle import mali_oracle as mo
     from lightspinner_b200 import synth
     mo.build()
+    mo.set_threads(host_threads())
     ctxs = [mo.OracleContext(synth.jitter_problem(base, col0 + c)) for c in range(ncol_cpu)]
     t0 = time.perf_counter()
     mo.iterate_batch(ctxs, iters, start_iter=3)     # start_iter=3: every iteration does formal solution + stat-eq
@@ -139,10 +148,16 @@ def run_reference(args, base):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    ncol_cpu = max(threads, min(4 * threads, 256))
+    threads = host_threads()
+    # bounded sample: calibrate on one column per thread x 1 iteration, then size the step so that the whole
+    # --steps K --warmup W run stays within about a minute of CPU time whatever the box's core count
+    cpu_oracle_rate(base, threads, 1)                      # first touch (library load, page faults)
+    _, dt_cal, _, _ = cpu_oracle_rate(base, threads, 1)
+    budget = 60.0 / (args.steps + 1)
+    per_thread = int(budget / max(dt_cal * args.iters, 1e-6))
+    ncol_cpu = threads * max(1, min(16, per_thread))
     for _ in range(args.warmup and 1):
-        cpu_oracle_rate(base, min(ncol_cpu, threads), 1)
+        cpu_oracle_rate(base, threads, 1)
     rates, times = [], []
     for _ in range(args.steps):
         r, dt, th, _ = cpu_oracle_rate(base, ncol_cpu, args.iters)
@@ -157,11 +172,30 @@ def run_reference(args, base):
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * sum(times) / len(times),
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': workload_config(args, base),
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': th, 'kind': 'port', 'sample': sample},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': th, 'kind': 'port', 'sample': sample,
+                         'reference_numpy': reference_numpy_side_number()},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
     print(json.dumps(line))
+
+
+def reference_numpy_side_number():
+    """The UNMODIFIED reference's own numpy / numba path cannot run on the GPU box (it is not there); it was timed in
+    the build container where /root/reference is mounted (tools/time_reference_here.py) and is quoted from
+    profiles/ as a stated side number next to the C port that is timed live."""
+    for name in ('r02_reference_numpy_timing.json', 'r01_reference_numpy_timing.json'):
+        try:
+            d = json.load(open(os.path.join(ROOT, 'profiles', name)))
+            c2 = [c for c in d['cases'] if c['case'].startswith('C2')][0]
+            out = {'updates_per_s_one_core': c2['updates_per_s_one_core'], 'case': c2['case'],
+                   'where': d['where'], 'source': 'profiles/' + name}
+            if 'pool' in d:
+                out['pool'] = d['pool']
+            return out
+        except Exception:
+            continue
+    return None
 
 
 def workload_config(args, base):
@@ -215,7 +249,10 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
-        os.environ['NCCL_DEBUG'] = os.environ.get('MALI_NCCL_DEBUG', 'WARN')   # keep stdout to the one JSON line
+        # NCCL's own log (rank / channel lines) goes to stderr, whatever level the launcher asked for (INFO if it did
+        # not say): stdout carries the one JSON line only
+        os.environ.setdefault('NCCL_DEBUG', 'INFO')
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=dev)
 
     def barrier():
@@ -297,16 +334,18 @@ def main():
     fs_ms_mean = fs_ms / max(fs_n, 1)
     alg_bytes = algorithmic_bytes_per_column(base) * ncol
     achieved = alg_bytes / (fs_ms_mean * 1e-3) / 1e9
-    traffic = None
-    try:    # DRAM bytes per launch from the committed ncu capture of this very configuration (profiles/)
+    traffic, traffic_src = None, None
+    try:    # DRAM bytes per launch from the committed ncu capture of this very configuration (profiles/): ncu cannot
+        # run inside a timed bench, so this field is read from the capture, not measured in this run
         tj = json.load(open(os.path.join(ROOT, 'profiles', 'traffic_latest.json')))
         if int(tj['ncol']) == ncol and tj['fixture'] == args.fixture:
             traffic = float(tj['traffic_bytes_per_launch'])
+            traffic_src = 'from profiles/traffic_latest.json (%s), not measured in this run' % tj.get('source', 'ncu --set full')
     except Exception:
         pass
     roofline = {'kernel': 'fs_gamma_kernel_m<0,1,2> (formal solution + Gamma stage: 3 launches)', 'bound': 'hbm',
                 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
+                'frac': achieved / peak, 'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': alg_bytes, 'mean_launch_ms': fs_ms_mean, 'launches_timed': fs_n,
                 'share_of_step': fs_ms / ms if ms > 0 else None,
                 'note': 'fp64 CUDA-core work binds before HBM on this path (SURVEY.md 7.3-2); see DESIGN.md'}
@@ -454,12 +493,16 @@ def main():
     # ---- CPU baseline on the host cores (rank 0, N = 1)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        threads = os.cpu_count() or 1
-        ncol_cpu = max(1, min(ncol, max(threads, min(4 * threads, 256))))
+        threads = host_threads()
+        cpu_oracle_rate(base, threads, 1, col0=col_global0)     # first touch
+        _, dt_cal, _, _ = cpu_oracle_rate(base, threads, 1, col0=col_global0)
+        per_thread = int(20.0 / max(dt_cal * iters, 1e-6))          # about 20 s of CPU work
+        ncol_cpu = max(1, min(ncol, threads * max(1, min(16, per_thread))))
         rate, dt, th, ctxs = cpu_oracle_rate(base, ncol_cpu, iters, col0=col_global0)
         cpu = {'value': rate, 'unit': UNIT, 'cores': th, 'kind': 'port',
                'sample': '%d of the %d synthetic columns x %d MALI iterations, oracle C restatement with OpenMP '
-                         'over columns, %.1f s' % (ncol_cpu, ncol, iters, dt)}
+                         'over columns, %.1f s' % (ncol_cpu, ncol, iters, dt),
+               'reference_numpy': reference_numpy_side_number()}
 
     # ---- BASELINE configs 1/2 on the side: one CaII/FALC column to convergence (latency-bound by construction)
     single = None
@@ -509,6 +552,7 @@ def main():
                     break
             barrier()
             dt = max_over_ranks(time.perf_counter() - t0)
+            eng.raise_on_faults()
             its = eng.t_iter.cpu().numpy().astype(np.int64)
             tot = torch.tensor([float(its.sum()), float(its.max()), float(-its.min()),
                                 float((eng.t_done.cpu().numpy() != 0).sum())], dtype=torch.float64, device=dev)
@@ -572,6 +616,8 @@ def main():
                             break
                 barrier()
                 times.append(max_over_ranks(time.perf_counter() - t0))
+            if mine:
+                e3.raise_on_faults(0, len(mine))
             ok = True
             if mine:
                 its = e3.t_iter.cpu().numpy()[:len(mine)]

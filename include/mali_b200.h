@@ -106,7 +106,9 @@ typedef struct {
     int32_t *status;   /* [ncol] bit 0: a singular / non-finite statistical-equilibrium system was met;
                           bit 1: an opacity / optical-depth step left [2^-1000, 2^1000] (formal solution invalid) */
     int32_t *iter;     /* [ncol] iterations done by mali_iterate */
-    int32_t *done;     /* [ncol] non-zero: column is skipped by the compute entry points (converged) */
+    int32_t *done;     /* [ncol] mali_iterate only: 1 = converged, 2 = stopped on a fault (status != 0 or NaN); such
+                          columns are skipped by the remaining iterations.  The per-call entry points
+                          (mali_formal_sol_gamma, mali_stat_equil) ignore it and always recompute, like the reference */
 } mali_buffers;
 
 const char *mali_last_error(void);

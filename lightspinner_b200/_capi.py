@@ -86,6 +86,9 @@ def load(path=None):
     return L
 
 
-def check(code):
+def check(code, lib=None):
+    """Raise MaliError for a non-zero return code.  `lib`: the library that produced it (the message lives in a
+    thread-local of that very .so; model-specific variants are separate libraries)."""
     if code != 0:
-        raise MaliError(code, load().mali_last_error().decode('utf-8', 'replace'))
+        L = load() if lib is None else lib
+        raise MaliError(code, L.mali_last_error().decode('utf-8', 'replace'))

@@ -342,6 +342,7 @@ class BatchContext:
         torch.cuda.synchronize(self._engine.device)
         for c in self.contexts:
             c._pull_pops()
+        self._engine.raise_on_faults()      # LinAlgError / FloatingPointError, as the reference's loop would raise
         return self._engine.t_iter.cpu().numpy().copy()
 
     def close(self):

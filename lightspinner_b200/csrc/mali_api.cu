@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -64,8 +65,8 @@ __global__ void col_zero_bits_kernel(unsigned long long *bits, const int32_t *do
 
 // Per-column loop control of mali_iterate (test.py:23-28): phase 0 = after the formal solution: ++iter;
 // phase 1 = after stat_equil: convergence test.
-__global__ void iterate_ctl_kernel(int phase, double *dJ, double *dPops, int32_t *iter, int32_t *done, double tolJ,
-                                   double tolPops, int col0, int ncol)
+__global__ void iterate_ctl_kernel(int phase, double *dJ, double *dPops, int32_t *iter, int32_t *done,
+                                   const int32_t *status, double tolJ, double tolPops, int col0, int ncol)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncol) return;
@@ -73,10 +74,12 @@ __global__ void iterate_ctl_kernel(int phase, double *dJ, double *dPops, int32_t
     if (done[col] != 0) return;
     if (phase == 0) {
         iter[col] += 1;
-    } else if (tolJ >= 0.0) {
+    } else {
         const double a = dJ[col], b = dPops[col];
-        if (!(a > tolJ || b > tolPops)) done[col] = 1;  // the negation of `while dJ > 2e-3 or dPops > 1e-3`
-        if (a != a || b != b) done[col] = 2;            // NaN: stop touching the column, flag it
+        if (tolJ >= 0.0 && !(a > tolJ || b > tolPops)) done[col] = 1;  // the negation of `while dJ > 2e-3 or dPops > 1e-3`
+        // a singular system / a formal-solver domain fault (status) or a NaN: stop touching the column and flag it
+        // (the reference raises at this point; the host wrapper turns done == 2 into the same exceptions)
+        if (a != a || b != b || status[col] != 0) done[col] = 2;
     }
 }
 
@@ -127,8 +130,10 @@ __global__ void __launch_bounds__(32, spec_class_warps(CLS)) fs_gamma_kernel_m(c
 static const SpecEntry *find_spec(const std::string &key)
 {
     static std::map<std::string, const SpecEntry *> index;
-    if (index.empty())
+    static std::once_flag once;
+    std::call_once(once, [] {
         for (const SpecEntry *e = kSpecRegistry; e->key; ++e) index[e->key] = e;
+    });
     auto it = index.find(key);
     return it == index.end() ? nullptr : it->second;
 }
@@ -138,15 +143,9 @@ static cudaError_t launch_mega(const FsCommon &c, const std::vector<TileR<spec_c
                                size_t smem, cudaStream_t st, long long *launches)
 {
     using MP = MegaParams<CLS>;
-    static thread_local MP *P = nullptr;
-    static thread_local bool attr = false;
+    static thread_local MP *P = nullptr;   // host-side parameter block (31 KB): reused, the launch copies it
     if (!P) P = new MP();
     auto kern = fs_gamma_kernel_m<CLS>;
-    if (smem > 48 * 1024 && !attr) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return e;
-        attr = true;
-    }
     P->c = c;
     const int nt = (int)tiles.size();
     for (int t0 = 0; t0 < nt; t0 += MP::kMaxTiles) {
@@ -249,6 +248,12 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
     CU(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) return fail(MALI_EINVAL, "device %d out of range (%d devices)", device, ndev);
     CU(cudaSetDevice(device));
+    // the opt-in to more than 48 KB of dynamic shared memory is a per-device function attribute: set it for the
+    // device this model lives on (deep columns need it), every time a model is created there
+    CU(cudaFuncSetAttribute(fs_gamma_kernel_m<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CU(cudaFuncSetAttribute(fs_gamma_kernel_m<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CU(cudaFuncSetAttribute(fs_gamma_kernel_m<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CU(cudaFuncSetAttribute(fs_gamma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 
     auto *m = new mali_model();
     m->device = device;
@@ -280,11 +285,12 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
     for (int t = 0; t < d->Ntrans; ++t) {
         const int32_t *tr = &m->trans[(size_t)t * 6];
         const bool bad = tr[0] < 0 || tr[0] >= d->Natom || tr[1] < 0 || tr[2] < 0 || tr[1] >= m->Nlevel[tr[0]] ||
-                         tr[2] >= m->Nlevel[tr[0]] || tr[1] == tr[2] || tr[4] < 0 || tr[5] < 2 ||
+                         tr[2] >= m->Nlevel[tr[0]] || tr[1] == tr[2] || tr[4] < 0 || tr[5] < 1 ||
                          tr[4] + tr[5] > d->Nspect;
         if (bad) {
             delete m;
-            return fail(MALI_EINVAL, "transition %d: inconsistent descriptor", t);
+            return fail(MALI_EINVAL, "transition %d: inconsistent descriptor (atom %d, levels %d -> %d of %d, wavelengths [%d, %d) of %d)",
+                        t, tr[0], tr[1], tr[2], (tr[0] >= 0 && tr[0] < d->Natom) ? m->Nlevel[tr[0]] : -1, tr[4], tr[4] + tr[5], d->Nspect);
         }
         m->toff[t + 1] = m->toff[t] + tr[5];
     }
@@ -883,11 +889,6 @@ static int launch_fs(const mali_model *m, const mali_buffers *b, int col0, int n
         FsParams p = make_fs_params(m, b, col0, ncol, wpb);
         const size_t smem = (size_t)p.smemPerWarp * wpb * sizeof(double);
         if (smem > 227 * 1024) return fail(MALI_ELIMIT, "tile needs %zu B of shared memory", smem);
-        static bool attr_set = false;
-        if (smem > 48 * 1024 && !attr_set) {
-            CU(cudaFuncSetAttribute(fs_gamma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            attr_set = true;
-        }
         const int nt = (int)m->genericTiles.size();
         p.blocksPerCol = (nt + wpb - 1) / wpb;
         fs_gamma_kernel<<<(unsigned)(p.blocksPerCol * ncol), 32 * wpb, smem, st>>>(p);
@@ -984,7 +985,11 @@ int mali_formal_sol_gamma(const mali_model *m, const mali_buffers *b, int32_t co
     if (int r = check_range(m, b, col0, ncol, "mali_formal_sol_gamma")) return r;
     if (!b->colconst || !b->pops || !b->J || !b->I || !b->Gamma || !b->scratch || !b->dJ)
         return fail(MALI_EINVAL, "mali_formal_sol_gamma: null buffer");
-    return launch_fs(m, b, col0, ncol, (cudaStream_t)stream);
+    // the done mask belongs to mali_iterate: a per-call formal solution always recomputes, like the reference
+    mali_buffers bb = *b;
+    bb.done = nullptr;
+    bb.iter = nullptr;
+    return launch_fs(m, &bb, col0, ncol, (cudaStream_t)stream);
 }
 
 int mali_stat_equil(const mali_model *m, const mali_buffers *b, int32_t col0, int32_t ncol, void *stream)
@@ -992,7 +997,10 @@ int mali_stat_equil(const mali_model *m, const mali_buffers *b, int32_t col0, in
     if (int r = check_range(m, b, col0, ncol, "mali_stat_equil")) return r;
     if (!b->colconst || !b->pops || !b->Gamma || !b->dPops || !b->status)
         return fail(MALI_EINVAL, "mali_stat_equil: null buffer");
-    return launch_se(m, b, col0, ncol, nullptr, 0, (cudaStream_t)stream);
+    mali_buffers bb = *b;
+    bb.done = nullptr;
+    bb.iter = nullptr;
+    return launch_se(m, &bb, col0, ncol, nullptr, 0, (cudaStream_t)stream);
 }
 
 int mali_iterate(const mali_model *m, const mali_buffers *b, int32_t col0, int32_t ncol, int32_t max_iter, double tolJ,
@@ -1006,9 +1014,9 @@ int mali_iterate(const mali_model *m, const mali_buffers *b, int32_t col0, int32
     const int nb = (ncol + 127) / 128;
     for (int it = 0; it < max_iter; ++it) {
         if (int r = launch_fs(m, b, col0, ncol, st)) return r;
-        iterate_ctl_kernel<<<nb, 128, 0, st>>>(0, b->dJ, b->dPops, b->iter, b->done, tolJ, tolPops, col0, ncol);
+        iterate_ctl_kernel<<<nb, 128, 0, st>>>(0, b->dJ, b->dPops, b->iter, b->done, b->status, tolJ, tolPops, col0, ncol);
         if (int r = launch_se(m, b, col0, ncol, b->iter, 4, st)) return r;
-        iterate_ctl_kernel<<<nb, 128, 0, st>>>(1, b->dJ, b->dPops, b->iter, b->done, tolJ, tolPops, col0, ncol);
+        iterate_ctl_kernel<<<nb, 128, 0, st>>>(1, b->dJ, b->dPops, b->iter, b->done, b->status, tolJ, tolPops, col0, ncol);
         m->launches += 2;
     }
     CU(cudaGetLastError());
@@ -1075,7 +1083,10 @@ int mali_fp64_peak(int32_t iters, double *scratch_dev, double *ops_per_second)
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0));
     CU(cudaEventCreate(&e1));
-    const int blocks = 148 * 8, threads = 256;
+    int dev = 0, sms = 148;
+    CU(cudaGetDevice(&dev));
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int blocks = sms * 8, threads = 256;
     fp64_peak_kernel<<<blocks, threads>>>(iters / 8 + 1, 1.0, scratch_dev);  // warm-up
     CU(cudaEventRecord(e0));
     fp64_peak_kernel<<<blocks, threads>>>(iters, 1.0, scratch_dev);

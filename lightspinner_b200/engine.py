@@ -37,9 +37,9 @@ class MaliEngine:
         self.lib = _capi.load(lib_path)
         self._handle = C.c_void_p()
         desc = self.mt.desc()
-        _capi.check(self.lib.mali_model_create(C.byref(desc), self.device.index, C.byref(self._handle)))
+        self._check(self.lib.mali_model_create(C.byref(desc), self.device.index, C.byref(self._handle)))
         self.lay = _capi.Layout()
-        _capi.check(self.lib.mali_model_layout(self._handle, C.byref(self.lay)))
+        self._check(self.lib.mali_model_layout(self._handle, C.byref(self.lay)))
         L = self.lay
         f64 = dict(dtype=torch.float64, device=self.device)
         i32 = dict(dtype=torch.int32, device=self.device)
@@ -61,6 +61,9 @@ class MaliEngine:
         self.chunk = max(1, min(int(max_upload_chunk), n))
         self._staging = None
         self._pinned = None
+
+    def _check(self, code):
+        _capi.check(code, self.lib)
 
     def close(self):
         if self._handle:
@@ -120,10 +123,10 @@ class MaliEngine:
                 raise ValueError('aDamp / vBroad / vlos must be [Ntrans, Nspace] / [Natom, Nspace] / [Nspace]')
             dev = [torch.from_numpy(np.ascontiguousarray(a)).to(self.device) for a in aux]
             with torch.cuda.device(self.device):
-                _capi.check(self.lib.mali_upload_columns_nophi(self._handle, C.byref(self.bufs), col0 + c0, len(chunk),
+                self._check(self.lib.mali_upload_columns_nophi(self._handle, C.byref(self.bufs), col0 + c0, len(chunk),
                                                                C.c_void_p(pinned.data_ptr()),
                                                                C.c_void_p(staging.data_ptr()), self._stream()))
-                _capi.check(self.lib.mali_compute_phi(self._handle, C.byref(self.bufs), col0 + c0, len(chunk),
+                self._check(self.lib.mali_compute_phi(self._handle, C.byref(self.bufs), col0 + c0, len(chunk),
                                                       *(C.c_void_p(t.data_ptr()) for t in dev), self._stream()))
             torch.cuda.current_stream(self.device).synchronize()
 
@@ -135,10 +138,10 @@ class MaliEngine:
         if ncol * self.lay.hostpack > staging.numel():
             raise ValueError('staging buffer too small for %d columns' % ncol)
         with torch.cuda.device(self.device):
-            _capi.check(self.lib.mali_upload_columns_nophi(self._handle, C.byref(self.bufs), col0, ncol,
+            self._check(self.lib.mali_upload_columns_nophi(self._handle, C.byref(self.bufs), col0, ncol,
                                                            C.c_void_p(host_prefix_pinned.data_ptr()),
                                                            C.c_void_p(staging.data_ptr()), self._stream()))
-            _capi.check(self.lib.mali_compute_phi(self._handle, C.byref(self.bufs), col0, ncol,
+            self._check(self.lib.mali_compute_phi(self._handle, C.byref(self.bufs), col0, ncol,
                                                   C.c_void_p(aDamp.data_ptr()), C.c_void_p(vBroad.data_ptr()),
                                                   C.c_void_p(vlos.data_ptr()), self._stream()))
 
@@ -149,26 +152,26 @@ class MaliEngine:
         if ncol * self.lay.hostpack > staging.numel():
             raise ValueError('staging buffer too small for %d columns' % ncol)
         with torch.cuda.device(self.device):
-            _capi.check(self.lib.mali_upload_columns(self._handle, C.byref(self.bufs), col0, ncol,
+            self._check(self.lib.mali_upload_columns(self._handle, C.byref(self.bufs), col0, ncol,
                                                      C.c_void_p(host_pinned.data_ptr()),
                                                      C.c_void_p(staging.data_ptr()), self._stream()))
 
     def repack_from_staging(self, staging, col0, ncol):
         """Device re-layout only (the staging tensor already holds host-pack blocks on the device)."""
         with torch.cuda.device(self.device):
-            _capi.check(self.lib.mali_upload_columns(self._handle, C.byref(self.bufs), col0, ncol, None,
+            self._check(self.lib.mali_upload_columns(self._handle, C.byref(self.bufs), col0, ncol, None,
                                                      C.c_void_p(staging.data_ptr()), self._stream()))
 
     # ------------------------------------------------------------------ the hot path
     def formal_sol_gamma_async(self, col0=0, ncol=None):
         ncol = self.ncol - col0 if ncol is None else ncol
         with torch.cuda.device(self.device):
-            _capi.check(self.lib.mali_formal_sol_gamma(self._handle, C.byref(self.bufs), col0, ncol, self._stream()))
+            self._check(self.lib.mali_formal_sol_gamma(self._handle, C.byref(self.bufs), col0, ncol, self._stream()))
 
     def stat_equil_async(self, col0=0, ncol=None):
         ncol = self.ncol - col0 if ncol is None else ncol
         with torch.cuda.device(self.device):
-            _capi.check(self.lib.mali_stat_equil(self._handle, C.byref(self.bufs), col0, ncol, self._stream()))
+            self._check(self.lib.mali_stat_equil(self._handle, C.byref(self.bufs), col0, ncol, self._stream()))
 
     def formal_sol_gamma_matrices(self, col0=0, ncol=None):
         """One Lambda iteration for columns [col0, col0+ncol) (default: all); returns their dJ (device->host read)."""
@@ -199,8 +202,23 @@ class MaliEngine:
         """The loop of test.py:20-29 on the device with per-column convergence (tolJ < 0: fixed iteration count)."""
         ncol = self.ncol - col0 if ncol is None else ncol
         with torch.cuda.device(self.device):
-            _capi.check(self.lib.mali_iterate(self._handle, C.byref(self.bufs), col0, ncol, int(max_iter),
+            self._check(self.lib.mali_iterate(self._handle, C.byref(self.bufs), col0, ncol, int(max_iter),
                                               float(tolJ), float(tolPops), self._stream()))
+
+    def raise_on_faults(self, col0=0, ncol=None):
+        """What the reference would have raised during the loop: LinAlgError for a singular statistical-equilibrium
+        system (status bit 0), FloatingPointError for an opacity / optical-depth step outside the formal solver's
+        domain (status bit 1) or a NaN in dJ / dPops (done == 2).  mali_iterate stops such a column where it fails."""
+        ncol = self.ncol - col0 if ncol is None else ncol
+        status = self.t_status[col0:col0 + ncol].cpu().numpy()
+        done = self.t_done[col0:col0 + ncol].cpu().numpy()
+        if (status & 1).any():
+            bad = col0 + np.nonzero(status & 1)[0]
+            raise np.linalg.LinAlgError('singular statistical-equilibrium system in column(s) %s' % bad[:8].tolist())
+        if (status & 2).any() or (done == 2).any():
+            bad = col0 + np.nonzero((status & 2) | (done == 2))[0]
+            raise FloatingPointError('non-finite result or opacity / optical-depth step outside the formal solver\'s '
+                                     'numeric domain in column(s) %s' % bad[:8].tolist())
 
     def reset_iteration_state(self):
         self.t_iter.zero_()
@@ -211,17 +229,17 @@ class MaliEngine:
 
     # ------------------------------------------------------------------ measurement
     def profile_begin(self, max_launches):
-        _capi.check(self.lib.mali_profile_begin(self._handle, int(max_launches)))
+        self._check(self.lib.mali_profile_begin(self._handle, int(max_launches)))
 
     def profile_end(self):
         """(summed device ms of the fs_gamma_kernel launches since profile_begin, number of launches)"""
         ms, n = C.c_double(0.0), C.c_int32(0)
-        _capi.check(self.lib.mali_profile_end(self._handle, C.byref(ms), C.byref(n)))
+        self._check(self.lib.mali_profile_end(self._handle, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
     def model_info(self):
         out = (C.c_int32 * 8)()
-        _capi.check(self.lib.mali_model_info(self._handle, out))
+        self._check(self.lib.mali_model_info(self._handle, out))
         keys = ('ntile', 'spec_tiles', 'generic_tiles', 'max_slots', 'max_levels', 'row_stride', 'smem_per_warp', 'tma')
         return dict(zip(keys, list(out)))
 
@@ -259,7 +277,7 @@ class MaliEngine:
         N = self.mt.Nspace
         out = torch.empty(3, N, dtype=torch.float64, device=self.device)
         with torch.cuda.device(self.device):
-            _capi.check(self.lib.mali_uv(self._handle, C.byref(self.bufs), col, t, la, mu, int(bool(toFrom)),
+            self._check(self.lib.mali_uv(self._handle, C.byref(self.bufs), col, t, la, mu, int(bool(toFrom)),
                                          C.c_void_p(out[0].data_ptr()), C.c_void_p(out[1].data_ptr()),
                                          C.c_void_p(out[2].data_ptr()), self._stream()))
         o = out.cpu().numpy()

@@ -97,6 +97,9 @@ class ModelTables:
             if w_given is not None:
                 w = w_given[o:o + Nlam]
             else:
+                if Nlam < 2:
+                    raise ValueError('transition %d has %d wavelength(s): its quadrature weights need at least 2 '
+                                     '(a wavelength shard that clips a transition must pass wlambda_table)' % (t, Nlam))
                 w = np.empty(Nlam)
                 w[0] = 0.5 * (wl[1] - wl[0]) * dopplerWidth          # :185
                 w[-1] = 0.5 * (wl[-1] - wl[-2]) * dopplerWidth       # :187

@@ -500,6 +500,16 @@ void lso_iterate_batch(const lso_model *m, lso_column *cols, int ncol, int niter
     }
 }
 
+void lso_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0)
+        omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int lso_max_threads(void)
 {
 #ifdef _OPENMP

@@ -87,6 +87,8 @@ def lib():
         L.lso_stat_equil.argtypes = [C.POINTER(_Model), C.POINTER(_Column), _ip]
         L.lso_iterate_batch.argtypes = [C.POINTER(_Model), C.POINTER(_Column), C.c_int, C.c_int, C.c_int, _dp, _dp]
         L.lso_max_threads.restype = C.c_int
+        L.lso_set_threads.argtypes = [C.c_int]
+        L.lso_set_threads.restype = None
         _lib = L
     return _lib
 
@@ -295,6 +297,11 @@ def max_threads():
     return lib().lso_max_threads()
 
 
+def set_threads(n):
+    """OpenMP thread count of iterate_batch (torchrun exports OMP_NUM_THREADS=1 for nproc > 1)."""
+    lib().lso_set_threads(int(n))
+
+
 def planck_bc(temperature, wavelength):
     """[Nspect, 2] table of planck(T[-2:], wav) (formal_solver.py:206) evaluated by the C restatement."""
     out = np.zeros((len(wavelength), 2))
@@ -305,4 +312,4 @@ def planck_bc(temperature, wavelength):
 
 
 __all__ = ['OracleContext', 'build', 'lib', 'w2', 'planck', 'piecewise_linear_1d', 'model_tables',
-           'column_tables', 'iterate_batch', 'max_threads', 'planck_bc', 'math']
+           'column_tables', 'iterate_batch', 'max_threads', 'set_threads', 'planck_bc', 'math']

@@ -12,7 +12,13 @@ from them: dJ/dPops history and J, I, Gamma, n at selected iterations of the tes
 
 Fixtures
   c1_falc_ca        test.py's problem: CaII active, H passive, FALC, 5 rays (BASELINE configs 0/1); run to convergence
-  c2_falc_cah       CaII + H active, FALC, 5 rays (C2 of SURVEY 8); 12 iterations + iteration count to convergence
+  c2_falc_cah       CaII + H active, FALC, 5 rays (C2 of SURVEY 8); run to convergence (79 iterations)
+  c2v_jitter_cah_0, c2v_jitter_cah_1
+                    BASELINE config 4's recipe, columns 0 and 1: T / ne jitter and non-zero vlos applied
+                    before convert_scales, CaII + H active, 5 rays; run to convergence
+  stress_r10_d512   BASELINE config 5's recipe, wavelength-reduced: every line's NlambdaGen x1 (the config says x10),
+                    quadrature(10), FALC interpolated to 512 depths, CaII active; 8 iterations.  vlos = 0, so the line
+                    profiles are stored once per (wavelength, depth) (`p_phi_compact`; helpers.load_golden expands them)
   c1v_jitter_ca3    CaII active, 3 rays, config-4 jitter recipe column 0 (T, ne, non-zero vlos): phi differs up/down
   rf_k40p, rf_k10m  response_fn.py columns: T[k] +/- 25 K, warm-started from the converged c1 populations
   units             formal-solver / w2 / planck / uv known answers
@@ -103,8 +109,45 @@ def make_c2(ref):
     atmos, spect, eqPops, bg = build_falc_setup(active=('Ca', 'H'), nrays=5)
     ctx = ref['rh_method'].Context(atmos, spect, eqPops, bg)
     p = problem_from_reference_context(ctx)
-    r = run(ctx, 12, keep_full={1, 5}, keep_small={4, 6, 8, 12})
+    r = run(ctx, 1000, keep_full={1, 5}, keep_small={4, 6, 8, 12, 20, 40, 60, 79})
     save('c2_falc_cah', p, r)
+
+
+def make_c2v(ref, col, with_phi):
+    atmos, spect, eqPops, bg = build_falc_setup(active=('Ca', 'H'), nrays=5, modify_constructor=jitter_modifier(col, ref))
+    ctx = ref['rh_method'].Context(atmos, spect, eqPops, bg)
+    p = problem_from_reference_context(ctx)
+    r = run(ctx, 1000, keep_full=set(), keep_small={1, 4, 6, 12, 20, 40})
+    if not with_phi:
+        # 4.9 MB of incompressible profiles: column 1 keeps what compute_phi consumes (aDamp, vBroad, vlos are in the
+        # problem); tests re-form phi from them (helpers.recompute_phi = rh_method.py:198-243) or on the device
+        p.pop('phi')
+        p['phi_recompute'] = np.array(1)
+    save('c2v_jitter_cah_%d' % col, p, r)
+
+
+def make_stress(ref, refine=1, nrays=10, ndepth=512, niter=8):
+    from oracle.refharness import falc_interpolated_constructor
+
+    def refine_lines(models, ref):
+        for m in models:
+            for l in m.lines:
+                l.NlambdaGen *= refine                       # SURVEY 8d item 5 (the full config uses 10)
+            ref['atomic_model'].reconfigure_atom(m)          # atomic_model.py:71-72
+
+    atmos, spect, eqPops, bg = build_falc_setup(active=('Ca',), nrays=nrays, modify_atoms=refine_lines,
+                                                constructor=lambda: falc_interpolated_constructor(ndepth))
+    ctx = ref['rh_method'].Context(atmos, spect, eqPops, bg)
+    p = problem_from_reference_context(ctx)
+    r = run(ctx, niter, keep_full={1}, keep_small={4, 5, 6, 8})
+    del r['final_J']
+    # vlos == 0: phi[la, mu, toFrom, k] does not depend on (mu, toFrom); keep one copy per (la, k)
+    assert not np.any(p['vlos'])
+    N, R = int(p['Nspace']), int(p['Nrays'])
+    full = p.pop('phi').reshape(-1, R, 2, N)
+    assert np.array_equal(full, np.broadcast_to(full[:, :1, :1, :], full.shape))
+    p['phi_compact'] = np.ascontiguousarray(full[:, 0, 0, :])
+    save('stress_r%d_d%d' % (nrays, ndepth), p, r)
 
 
 def make_c1v(ref):
@@ -185,4 +228,9 @@ if __name__ == '__main__':
         make_c2(ref)
     if not which or 'c1v' in which:
         make_c1v(ref)
+    if not which or 'c2v' in which:
+        make_c2v(ref, 0, True)
+        make_c2v(ref, 1, False)
+    if not which or 'stress' in which:
+        make_stress(ref)
     print('done in %.0f s' % (time.time() - t0))

@@ -13,7 +13,48 @@ def load_golden(name):
     r = {k[2:]: z[k] for k in z.files if k.startswith('r_')}
     for k in ('Nspace', 'Nrays', 'Nspect'):
         p[k] = int(p[k])
+    if 'phi_compact' in p:      # vlos == 0 fixtures keep one profile per (wavelength, depth): expand to the reference's shape
+        c = p.pop('phi_compact')
+        p['phi'] = np.ascontiguousarray(np.broadcast_to(c[:, None, None, :], (c.shape[0], p['Nrays'], 2, c.shape[1]))).reshape(-1)
+    if 'phi_recompute' in p:    # fixture without the (incompressible) profiles: re-form them as the reference does
+        p.pop('phi_recompute')
+        p['phi'], p['wphi'] = recompute_phi(p)
     return p, r
+
+
+def recompute_phi(p):
+    """ComputationalTransition.compute_phi (rh_method.py:198-243) from a problem's aDamp / vBroad / vlos with the
+    reference's own expressions (scipy wofz): (phi concat [Nlam, Nrays, 2, N] per line, wphi [Ntrans, N])."""
+    from scipy import special
+    CLight = 2.99792458E+08
+    N, R = int(p['Nspace']), int(p['Nrays'])
+    trans = np.asarray(p['trans']).reshape(-1, 6)
+    wav, muz, wmu = np.asarray(p['wavelength']), np.asarray(p['muz']), np.asarray(p['wmu'])
+    sqrtPi = np.sqrt(np.pi)
+    phis, wphi = [], np.zeros((trans.shape[0], N))
+    for t, (atom, i, j, isLine, Nblue, Nlam) in enumerate(trans):
+        if not isLine:
+            continue
+        lambda0 = np.asarray(p['linepar']).reshape(-1, 4)[t, 3]
+        vBroad, aDamp = np.asarray(p['vBroad'])[atom], np.asarray(p['aDamp'])[t]
+        wl = wav[Nblue:Nblue + Nlam]
+        w = np.zeros(Nlam)
+        w[0], w[-1], w[1:-1] = 0.5 * (wl[1] - wl[0]), 0.5 * (wl[-1] - wl[-2]), 0.5 * (wl[2:] - wl[:-2])
+        w = (CLight / lambda0) * w
+        phi = np.zeros((Nlam, R, 2, N))
+        wPhi = np.zeros(N)
+        vlosDop = np.stack([muz[mu] * np.asarray(p['vlos']) / vBroad for mu in range(R)])
+        for la in range(Nlam):
+            v = (wl[la] - lambda0) * CLight / (vBroad * lambda0)
+            for mu in range(R):
+                wlamu = w * 0.5 * wmu[mu]
+                for toFrom, sign in enumerate([-1.0, 1.0]):
+                    vk = v + sign * vlosDop[mu]
+                    phi[la, mu, toFrom, :] = special.wofz(vk + 1j * aDamp).real / (sqrtPi * vBroad)
+                    wPhi[:] += phi[la, mu, toFrom, :] * wlamu[la]
+        phis.append(phi.reshape(-1))
+        wphi[t] = 1.0 / wPhi
+    return (np.concatenate(phis) if phis else np.zeros(0)), wphi
 
 
 def load_units():

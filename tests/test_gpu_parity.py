@@ -185,22 +185,6 @@ def test_c1_free_running_to_convergence(eng_mod):
     eng.close()
 
 
-def test_c2_two_atoms_fixed_iterations(eng_mod):
-    p, r = load_golden('c2_falc_cah')
-    eng = eng_mod.MaliEngine(p, 1)
-    eng.upload([p])
-    for i in range(1, 13):
-        dJ = float(eng.formal_sol_gamma_matrices()[0])
-        dP = float(eng.stat_equil()[0]) if i > 3 else 1.0
-        assert np.allclose([dJ, dP], r['hist'][i - 1], rtol=1e-6)
-        if 'it%d_n' % i in r:
-            e_n = relerr(eng.n(0), r['it%d_n' % i])
-            e_I = relerr(eng.I(0), r['it%d_I' % i])
-            print('C2 iteration %d: rel err n %.2e  I %.2e' % (i, e_n, e_I))
-            assert e_n < 5e-9 and e_I < 5e-9
-    eng.close()
-
-
 def test_deterministic_and_batch_equals_single(eng_mod):
     """Run twice -> bitwise equal; a 3-column batch (response-function columns share the model) equals the
     single-column runs bit for bit (no cross-column arithmetic, fixed reduction order)."""
