@@ -2,25 +2,31 @@
 
     python -m lightspinner_b200.build [--force] [--verbose]
 
---fmad=false is part of the numerical contract (see csrc/mali_kernels.cuh); -lineinfo keeps the ncu source
-page usable.  The built library lives in lightspinner_b200/_lib/ (git-ignored, travels with gpurun).
+--fmad=false is part of the numerical contract (see csrc/mali_device.cuh); -lineinfo keeps the ncu source page
+usable.  Four translation units -- the host API with the small kernels, and one per register class of the
+structure-specialised formal-solution kernels -- are compiled in parallel and linked into one shared library, which
+lives in lightspinner_b200/_lib/ (git-ignored, travels with gpurun).
 """
 import os
 import shutil
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIBDIR = os.path.join(HERE, '_lib')
 LIB = os.path.join(LIBDIR, os.environ.get('MALI_LIB_NAME', 'libmali_b200.so'))
-SOURCES = ['mali_api.cu']
-DEPS = ['mali_api.cu', 'mali_kernels.cuh', 'mali_types.cuh', 'exp_table.inc', 'mali_solve.h', 'mali_voigt.h', 'mali_fs_spec.cuh', 'mali_fs_step.inc', 'spec_instances.inc', os.path.join('..', '..', 'include', 'mali_b200.h')]
+DEPS = ['mali_api.cu', 'mali_fs_class.cu', 'mali_fs_launch.h', 'mali_kernels.cuh', 'mali_device.cuh', 'mali_types.cuh',
+        'exp_table.inc', 'mali_solve.h', 'mali_voigt.h', 'mali_fs_spec.cuh', 'mali_fs_step.inc', 'spec_instances.inc',
+        os.path.join('..', '..', 'include', 'mali_b200.h')]
 
 EXTRA = os.environ.get('MALI_NVCC_EXTRA', '').split()
 NVCC_FLAGS = EXTRA + ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '--fmad=false', '-std=c++20',
-              '-shared', '-Xcompiler', '-fPIC', '-Xcompiler', '-ffp-contract=off', '-Xcompiler', '-O2',
-              '-cudart', 'static']
+                      '-Xcompiler', '-fPIC', '-Xcompiler', '-ffp-contract=off', '-Xcompiler', '-O2']
+# (object name, source, extra flags)
+UNITS = [('api', 'mali_api.cu', []), ('fs0', 'mali_fs_class.cu', ['-DMALI_CLS=0']),
+         ('fs1', 'mali_fs_class.cu', ['-DMALI_CLS=1']), ('fs2', 'mali_fs_class.cu', ['-DMALI_CLS=2'])]
 
 
 def nvcc_path():
@@ -37,22 +43,45 @@ def stale():
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS) or os.path.getmtime(__file__) > t
 
 
-def build(force=False, verbose=False, lib=None, spec_inc=None):
-    """Build libmali_b200.so, or (lib, spec_inc given) a model-specific variant with other kernel instances."""
+def build(force=False, verbose=False, lib=None, spec_inc=None, defines=()):
+    """Build libmali_b200.so, or (lib, spec_inc / defines given) a variant with other kernel instances / options."""
     lib = LIB if lib is None else lib
     if lib == LIB and not force and not stale():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
-    extra = ['-DMALI_SPEC_INC="%s"' % spec_inc] if spec_inc else []
-    cmd = [nvcc_path()] + NVCC_FLAGS + extra + (['-Xptxas', '-v'] if verbose else []) + \
-        ['-ccbin', '/usr/bin/g++' if os.path.isfile('/usr/bin/g++') else 'g++'] + \
-        ['-o', lib + '.tmp'] + [os.path.join(CSRC, s) for s in SOURCES]
+    extra = (['-DMALI_SPEC_INC="%s"' % spec_inc] if spec_inc else []) + ['-D' + d for d in defines]
+    nvcc = nvcc_path()
+    ccbin = ['-ccbin', '/usr/bin/g++' if os.path.isfile('/usr/bin/g++') else 'g++']
+    tag = os.path.basename(lib)
+    objdir = os.path.join(LIBDIR, 'obj_' + tag)
+    os.makedirs(objdir, exist_ok=True)
+
+    def compile_unit(u):
+        name, src, flags = u
+        obj = os.path.join(objdir, name + '.o')
+        cmd = [nvcc] + NVCC_FLAGS + extra + flags + (['-Xptxas', '-v'] if verbose else []) + ccbin + \
+            ['-c', '-o', obj, os.path.join(CSRC, src)]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        return obj, res
+
+    with ThreadPoolExecutor(max_workers=len(UNITS)) as ex:
+        results = list(ex.map(compile_unit, UNITS))
+    ok = True
+    for obj, res in results:
+        if verbose or res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+        ok = ok and res.returncode == 0
+    if not ok:
+        raise RuntimeError('nvcc failed building %s' % os.path.basename(lib))
+    cmd = [nvcc, '-shared', '-cudart', 'static', '-gencode', 'arch=compute_100a,code=sm_100a'] + ccbin + \
+        ['-o', lib + '.tmp'] + [obj for obj, _ in results]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
-        raise RuntimeError('nvcc failed building %s' % os.path.basename(lib))
+        raise RuntimeError('link failed for %s' % os.path.basename(lib))
     os.replace(lib + '.tmp', lib)
+    shutil.rmtree(objdir, ignore_errors=True)
     return lib
 
 

@@ -14,7 +14,8 @@
 #include <vector>
 
 #include "../../include/mali_b200.h"
-#include "mali_fs_spec.cuh"
+#include "mali_kernels.cuh"
+#include "mali_fs_launch.h"
 
 using namespace mali;
 
@@ -63,6 +64,25 @@ __global__ void col_zero_bits_kernel(unsigned long long *bits, const int32_t *do
     bits[col] = 0ull;
 }
 
+// First kernel of every formal solution, one block per column: resets dJ and rebuilds the depth-major popsT table
+// (mali_types.cuh) from the heights and the CURRENT populations n[level][k] -- the caller may have edited them since
+// the last call, as the reference's users do through the eqPops alias.
+__global__ void fs_prepare_kernel(unsigned long long *dJbits, const int32_t *done, int col0, double *colconst,
+                                  int64_t colStride, int64_t off_z, int64_t off_popsT, int PW, int N, int sumNlevel,
+                                  const double *pops, int64_t popStride)
+{
+    const int col = col0 + blockIdx.x;
+    if (done != nullptr && done[col] != 0) return;
+    if (threadIdx.x == 0) dJbits[col] = 0ull;
+    double *cc = colconst + (size_t)col * colStride;
+    const double *z = cc + off_z, *n = pops + (size_t)col * popStride;
+    double *pt = cc + off_popsT;
+    for (int idx = threadIdx.x; idx < N * PW; idx += blockDim.x) {
+        const int k = idx / PW, c = idx - k * PW;
+        pt[idx] = c == 0 ? z[k] : (c - 1 < sumNlevel ? n[(size_t)(c - 1) * N + k] : 0.0);
+    }
+}
+
 // Per-column loop control of mali_iterate (test.py:23-28): phase 0 = after the formal solution: ++iter;
 // phase 1 = after stat_equil: convergence test.
 __global__ void iterate_ctl_kernel(int phase, double *dJ, double *dPops, int32_t *iter, int32_t *done,
@@ -86,76 +106,17 @@ __global__ void iterate_ctl_kernel(int phase, double *dJ, double *dPops, int32_t
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------
-// Ahead-of-time instances of the structure-specialised kernel (generated: tools/gen_spec_instances.py; a
-// model-specific library is built with -DMALI_SPEC_INC=\"<file>\" by lightspinner_b200/specialize.py)
-#ifndef MALI_SPEC_INC
-#define MALI_SPEC_INC "spec_instances.inc"
-#endif
-#define MALI_SPEC(ID, KEY, ...)                          \
-    struct SpecTag##ID {                                 \
-        static constexpr TileStruct S = {__VA_ARGS__};   \
-    };
-#include MALI_SPEC_INC
-#undef MALI_SPEC
-#define MALI_SPEC(ID, KEY, ...) {KEY, SpecTag##ID::S.nslot, ID},
-static const SpecEntry kSpecRegistry[] = {
-#include MALI_SPEC_INC
-    {nullptr, 0, 0}};
-#undef MALI_SPEC
-
-namespace mali {
-// One kernel per register class; the structure id of the tile selects the specialised body (uniform switch).
-// blockIdx.x runs over columns, blockIdx.y over (tile, sweep direction): co-resident blocks share a structure, hence
-// one instruction stream per SM.  The down and the up sweep of a tile are independent warps (their partial sums go
-// to separate scratch copies), which doubles the parallelism of small launches and halves the tail of every wave.
-template <int CLS>
-__global__ void __launch_bounds__(32, spec_class_warps(CLS)) fs_gamma_kernel_m(const __grid_constant__ MegaParams<CLS> P)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const TileR<MegaParams<CLS>::NSP> &T = P.tiles[blockIdx.y >> 1];
-    const int dir = blockIdx.y & 1;
-    switch (T.spec) {
-#define MALI_SPEC(ID, KEY, ...)                                                                        \
-    case ID:                                                                                           \
-        if constexpr (spec_class(SpecTag##ID::S.nslot) == CLS) fs_body<SpecTag##ID>(P.c, T, dir, smem_raw); \
-        break;
-#include MALI_SPEC_INC
-#undef MALI_SPEC
-        default:
-            break;
-    }
-}
-}  // namespace mali
-
+// The structure-specialised kernels and their instance registry live in mali_fs_class.cu (one translation unit per
+// register class); tiles are routed to them by structure key.
 static const SpecEntry *find_spec(const std::string &key)
 {
     static std::map<std::string, const SpecEntry *> index;
     static std::once_flag once;
     std::call_once(once, [] {
-        for (const SpecEntry *e = kSpecRegistry; e->key; ++e) index[e->key] = e;
+        for (const SpecEntry *e = mali_fs_registry(); e->key; ++e) index[e->key] = e;
     });
     auto it = index.find(key);
     return it == index.end() ? nullptr : it->second;
-}
-
-template <int CLS>
-static cudaError_t launch_mega(const FsCommon &c, const std::vector<TileR<spec_class_slots(CLS)>> &tiles, int ncol,
-                               size_t smem, cudaStream_t st, long long *launches)
-{
-    using MP = MegaParams<CLS>;
-    static thread_local MP *P = nullptr;   // host-side parameter block (31 KB): reused, the launch copies it
-    if (!P) P = new MP();
-    auto kern = fs_gamma_kernel_m<CLS>;
-    P->c = c;
-    const int nt = (int)tiles.size();
-    for (int t0 = 0; t0 < nt; t0 += MP::kMaxTiles) {
-        const int n = std::min(MP::kMaxTiles, nt - t0);
-        memcpy(P->tiles, tiles.data() + t0, sizeof(tiles[0]) * n);
-        dim3 grid(ncol, 2 * n);
-        kern<<<grid, 32, smem, st>>>(*P);
-        if (launches) *launches += 1;
-    }
-    return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -173,10 +134,10 @@ struct mali_model {
     std::vector<TileR<8>> spec2;
     int specTiles = 0;
     mali_layout lay{};
-    int64_t off_z = 0, off_bbc = 0, off_C = 0, off_nTotal = 0, off_tab = 0, rowStride = 0;
+    int64_t off_z = 0, off_bbc = 0, off_C = 0, off_nTotal = 0, off_tab = 0, off_popsT = 0, rowStride = 0;
+    int popsW = 0;
     int64_t off_jpart = 0, off_part = 0, upOff = 0;
-    int smemPopDoubles = 0, smemZOff = 0, smemLvlOff = 0, smemMbarOff = 0, smemExpOff = 0, smemBytesPerWarp = 0, useBulk = 0;
-    int ringStage[3] = {16, 16, 16};
+    int smemClass[3] = {0, 0, 0};   // shared-memory bytes per warp of the three specialised kernels
     std::vector<CopyJob> cjobs;
     int packChunks = 0;
     // device copies
@@ -185,8 +146,9 @@ struct mali_model {
     double *d_alpha = nullptr, *d_twohc = nullptr, *d_wlacont = nullptr, *d_wlambda = nullptr, *d_zmu = nullptr,
            *d_hw = nullptr;
     int32_t *d_Nlevel = nullptr, *d_lvlOff = nullptr, *d_g2Off = nullptr, *d_trans = nullptr, *d_trPartOff = nullptr,
-            *d_trPartRows = nullptr, *d_genericTiles = nullptr, *d_tileJOff = nullptr, *d_phiTileV = nullptr,
-            *d_phiTileDir = nullptr, *d_phiTileF = nullptr;
+            *d_trPartRows = nullptr, *d_genericTiles = nullptr;
+    TileJ *d_tileJ = nullptr;
+    PhiTile *d_phiTiles = nullptr;
     PhiLine *d_phiLines = nullptr;
     double *d_wavelength = nullptr, *d_muz = nullptr, *d_wmu = nullptr;
     int nPhiLines = 0;
@@ -250,9 +212,9 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
     CU(cudaSetDevice(device));
     // the opt-in to more than 48 KB of dynamic shared memory is a per-device function attribute: set it for the
     // device this model lives on (deep columns need it), every time a model is created there
-    CU(cudaFuncSetAttribute(fs_gamma_kernel_m<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CU(cudaFuncSetAttribute(fs_gamma_kernel_m<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CU(cudaFuncSetAttribute(fs_gamma_kernel_m<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CU(mali_fs_set_attr_0());
+    CU(mali_fs_set_attr_1());
+    CU(mali_fs_set_attr_2());
     CU(cudaFuncSetAttribute(fs_gamma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 
     auto *m = new mali_model();
@@ -341,13 +303,13 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
     // ---- tiles, slots and the tile-major record layout (mali_types.cuh)
     std::vector<std::vector<int32_t>> trRows(d->Ntrans);
     std::vector<PackTile> ptiles;
-    std::vector<int32_t> tileJOff;   // per tile: offset of the J-dagger field inside a depth row
-    std::vector<std::vector<int32_t>> phiV(d->Ntrans), phiDir(d->Ntrans), phiF(d->Ntrans);
+    std::vector<TileJ> tileJ;        // per tile: J-dagger field of the depth-0 record, record stride
+    std::vector<std::vector<PhiTile>> phiT(d->Ntrans);
     std::vector<int32_t> phiTile0(d->Ntrans, -1);
     std::vector<PackSlot> pslots;
     std::vector<PackChunk> pchunks;
     int partRow = 0;
-    int64_t rowOff = 0;
+    int64_t rowOff = 0, rowSum = 0;
     for (int ti = 0; ti < m->ntile; ++ti) {
         const int la0 = ti * Lw, la1 = std::min(d->Nspect, la0 + Lw);
         TileDesc td{};
@@ -378,23 +340,25 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
             m->slots.push_back(s);
             td.nslot++;
         }
-        const int sb = 2 * kVRow * nLine;
+        const int vb = kVRow * nLine;            // one direction's Vij rows
         PackTile pt{};
-        pt.recOff = (int32_t)rowOff;
-        // after the Vij rows: the J-dagger field (written by j_finish_kernel; padded to whole 32-byte sectors), then
-        // the per-wavelength fields
+        pt.recOff = (int32_t)rowOff;             // depth-0 record of the tile; records of one tile are contiguous over depth
+        // record = [Vij rows dir 0 | fields | Vij rows dir 1]; fields = J-dagger (written by j_finish_kernel; padded to
+        // whole 32-byte sectors), bg chi / eta / sca, one per-wavelength field per slot -- padded to whole sectors
         const int jw = (Lw + 3) & ~3;
-        pt.recSize = (int32_t)align_up(sb + jw + (3 + td.nslot) * Lw, 16);
-        tileJOff.push_back((int32_t)rowOff + sb);
+        const int sf = (int)align_up(jw + (3 + td.nslot) * Lw, 4);
+        pt.recSize = 2 * vb + sf;
+        tileJ.push_back(TileJ{(int32_t)rowOff + vb, pt.recSize});
         pt.la0 = la0;
         pt.nslot = td.nslot;
         pt.slot0 = (int32_t)pslots.size();
-        pt.sb = sb;
-        pt.pad0 = jw;
+        pt.vb = vb;
+        pt.jw = jw;
+        pt.sf = sf;
         int lineIdx = 0;
         for (int q = 0; q < td.nslot; ++q) {
             SlotDesc &s = m->slots[td.slot0 + q];
-            s.fOff = sb + jw + (3 + q) * Lw;
+            s.fOff = vb + jw + (3 + q) * Lw;
             PackSlot ps{};
             ps.isLine = s.isLine;
             ps.Nblue = s.Nblue;
@@ -406,25 +370,29 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
             ps.c0 = s.c0;
             pslots.push_back(ps);
             if (s.isLine) {   // where compute_phi_kernel finds this line's entries of this tile
-                phiV[s.t].push_back((int32_t)rowOff + s.vOff);
-                phiDir[s.t].push_back(sb / 2);
-                phiF[s.t].push_back((int32_t)rowOff + s.fOff);
+                phiT[s.t].push_back(PhiTile{(int32_t)rowOff + s.vOff, vb + sf, (int32_t)rowOff + s.fOff, pt.recSize});
                 if (phiTile0[s.t] < 0) phiTile0[s.t] = ti;
             }
         }
         for (int e0 = 0; e0 < pt.recSize; e0 += 32) pchunks.push_back(PackChunk{ti, e0});
         ptiles.push_back(pt);
         td.recOff = pt.recOff;
-        td.bgOff = sb + jw;
-        td.vDir = kVRow * nLine;
+        td.bgOff = vb + jw;
+        td.vDir = vb + sf;
+        td.stride = pt.recSize;
         td.nlevslot = (int)lev.size();
-        rowOff += pt.recSize;
+        rowOff += (int64_t)pt.recSize * N;
+        rowSum += pt.recSize;
         m->Dmax = std::max(m->Dmax, td.nlevslot);
         m->Tmax = std::max(m->Tmax, td.nslot);
         m->tiles.push_back(td);
     }
+    if (rowOff >= (int64_t)1 << 31) {
+        delete m;
+        return fail(MALI_ELIMIT, "per-column table of %lld doubles exceeds the 32-bit record offsets", (long long)rowOff);
+    }
     m->nPartRows = partRow;
-    m->rowStride = rowOff;
+    m->rowStride = rowSum;      // doubles of the table per depth point (all tiles)
     m->packChunks = (int)pchunks.size();
     std::vector<int32_t> trPartOff(d->Ntrans + 1, 0), trPartRows;
     for (int t = 0; t < d->Ntrans; ++t) {
@@ -439,6 +407,8 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
     m->off_bbc = take(2 * (int64_t)d->Nspect);
     m->off_C = take((int64_t)m->sumNlevel2 * N);
     m->off_nTotal = take((int64_t)d->Natom * N);
+    m->popsW = (int)align_up(1 + m->sumNlevel, 4);          // popsT row: z | n[all levels] | pad  (mali_types.cuh)
+    m->off_popsT = take((int64_t)N * m->popsW);
     m->off_tab = take((int64_t)N * m->rowStride);
     L.colconst = o;
     L.pops = (int64_t)m->sumNlevel * N;
@@ -480,7 +450,7 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
         };
         return "{" + std::to_string(Lw) + "," + std::to_string(td.nslot) + "," + std::to_string(d->Natom) + "," +
                std::to_string(td.nlevslot) + "," + arr(kind) + "," + arr(atom) + "," + arr(lvI) + "," + arr(lvJ) + "," +
-               arr(rowI) + "," + arr(rowJ) + "," + std::to_string(d->Nrays) + "}";
+               arr(rowI) + "," + arr(rowJ) + "," + std::to_string(d->Nrays) + "," + std::to_string(m->popsW) + "}";
     };
     auto fill_tile = [&](auto &t, const TileDesc &td, int spec) {
         t.la0 = td.la0;
@@ -524,24 +494,13 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
         }
         m->specTiles++;
     }
-    {   // per-warp shared memory: populations | heights | level array / reduce scratch | mbarrier | exp table
-        auto even = [](int x) { return (x + 1) & ~1; };
-        m->smemPopDoubles = m->sumNlevel * N;
-        m->smemZOff = even(m->smemPopDoubles);
-        m->smemLvlOff = m->smemZOff + even(N);
-        m->smemMbarOff = (m->smemLvlOff + std::max(std::max(m->Dmax, 1) * 64 + d->Natom * 32, 16 * 36)) * 8;
-        m->smemExpOff = (int)align_up(m->smemMbarOff + 32, 16);  // staging barrier + three ring barriers
-        m->smemBytesPerWarp = m->smemExpOff + 128 * 16;   // generic kernel / upper bound without the TMA ring
-        // TMA ring of the specialised kernels, per register class: 3 stages of the largest record part one sweep
-        // direction needs (its Vij rows + the per-wavelength fields)
-        for (int c = 0; c < 3; ++c) m->ringStage[c] = 16;
-        for (size_t ti = 0; ti < ptiles.size(); ++ti) {
-            const PackTile &pt = ptiles[ti];
-            if (pt.nslot > kSpecMaxSlots) continue;
-            int &st = m->ringStage[spec_class(pt.nslot)];
-            st = std::max(st, pt.recSize - pt.sb / 2);
-        }
-        m->useBulk = (N % 2 == 0 && m->smemPopDoubles % 2 == 0) ? 1 : 0;  // cp.async.bulk: 16-byte sizes / addresses
+    // per-warp shared memory of the specialised kernels, per register class: the largest instance's need
+    for (int c = 0; c < 3; ++c) m->smemClass[c] = 0;
+    for (size_t ti = 0; ti < ptiles.size(); ++ti) {
+        const PackTile &pt = ptiles[ti];
+        if (pt.nslot > kSpecMaxSlots) continue;
+        int &sm = m->smemClass[spec_class(pt.nslot)];
+        sm = std::max(sm, fs_smem_bytes(pt.vb / kVRow, Lw, pt.nslot, m->popsW));
     }
 
     // ---- small copies of the upload path
@@ -583,10 +542,10 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
     up(to_device(m->trans, &m->d_trans));
     up(to_device(trPartOff, &m->d_trPartOff));
     up(to_device(trPartRows, &m->d_trPartRows));
-    up(to_device(tileJOff, &m->d_tileJOff));
+    up(to_device(tileJ, &m->d_tileJ));
     {   // tables of the device compute_phi
         std::vector<PhiLine> lines;
-        std::vector<int32_t> tv, td2, tf;
+        std::vector<PhiTile> tv;
         for (int t = 0; t < d->Ntrans; ++t) {
             const int32_t *tr = &m->trans[(size_t)t * 6];
             if (!tr[3]) continue;
@@ -598,20 +557,16 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
             ln.toff = m->toff[t];
             ln.tile0 = phiTile0[t];
             ln.tab0 = (int32_t)tv.size();
-            ln.ntile = (int32_t)phiV[t].size();
+            ln.ntile = (int32_t)phiT[t].size();
             ln.lambda0 = d->lambda0 ? d->lambda0[t] : 0.0;
             ln.c0 = d->lineconst[3 * t + 0];
             lines.push_back(ln);
-            tv.insert(tv.end(), phiV[t].begin(), phiV[t].end());
-            td2.insert(td2.end(), phiDir[t].begin(), phiDir[t].end());
-            tf.insert(tf.end(), phiF[t].begin(), phiF[t].end());
+            tv.insert(tv.end(), phiT[t].begin(), phiT[t].end());
         }
         m->nPhiLines = (int)lines.size();
         m->haveLambda0 = d->lambda0 != nullptr;
         up(to_device(lines, &m->d_phiLines));
-        up(to_device(tv, &m->d_phiTileV));
-        up(to_device(td2, &m->d_phiTileDir));
-        up(to_device(tf, &m->d_phiTileF));
+        up(to_device(tv, &m->d_phiTiles));
         std::vector<double> wl(d->wavelength, d->wavelength + d->Nspect), mz(d->muz, d->muz + d->Nrays),
             wm(d->wmu, d->wmu + d->Nrays);
         up(to_device(wl, &m->d_wavelength));
@@ -648,8 +603,8 @@ void mali_model_destroy(mali_model *m)
     cudaSetDevice(m->device);
     void *ptrs[] = {m->d_tiles, m->d_slots, m->d_alpha, m->d_twohc, m->d_wlacont, m->d_wlambda, m->d_zmu, m->d_hw,
                     m->d_Nlevel, m->d_lvlOff, m->d_g2Off, m->d_trans, m->d_trPartOff, m->d_trPartRows,
-                    m->d_genericTiles, m->d_cjobs, m->d_pchunks, m->d_ptiles, m->d_pslots, m->d_tileJOff, m->d_phiTileV,
-                    m->d_phiTileDir, m->d_phiTileF, m->d_phiLines, m->d_wavelength, m->d_muz, m->d_wmu};
+                    m->d_genericTiles, m->d_cjobs, m->d_pchunks, m->d_ptiles, m->d_pslots, m->d_tileJ, m->d_phiTiles,
+                    m->d_phiLines, m->d_wavelength, m->d_muz, m->d_wmu};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (cudaEvent_t e : m->profEvents) cudaEventDestroy(e);
@@ -677,8 +632,8 @@ int mali_model_info(const mali_model *m, int32_t *out8)
     out8[3] = m->Tmax;
     out8[4] = m->Dmax;
     out8[5] = (int32_t)m->rowStride;
-    out8[6] = m->smemBytesPerWarp;
-    out8[7] = m->useBulk;
+    out8[6] = std::max(m->smemClass[0], std::max(m->smemClass[1], m->smemClass[2]));
+    out8[7] = 1;
     return MALI_OK;
 }
 
@@ -707,8 +662,7 @@ static int upload_columns(const mali_model *m, const mali_buffers *b, int32_t co
         dim3 grid(m->packChunks, (m->N + 31) / 32, ncol), block(32, 8);
         pack_tiles_kernel<<<grid, block, 0, st>>>(m->d_pchunks, m->d_ptiles, m->d_pslots, m->d_wlambda, m->N, m->Nrays,
                                                   m->Nspect, m->Lw, staging_dev, L.hostpack, L.hp_bg_chi, L.hp_bg_eta,
-                                                  L.hp_bg_sca, b->colconst, L.colconst, m->off_tab, m->rowStride, col0,
-                                                  nophi ? 1 : 0);
+                                                  L.hp_bg_sca, b->colconst, L.colconst, m->off_tab, col0, nophi ? 1 : 0);
     }
     {
         dim3 grid(32, ncol);
@@ -741,9 +695,9 @@ int mali_compute_phi(const mali_model *m, const mali_buffers *b, int32_t col0, i
     if (m->nPhiLines == 0) return MALI_OK;
     dim3 grid((m->N + 3) / 4, m->nPhiLines, ncol);     // 4 warps per block, one depth point each
     compute_phi_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(
-        m->d_phiLines, m->d_phiTileV, m->d_phiTileDir, m->d_phiTileF, m->d_wavelength, m->d_wlambda, m->d_muz, m->d_wmu,
+        m->d_phiLines, m->d_phiTiles, m->d_wavelength, m->d_wlambda, m->d_muz, m->d_wmu,
         m->N, m->Nrays, m->Nspect, m->Lw, m->Ntrans, m->Natom, aDamp, vBroad, vlos, b->colconst, m->lay.colconst, m->off_tab,
-        m->rowStride, col0);
+        col0);
     m->launches += 1;
     CU(cudaGetLastError());
     return MALI_OK;
@@ -773,7 +727,6 @@ static FsParams make_fs_params(const mali_model *m, const mali_buffers *b, int c
     p.off_z = m->off_z;
     p.off_bbc = m->off_bbc;
     p.off_tab = m->off_tab;
-    p.rowStride = m->rowStride;
     p.off_jpart = m->off_jpart;
     p.off_part = m->off_part;
     p.upOff = m->upOff;
@@ -806,23 +759,13 @@ static FsCommon make_fs_common(const mali_model *m, const mali_buffers *b, int c
     c.Lw = m->Lw;
     c.col0 = col0;
     c.ncol = ncol;
-    c.warpsPerBlock = 1;
-    c.useBulk = m->useBulk;
-    c.smemBytesPerWarp = m->smemBytesPerWarp;
-    c.popDoubles = m->smemPopDoubles;
-    c.zOffDoubles = m->smemZOff;
-    c.lvlOffDoubles = m->smemLvlOff;
-    c.mbarOffBytes = m->smemMbarOff;
-    c.expTabOffBytes = m->smemExpOff;
+    c.popsW = m->popsW;
     c.colStride = m->lay.colconst;
-    c.popStride = m->lay.pops;
-    c.JStride = m->lay.J;
     c.IStride = m->lay.I;
     c.scratchStride = m->lay.scratch;
-    c.off_z = m->off_z;
     c.off_bbc = m->off_bbc;
     c.off_tab = m->off_tab;
-    c.rowStride = m->rowStride;
+    c.off_popsT = m->off_popsT;
     c.off_jpart = m->off_jpart;
     c.off_part = m->off_part;
     c.upOff = m->upOff;
@@ -832,11 +775,8 @@ static FsCommon make_fs_common(const mali_model *m, const mali_buffers *b, int c
     c.zmu = m->d_zmu;
     c.hw = m->d_hw;
     c.colconst = b->colconst;
-    c.pops = b->pops;
-    c.J = b->J;
     c.I = b->I;
     c.scratch = b->scratch;
-    c.dJbits = reinterpret_cast<unsigned long long *>(b->dJ);
     c.status = b->status;
     c.done = b->done;
     return c;
@@ -878,8 +818,9 @@ static FinishParams make_finish_params(const mali_model *m, const mali_buffers *
 
 static int launch_fs(const mali_model *m, const mali_buffers *b, int col0, int ncol, cudaStream_t st)
 {
-    col_zero_bits_kernel<<<(ncol + 127) / 128, 128, 0, st>>>(reinterpret_cast<unsigned long long *>(b->dJ), b->done,
-                                                           nullptr, 0, col0, ncol);
+    fs_prepare_kernel<<<ncol, 128, 0, st>>>(reinterpret_cast<unsigned long long *>(b->dJ), b->done, col0, b->colconst,
+                                            m->lay.colconst, m->off_z, m->off_popsT, m->popsW, m->N, m->sumNlevel, b->pops,
+                                            m->lay.pops);
     m->launches += 1;
     const bool rec = m->profOn && m->profUsed + 2 <= (int)m->profEvents.size();
     if (rec) cudaEventRecord(m->profEvents[m->profUsed], st);
@@ -895,24 +836,11 @@ static int launch_fs(const mali_model *m, const mali_buffers *b, int col0, int n
         m->launches += 1;
     }
     if (m->specTiles > 0) {
-        // per-warp shared memory of a class: populations | heights | reduce scratch | barriers | exp table | TMA ring
-        FsCommon cc[3];
+        const FsCommon cc = make_fs_common(m, b, col0, ncol);
         size_t smem[3];
         for (int cls = 0; cls < 3; ++cls) {
-            FsCommon &c = cc[cls];
-            c = make_fs_common(m, b, col0, ncol);
-            // populations: only the level rows a tile of this class can touch, transposed to [depth][level-slot]
-            c.popDoubles = std::min(2 * spec_class_slots(cls), std::max(m->sumNlevel, 1)) * m->N;
-            c.zOffDoubles = (c.popDoubles + 1) & ~1;
-            c.lvlOffDoubles = c.zOffDoubles + ((m->N + 1) & ~1);
-            c.useBulk = (m->N % 2 == 0) ? 1 : 0;   // cp.async.bulk: 16-byte sizes / addresses
-            const int red = spec_pow2(2 * spec_class_slots(cls)) * 36;
-            c.mbarOffBytes = (c.lvlOffDoubles + red) * 8;
-            c.expTabOffBytes = (int)align_up(c.mbarOffBytes + 8 + 8 * kRingStages, 16);   // staging + ring barriers
-            c.ringOffDoubles = (c.expTabOffBytes + 128 * 16) / 8;
-            c.smemBytesPerWarp = (c.ringOffDoubles + kRingStages * m->ringStage[cls]) * 8;
-            smem[cls] = (size_t)c.smemBytesPerWarp;
-            if (smem[cls] > 227 * 1024) return fail(MALI_ELIMIT, "column needs %zu B of shared memory per warp", smem[cls]);
+            smem[cls] = (size_t)m->smemClass[cls];
+            if (smem[cls] > 227 * 1024) return fail(MALI_ELIMIT, "a tile needs %zu B of shared memory per warp", smem[cls]);
         }
         // fork: class 2 (heaviest warps) stays on the caller's stream, classes 1 and 0 go to the side streams
         // -- only for small launches (a few waves of warps: single columns, response-function batches), where the
@@ -932,9 +860,11 @@ static int launch_fs(const mali_model *m, const mali_buffers *b, int col0, int n
             CU(cudaStreamWaitEvent(s0, m->forkEvent, 0));
         }
         cudaError_t e = cudaSuccess;
-        if (!m->spec2.empty()) e = launch_mega<2>(cc[2], m->spec2, ncol, smem[2], st, &m->launches);
-        if (e == cudaSuccess && !m->spec1.empty()) e = launch_mega<1>(cc[1], m->spec1, ncol, smem[1], s1, &m->launches);
-        if (e == cudaSuccess && !m->spec0.empty()) e = launch_mega<0>(cc[0], m->spec0, ncol, smem[0], s0, &m->launches);
+        if (!m->spec2.empty()) e = mali_fs_launch_2(cc, m->spec2.data(), (int)m->spec2.size(), ncol, smem[2], st, &m->launches);
+        if (e == cudaSuccess && !m->spec1.empty())
+            e = mali_fs_launch_1(cc, m->spec1.data(), (int)m->spec1.size(), ncol, smem[1], s1, &m->launches);
+        if (e == cudaSuccess && !m->spec0.empty())
+            e = mali_fs_launch_0(cc, m->spec0.data(), (int)m->spec0.size(), ncol, smem[0], s0, &m->launches);
         if (e != cudaSuccess) return fail((int)e, "fs_gamma_kernel_m: %s", cudaGetErrorString(e));
         if (side1) {   // join
             CU(cudaEventRecord(m->joinEvent[0], s1));
@@ -954,7 +884,7 @@ static int launch_fs(const mali_model *m, const mali_buffers *b, int col0, int n
     gamma_finish_kernel<<<grid, dim3(32, 8), 0, st>>>(f);
     {
         const int nb = std::min(m->N, 41);   // depth rows are dealt round-robin to the blocks of a column
-        j_finish_kernel<<<dim3(nb, ncol), 256, 0, st>>>(b->J, m->lay.J, b->scratch, m->lay.scratch, m->off_jpart, m->upOff, b->colconst, m->lay.colconst, m->off_tab, m->rowStride, m->d_tileJOff, m->Nspect, m->Lw,
+        j_finish_kernel<<<dim3(nb, ncol), 256, 0, st>>>(b->J, m->lay.J, b->scratch, m->lay.scratch, m->off_jpart, m->upOff, b->colconst, m->lay.colconst, m->off_tab, m->d_tileJ, m->Nspect, m->Lw,
                                                       reinterpret_cast<unsigned long long *>(b->dJ), b->done, col0);
     }
     m->launches += 2;
@@ -1123,7 +1053,7 @@ int mali_uv(const mali_model *m, const mali_buffers *b, int32_t col, int32_t t, 
         if (m->slots[td.slot0 + q].t == t) sd = &m->slots[td.slot0 + q];
     if (!sd) return fail(MALI_EINVAL, "mali_uv: internal error, transition %d missing from tile %d", t, ti);
     FsParams p = make_fs_params(m, b, col, 1, 1);
-    uv_hook_kernel<<<(m->N + 63) / 64, 64, 0, (cudaStream_t)stream>>>(p, col, *sd, td.recOff, td.vDir, la, la - td.la0,
+    uv_hook_kernel<<<(m->N + 63) / 64, 64, 0, (cudaStream_t)stream>>>(p, col, *sd, td.recOff, td.stride, td.vDir, la, la - td.la0,
                                                                       mu, toFrom ? 1 : 0, Uji, Vij, Vji);
     CU(cudaGetLastError());
     return MALI_OK;

@@ -1,81 +1,10 @@
-// mali_kernels.cuh -- hand-written sm_100a kernels of the MALI hot path (fp64, CUDA cores, no tensor cores:
-// nothing on this path is a dense contraction; the largest "matrix" is Nlevel x Nlevel).
-//
-// Compile with --fmad=false: the reference arithmetic (numpy, numba without fastmath) never contracts
-// a*b+c, and every expression below is written in the reference's evaluation order so that
-// the only source of difference is the order of the J / Gamma sums (exp_m below reproduces libm's exp).
-// This file holds the generic kernel (any number of transitions per tile; runtime loops) and the small kernels;
-// the production formal-solution kernel is the register-resident fs_gamma_kernel_t in mali_fs_kernel.cuh.
+// mali_kernels.cuh -- the generic formal-solution kernel (any number of transitions per tile; runtime loops), the
+// finish / statistical-equilibrium / upload kernels and the test hooks.  Included by mali_api.cu only (the
+// structure-specialised formal-solution kernels live in mali_fs_spec.cuh / mali_fs_class.cu).
 #pragma once
-#include <cfloat>
-#include <cmath>
-#include <cstdint>
-
-#include "mali_solve.h"
-#include "mali_voigt.h"
-#include "mali_types.cuh"
+#include "mali_device.cuh"
 
 namespace mali {
-
-// --------------------------------------------------------------------------------------------------------
-// exp(x) for 2^-54 <= |x| < 512, bit-identical to the libm the reference's numba code calls (glibc >= 2.28 on
-// x86-64 with FMA: table-driven, x = k ln2/128 + r, degree-5 polynomial, fused evaluation).  The operation
-// sequence below is that algorithm with every fused step written as an explicit __fma_rn, so --fmad=false does not
-// touch it; the 2^(k/128) table is generated from first principles by gen_exp_table.py.  13 fp64 operations
-// -- also cheaper than libdevice's exp.  tests/test_exp_model.py pins the algorithm to libm bit for bit.
-__device__ const ulonglong2 kExpTab[128] = {
-#include "exp_table.inc"
-};
-
-// tab: the 128-entry table, either kExpTab (global, read-only path) or a shared-memory copy of it
-template <bool SMEM_TAB>
-__device__ __forceinline__ double exp_m_t(double x, const ulonglong2 *tab)
-{
-    const double InvLn2N = 0x1.71547652b82fep+7, Shift = 0x1.8p+52;
-    const double NegLn2hiN = -0x1.62e42fefa0000p-8, NegLn2loN = -0x1.cf79abc9e3b3ap-47;
-    const double C2 = 0x1.ffffffffffdbdp-2, C3 = 0x1.555555555543cp-3, C4 = 0x1.55555cf172b91p-5,
-                 C5 = 0x1.1111167a4d017p-7;
-    double kd = __fma_rn(x, InvLn2N, Shift);
-    const unsigned long long ki = (unsigned long long)__double_as_longlong(kd);
-    const ulonglong2 e = SMEM_TAB ? tab[ki & 127ull] : __ldg(&tab[ki & 127ull]);
-    kd = __dsub_rn(kd, Shift);
-    double r = __fma_rn(kd, NegLn2hiN, x);
-    r = __fma_rn(kd, NegLn2loN, r);
-    const double tail = __longlong_as_double((long long)e.x);
-    const double scale = __longlong_as_double((long long)(e.y + (ki << 45)));
-    const double t1 = __fma_rn(r, C3, C2);
-    const double s = __dadd_rn(r, tail);
-    const double r2 = __dmul_rn(r, r);
-    const double t2 = __fma_rn(r, C5, C4);
-    const double s2 = __fma_rn(t1, r2, s);
-    const double r4 = __dmul_rn(r2, r2);
-    const double tmp = __fma_rn(r4, t2, s2);
-    return __fma_rn(scale, tmp, scale);
-}
-
-__device__ __forceinline__ double exp_m(double x)
-{
-    const double InvLn2N = 0x1.71547652b82fep+7, Shift = 0x1.8p+52;
-    const double NegLn2hiN = -0x1.62e42fefa0000p-8, NegLn2loN = -0x1.cf79abc9e3b3ap-47;
-    const double C2 = 0x1.ffffffffffdbdp-2, C3 = 0x1.555555555543cp-3, C4 = 0x1.55555cf172b91p-5,
-                 C5 = 0x1.1111167a4d017p-7;
-    double kd = __fma_rn(x, InvLn2N, Shift);
-    const unsigned long long ki = (unsigned long long)__double_as_longlong(kd);
-    kd = __dsub_rn(kd, Shift);
-    double r = __fma_rn(kd, NegLn2hiN, x);
-    r = __fma_rn(kd, NegLn2loN, r);
-    const ulonglong2 e = __ldg(&kExpTab[ki & 127ull]);
-    const double tail = __longlong_as_double((long long)e.x);
-    const double scale = __longlong_as_double((long long)(e.y + (ki << 45)));
-    const double t1 = __fma_rn(r, C3, C2);
-    const double s = __dadd_rn(r, tail);
-    const double r2 = __dmul_rn(r, r);
-    const double t2 = __fma_rn(r, C5, C4);
-    const double s2 = __fma_rn(t1, r2, s);
-    const double r4 = __dmul_rn(r2, r2);
-    const double tmp = __fma_rn(r4, t2, s2);
-    return __fma_rn(scale, tmp, scale);
-}
 
 // fp64 CUDA-core peak probe for the roofline: 8 independent unfused mul/add chains per thread.
 __global__ void fp64_peak_kernel(int iters, double seed, double *out)
@@ -100,44 +29,6 @@ __global__ void exp_hook_kernel(int n, const double *x, double *y)
     if (i < n) y[i] = exp_m(x[i]);
 }
 
-// --------------------------------------------------------------------------------------------------------
-// Correctly rounded fp64 division with a SHARED reciprocal.  The formal solver divides twice by the same optical
-// depth step (dS = (S' - S)/dtau, w1/dtau) and twice by the same opacity (S = .../chi, Psi = Lambda/chi); nvcc's
-// a / b expands to: 20-bit reciprocal seed, two Newton steps to a full-precision reciprocal r, q0 = a r,
-// rem = fma(-b, q0, a), q = fma(r, rem, q0) -- exactly rounded for normal-range operands -- plus a branch to a slow
-// path for subnormal / overflowing cases.  rcp_full() is that reciprocal, div_by() that quotient: 3 dependent
-// operations per division instead of 9, no branch in the instruction stream.  Domain (always met by physical
-// opacities / source functions; checked by div_domain_ok and reported through the column status word):
-// b finite, normal, non-zero; a == 0 or 2^-969 <= |a|; |a / b| normal.
-// tests: test_gpu_parity.py::test_shared_reciprocal_division_bitwise compares with a / b bit for bit.
-__device__ __forceinline__ double rcp_full(double b)
-{
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
-    r = __hiloint2double(__double2hiint(r), 1);  // nvcc's own division seeds the low word with 1 (MUFU.RCP64H + MOV)
-    double e = __fma_rn(-b, r, 1.0);
-    e = __fma_rn(e, e, e);
-    r = __fma_rn(r, e, r);
-    e = __fma_rn(-b, r, 1.0);
-    return __fma_rn(r, e, r);
-}
-
-__device__ __forceinline__ double div_by(double a, double b, double r)
-{
-    const double q0 = __dmul_rn(a, r);
-    const double rem = __fma_rn(-b, q0, a);
-    return __fma_rn(r, rem, q0);
-}
-
-__device__ __forceinline__ bool div_domain_ok(double a, double b, double q)
-{
-    const double aa = fabs(a), ab = fabs(b), aq = fabs(q);
-    const bool b_ok = ab >= 0x1p-1000 && ab <= 0x1p1000;
-    const bool a_ok = (a == 0.0) || (aa >= 0x1p-969 && aa <= 0x1p1000);
-    const bool q_ok = (a == 0.0) || (aq >= 0x1p-1021 && aq <= 0x1p1022);
-    return b_ok && a_ok && q_ok;
-}
-
 __global__ void div_hook_kernel(int n, const double *a, const double *b, double *q, int *bad)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -145,151 +36,6 @@ __global__ void div_hook_kernel(int n, const double *a, const double *b, double 
     const double r = rcp_full(b[i]);
     q[i] = div_by(a[i], b[i], r);
     bad[i] = div_domain_ok(a[i], b[i], q[i]) ? 0 : 1;
-}
-
-// --------------------------------------------------------------------------------------------------------
-// formal_solver.py:14-44
-__device__ __forceinline__ void w2(double dtau, double &w0, double &w1)
-{
-    if (dtau < 5e-4) {
-        w0 = dtau * (1.0 - 0.5 * dtau);
-        w1 = (dtau * dtau) * (0.5 - dtau / 3.0);
-    } else if (dtau > 50.0) {
-        w0 = 1.0;
-        w1 = 1.0;
-    } else {
-        const double expdt = exp_m(-dtau);  // 5e-4 <= dtau <= 50: inside exp_m's domain
-        w0 = 1.0 - expdt;
-        w1 = w0 - dtau * expdt;
-    }
-}
-
-// w2 with the exp table in shared memory and dtau / 3.0 through the shared-reciprocal division (r3 = rcp_full(3.0))
-__device__ __forceinline__ void w2_fast(double dtau, double r3, const ulonglong2 *stab, double &w0, double &w1)
-{
-    if (dtau < 5e-4) {
-        w0 = dtau * (1.0 - 0.5 * dtau);
-        w1 = (dtau * dtau) * (0.5 - div_by(dtau, 3.0, r3));
-    } else if (dtau > 50.0) {
-        w0 = 1.0;
-        w1 = 1.0;
-    } else {
-        const double expdt = exp_m_t<true>(-dtau, stab);
-        w0 = 1.0 - expdt;
-        w1 = w0 - dtau * expdt;
-    }
-}
-
-// One ray's short-characteristic recurrence, one depth point per step() (formal_solver.py:46-142,191-211).
-// The caller supplies chi, S at the current point in sweep order; step() returns I and PsiStar = LambdaStar/chi there.
-// W2MODE 0: exp table in global memory (generic kernel, test hook); 1: table in shared memory (specialised kernels).
-// (A branch-free w2 -- both forms evaluated, selected per lane -- was measured 3 % slower than the branch.)
-template <int W2MODE>
-struct SweepT {
-    double Iupw, chiPrev, SPrev, zPrev, w0, w1;
-    double r3 = 0.0;                      // rcp_full(3.0) when the fast w2 is used
-    const ulonglong2 *stab = nullptr;     // shared-memory copy of the exp table (nullptr: global table)
-    unsigned bad;  // sticky: a divisor left the domain of the shared-reciprocal division (reported via status bit 1)
-
-    __device__ __forceinline__ static unsigned out_of_range(double b)
-    {
-        // exponent of |b| outside [2^-1000, 2^1000] (also catches 0, subnormals, inf, NaN)
-        const unsigned e = ((unsigned)__double2hiint(b) >> 20) & 0x7ffu;
-        return (e - 23u) > 2000u ? 1u : 0u;
-    }
-
-    // first point of the sweep (k = kStart).  chiNext = chi[kStart+dk] is only needed for the upgoing boundary.
-    __device__ __forceinline__ void first(bool up, double zmu, double chi, double S, double z, double chiNext,
-                                          double zNext, double bbc0, double bbc1, double &I, double &Psi)
-    {
-        if (up) {
-            // formal_solver.py:205-207
-            const double dtau_uw = zmu * (chi + chiNext) * 0.5 * fabs(z - zNext);
-            Iupw = bbc1 - (bbc0 - bbc1) / dtau_uw;
-        } else {
-            Iupw = 0.0;
-        }
-        chiPrev = chi;
-        SPrev = S;
-        zPrev = z;
-        w0 = 0.0;
-        w1 = 0.0;
-        bad = 0u;
-        I = Iupw;
-        Psi = 0.0 / chi;  // LambdaStar[kStart] = 0
-    }
-
-    // interior point (formal_solver.py:120-135) or, with last = true, the final point with the reference's
-    // stale-w / S[kEnd-dk] behaviour (formal_solver.py:137-139).  rchi = rcp_full(chi) (shared with the caller's
-    // S = .../chi); the two divisions by dtau share one reciprocal as well.
-    __device__ __forceinline__ void step(bool last, double zmu, double chi, double rchi, double S, double z, double &I,
-                                         double &Psi)
-    {
-        const double dtau = 0.5 * (chiPrev + chi) * zmu * fabs(zPrev - z);
-        const double rdt = rcp_full(dtau);
-        bad |= out_of_range(dtau) | out_of_range(chi);
-        const double dS = div_by(SPrev - S, dtau, rdt);
-        double Ik, Lam;
-        if (!last) {
-            if constexpr (W2MODE == 1)
-                w2_fast(dtau, r3, stab, w0, w1);
-            else
-                w2(dtau, w0, w1);
-            Ik = Iupw * (1.0 - w0) + w0 * S + w1 * dS;
-        } else {
-            Ik = (1.0 - w0) * Iupw + w0 * SPrev + w1 * dS;
-        }
-        Lam = w0 - div_by(w1, dtau, rdt);
-        Iupw = Ik;
-        chiPrev = chi;
-        SPrev = S;
-        zPrev = z;
-        I = Ik;
-        Psi = div_by(Lam, chi, rchi);
-    }
-};
-using Sweep = SweepT<0>;
-
-// --------------------------------------------------------------------------------------------------------
-// Deterministic warp reduce-scatter of 8 values per lane: after the call the lane holds, in the return value,
-// the sum over all 32 lanes of v[lane >> 2].  9 shuffle-adds instead of 40; fixed summation tree.
-__device__ __forceinline__ double reduce_scatter8(double (&v)[8], int lane)
-{
-    const unsigned full = 0xffffffffu;
-    {
-        const bool up = lane & 16;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const double send = up ? v[j] : v[j + 4];
-            const double keep = up ? v[j + 4] : v[j];
-            v[j] = keep + __shfl_xor_sync(full, send, 16);
-        }
-    }
-    {
-        const bool up = lane & 8;
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const double send = up ? v[j] : v[j + 2];
-            const double keep = up ? v[j + 2] : v[j];
-            v[j] = keep + __shfl_xor_sync(full, send, 8);
-        }
-    }
-    {
-        const bool up = lane & 4;
-        const double send = up ? v[0] : v[1];
-        const double keep = up ? v[1] : v[0];
-        v[0] = keep + __shfl_xor_sync(full, send, 4);
-    }
-    v[0] = v[0] + __shfl_xor_sync(full, v[0], 2);
-    v[0] = v[0] + __shfl_xor_sync(full, v[0], 1);
-    return v[0];
-}
-
-__device__ __forceinline__ unsigned long long absbits(double x)
-{
-    // |x| as an unsigned integer: ordering of non-negative doubles == ordering of their bit patterns, and any
-    // NaN compares above +inf, so an integer max is a NaN-propagating max like numpy's.
-    return (unsigned long long)__double_as_longlong(fabs(x));
 }
 
 // --------------------------------------------------------------------------------------------------------
@@ -366,7 +112,7 @@ __global__ void __launch_bounds__(128) fs_gamma_kernel(const FsParams p)
                 const int lt = laC - sd.Nblue;
                 const bool act = valid && lt >= 0 && lt < sd.Nlam;
                 const int ltC = act ? lt : 0;
-                const double *rec = tab + (size_t)k * p.rowStride;
+                const double *rec = tab + (size_t)k * td.stride;
                 double Vij, Vji, Uji;
                 if (sd.isLine) {
                     const double phi = act ? __ldg(rec + sd.vOff + d * td.vDir + laneV) : 0.0;
@@ -393,7 +139,7 @@ __global__ void __launch_bounds__(128) fs_gamma_kernel(const FsParams p)
                 etaTot += eta_t;
             }
             const size_t kl = (size_t)k * Nspect + laC;
-            const double *bg = tab + (size_t)k * p.rowStride + td.bgOff + lsC;
+            const double *bg = tab + (size_t)k * td.stride + td.bgOff + lsC;
             chiTot += __ldg(bg);
             if (probe) {
                 chiProbe = chiTot;
@@ -433,7 +179,7 @@ __global__ void __launch_bounds__(128) fs_gamma_kernel(const FsParams p)
                         const int lt = laC - sd.Nblue;
                         const bool act = valid && lt >= 0 && lt < sd.Nlam;
                         const int ltC = act ? lt : 0;
-                        const double *rec = tab + (size_t)k * p.rowStride;
+                        const double *rec = tab + (size_t)k * td.stride;
                         double Vij, Vji, Uji, wla;
                         if (sd.isLine) {
                             const double phi = act ? __ldg(rec + sd.vOff + d * td.vDir + laneV) : 0.0;
@@ -479,9 +225,12 @@ __global__ void __launch_bounds__(128) fs_gamma_kernel(const FsParams p)
 // --------------------------------------------------------------------------------------------------------
 // dJ = max |1 - JDag/J| (rh_method.py:705-706) and J <- the new mean intensity the sweeps accumulated in Jpart.
 // Elementwise over one column's [Nspace][Nspect] plane; block max -> one atomicMax per block.
+struct TileJ {
+    int32_t off, stride;   // J-dagger field of the tile's depth-0 record; record stride
+};
 __global__ void j_finish_kernel(double *J, int64_t JStride, const double *scratch, int64_t scratchStride,
                                 int64_t offJpart, int64_t upOff, double *colconst, int64_t colStride, int64_t offTab,
-                                int64_t rowStride, const int32_t *tileJOff, int Nspect, int Lw,
+                                const TileJ *tileJ, int Nspect, int Lw,
                                 unsigned long long *dJbits, const int32_t *done, int col0)
 {
     const int col = col0 + blockIdx.y;
@@ -495,7 +244,6 @@ __global__ void j_finish_kernel(double *J, int64_t JStride, const double *scratc
     const int ntile = (Nspect + Lw - 1) / Lw;
     for (int k = blockIdx.x; k < N; k += gridDim.x) {          // one depth row at a time: no 64-bit divisions
         const int64_t q0 = (int64_t)k * Nspect;
-        double *rec = tab + (size_t)k * rowStride;
         for (int idx = threadIdx.x; idx < ntile * jw; idx += blockDim.x) {
             const int ti = idx / jw, ls = idx - ti * jw;
             const int la = ti * Lw + ls;
@@ -508,7 +256,8 @@ __global__ void j_finish_kernel(double *J, int64_t JStride, const double *scratc
             }
             // the copy the next formal solution reads (J-dagger): a field of the tile-major records, so that it
             // arrives with the record's TMA and the depth loop holds no global loads; whole sectors are written
-            rec[tileJOff[ti] + ls] = jn;
+            const TileJ tj = tileJ[ti];
+            tab[tj.off + (size_t)k * tj.stride + ls] = jn;
         }
     }
 #pragma unroll
@@ -643,12 +392,12 @@ __global__ void sweep_hook_kernel(int N, int nray, const double *z, const double
 }
 
 // Test hook: ComputationalTransition.uv from the packed device tables of one column.
-__global__ void uv_hook_kernel(const FsParams p, int col, SlotDesc sd, int recOff, int vDir, int la, int ls, int mu, int d,
-                               double *Uji, double *Vij, double *Vji)
+__global__ void uv_hook_kernel(const FsParams p, int col, SlotDesc sd, int recOff, int stride, int vDir, int la, int ls,
+                               int mu, int d, double *Uji, double *Vij, double *Vji)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= p.N) return;
-    const double *rec = p.colconst + (size_t)col * p.colStride + p.off_tab + (size_t)k * p.rowStride + recOff;
+    const double *rec = p.colconst + (size_t)col * p.colStride + p.off_tab + (size_t)k * stride + recOff;
     const int lt = la - sd.Nblue;
     double vij, vji, uji;
     if (sd.isLine) {
@@ -676,7 +425,7 @@ struct PackSlot {
     double c0;        // hc/4pi*Bij
 };
 struct PackTile {
-    int32_t recOff, recSize, la0, nslot, slot0, sb, pad0, pad1;  // sb: size of the Vij rows; pad0: width of the J-dagger field
+    int32_t recOff, recSize, la0, nslot, slot0, vb, jw, sf;  // vb: one direction's Vij rows; jw: J-dagger field; sf: all fields
 };
 struct PackChunk {
     int32_t tile, e0;  // 32 consecutive record elements of one tile
@@ -685,12 +434,13 @@ struct PackChunk {
 __global__ void pack_tiles_kernel(const PackChunk *chunks, const PackTile *tiles, const PackSlot *slots,
                                   const double *wlambda, int N, int Nrays, int Nspect, int Lw, const double *staging,
                                   int64_t hpStride, int64_t hpBgChi, int64_t hpBgEta, int64_t hpBgSca, double *colconst,
-                                  int64_t colStride, int64_t offTab, int64_t rowStride, int col0, int skipPhi)
+                                  int64_t colStride, int64_t offTab, int col0, int skipPhi)
 {
     __shared__ double tile[32][33];
     const PackChunk ch = chunks[blockIdx.x];
     const PackTile pt = tiles[ch.tile];
-    if (skipPhi && ch.e0 + 32 <= pt.sb) return;   // a chunk of Vij rows only: compute_phi_kernel writes those rows whole
+    // a chunk of Vij rows only: compute_phi_kernel writes those rows whole
+    if (skipPhi && (ch.e0 + 32 <= pt.vb || (ch.e0 >= pt.vb + pt.sf))) return;
     const double *src = staging + (size_t)blockIdx.z * hpStride;
     double *dst = colconst + (size_t)(col0 + blockIdx.z) * colStride + offTab + pt.recOff;
     const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
@@ -699,9 +449,11 @@ __global__ void pack_tiles_kernel(const PackChunk *chunks, const PackTile *tiles
         const int e = ch.e0 + q;
         double v = 0.0;
         if (e < pt.recSize && k < N) {
-            if (e < pt.sb) {  // Vij rows
-                const int nLine = pt.sb / (2 * kVRow);
-                const int d = e / (nLine * kVRow), j = (e / kVRow) - d * nLine, idx = e % kVRow;
+            const bool inV0 = e < pt.vb, inV1 = e >= pt.vb + pt.sf;
+            if (inV0 || inV1) {  // Vij rows: direction 0 before the fields, direction 1 after them
+                const int d = inV1 ? 1 : 0;
+                const int ev = inV1 ? e - pt.vb - pt.sf : e;
+                const int j = ev / kVRow, idx = ev % kVRow;
                 const int ls = idx / Nrays, mu = idx - ls * Nrays;
                 int sq = -1;
                 for (int u = 0; u < pt.nslot; ++u)
@@ -712,8 +464,8 @@ __global__ void pack_tiles_kernel(const PackChunk *chunks, const PackTile *tiles
                     if (la < Nspect && lt >= 0 && lt < ps.Nlam)
                         v = ps.c0 * src[ps.srcOff + ((size_t)(lt * Nrays + mu) * 2 + d) * N + k];
                 }
-            } else if (e >= pt.sb + pt.pad0) {  // (the J-dagger field in between starts as zeros)
-                const int ef = e - pt.sb - pt.pad0;
+            } else if (e >= pt.vb + pt.jw) {  // (the J-dagger field at the head of the fields starts as zeros)
+                const int ef = e - pt.vb - pt.jw;
                 const int f = ef / Lw, ls = ef - f * Lw;
                 const int la = pt.la0 + ls;
                 const int laClamp = la < Nspect ? la : Nspect - 1;
@@ -740,7 +492,7 @@ __global__ void pack_tiles_kernel(const PackChunk *chunks, const PackTile *tiles
     __syncthreads();
     for (int q = ty; q < 32; q += 8) {
         const int kk = blockIdx.y * 32 + q, e = ch.e0 + tx;
-        if (kk < N && e < pt.recSize) dst[(size_t)kk * rowStride + e] = tile[tx][q];
+        if (kk < N && e < pt.recSize) dst[(size_t)kk * pt.recSize + e] = tile[tx][q];
     }
 }
 
@@ -755,11 +507,13 @@ struct PhiLine {
     int32_t t, atom, Nblue, Nlam, toff, tile0, tab0, ntile;  // tab0: first entry of the per-tile tables below
     double lambda0, c0;                                      // line centre (nm); hc/4pi*Bij
 };
-__global__ void compute_phi_kernel(const PhiLine *lines, const int32_t *tileV, const int32_t *tileDir,
-                                   const int32_t *tileF, const double *wavelength, const double *wlambda,
+struct PhiTile {
+    int32_t v0, vDir, f, stride;   // depth-0 offsets of the line's direction-0 Vij row and of its weight field; distance
+};                                 // to the direction-1 row; record stride of the tile
+__global__ void compute_phi_kernel(const PhiLine *lines, const PhiTile *ptile, const double *wavelength, const double *wlambda,
                                    const double *muz, const double *wmu, int N, int Nrays, int Nspect, int Lw, int Ntrans,
                                    int Natom, const double *aDamp, const double *vBroad, const double *vlos,
-                                   double *colconst, int64_t colStride, int64_t offTab, int64_t rowStride, int col0)
+                                   double *colconst, int64_t colStride, int64_t offTab, int col0)
 {
     const int lane = threadIdx.x & 31;
     const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -769,7 +523,7 @@ __global__ void compute_phi_kernel(const PhiLine *lines, const int32_t *tileV, c
     const double ad = aDamp[((size_t)c * Ntrans + ln.t) * N + k];
     const double vb = vBroad[((size_t)c * Natom + ln.atom) * N + k];
     const double vl = vlos[(size_t)c * N + k];
-    double *row = colconst + (size_t)(col0 + c) * colStride + offTab + (size_t)k * rowStride;
+    double *tab = colconst + (size_t)(col0 + c) * colStride + offTab;
     const int ls = lane / Nrays, mu = lane - ls * Nrays;
     const bool lane_on = ls < Lw;
     const double sqrtPi = sqrt(kPi);
@@ -787,9 +541,10 @@ __global__ void compute_phi_kernel(const PhiLine *lines, const int32_t *tileV, c
             p1 = voigt_H(ad, v + vd) * rnorm;
             wPhi += (p0 + p1) * ((wlambda[ln.toff + lt] * 0.5) * wm);                           // :227, :233
         }
-        double *v0 = row + tileV[ln.tab0 + j];
+        const PhiTile pt = ptile[ln.tab0 + j];
+        double *v0 = tab + pt.v0 + (size_t)k * pt.stride;
         v0[lane] = ln.c0 * p0;                         // whole rows, zero where the line is not active
-        v0[tileDir[ln.tab0 + j] + lane] = ln.c0 * p1;
+        v0[pt.vDir + lane] = ln.c0 * p1;
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) wPhi += __shfl_xor_sync(0xffffffffu, wPhi, off);
@@ -798,7 +553,8 @@ __global__ void compute_phi_kernel(const PhiLine *lines, const int32_t *tileV, c
         if (lane < Lw) {
             const int la = (ln.tile0 + j) * Lw + lane, lt = la - ln.Nblue;
             const bool on = lt >= 0 && lt < ln.Nlam && la < Nspect;
-            row[tileF[ln.tab0 + j] + lane] = on ? wlambda[ln.toff + lt] * wphi / kHC : 0.0;     // :451
+            const PhiTile pt = ptile[ln.tab0 + j];
+            tab[pt.f + (size_t)k * pt.stride + lane] = on ? wlambda[ln.toff + lt] * wphi / kHC : 0.0;     // :451
         }
     }
 }

@@ -5,17 +5,24 @@
 // Nspace depth points; a *tile* is the group of Lw = 32 / Nrays consecutive wavelengths (all angles)
 // one warp owns; a *slot* is one radiative transition overlapping a tile's wavelength range.
 //
-// The per-column tables are stored TILE-MAJOR: for every depth k one row of `rowStride` doubles holding, tile after
-// tile, one contiguous *record* with everything the tile's warp reads at that depth:
-//     [ Vij rows of direction 0: one per line slot, each kVRow = 32 doubles = (wavelength, angle) in lane order ]
-//     [ Vij rows of direction 1 ]
-//     [ J-dagger[Lw rounded up to 4]: the mean intensity of the previous iteration, rewritten by j_finish_kernel
-//       (the only part of a record that changes between iterations; zero after upload) ]
-//     [ bg chi[Lw] | bg eta[Lw] | bg sca[Lw] ]
-//     [ per slot: wla[Lw] (lines, rh_method.py:451) or g_ij[Lw] (continua, :453-454) ]      (padded to 16 doubles)
-// Entries for wavelengths on which a transition is not active are zero, so the kernels need no activity masks for
-// their loads; rows are 128-byte aligned, every warp load is a full-sector burst, and all streams of a warp advance
-// by the same stride per depth step.
+// The per-column tables are stored TILE-MAJOR, DEPTH-CONTIGUOUS: tile after tile, and inside a tile one *record* per
+// depth point k (record stride = the tile's record size), holding everything the tile's warp reads at that depth:
+//     [ Vij rows of direction 0 (down sweep): one per line slot, each kVRow = 32 doubles = (wavelength, angle) in lane order ]
+//     [ fields: J-dagger[Lw rounded up to 4]: the mean intensity of the previous iteration, rewritten by
+//               j_finish_kernel (the only part of a record that changes between iterations; zero after upload)
+//               bg chi[Lw] | bg eta[Lw] | bg sca[Lw]
+//               per slot: wla[Lw] (lines, rh_method.py:451) or g_ij[Lw] (continua, :453-454)     (padded to 4 doubles) ]
+//     [ Vij rows of direction 1 (up sweep) ]
+// The fields sit BETWEEN the two directions' rows, so what one sweep direction needs at a depth -- [rows 0 | fields]
+// or [fields | rows 1] -- is one contiguous piece: one TMA bulk copy per depth step, and a sweep walks its tile's
+// records as a single sequential stream.  Entries for wavelengths on which a transition is not active are zero, so
+// the kernels need no activity masks for their loads; records are 32-byte aligned.
+//
+// Level populations reach the formal-solution kernels through a second per-column table, depth-major:
+//     popsT[k] = [ z[k] | n[0][k] ... n[sumNlevel-1][k] | pad ]           (row width PW = 1 + sumNlevel rounded up to 4)
+// (heights first, then every level of every active atom), rebuilt from n[level][k] at the start of every formal
+// solution, so that the populations and heights of a depth step also arrive by TMA with that step's record and the
+// shared memory a warp needs does not depend on the number of depth points.
 #pragma once
 #include <cstdint>
 
@@ -50,9 +57,11 @@ struct TileDesc {
     int32_t slot0;     // first SlotDesc of the tile
     int32_t nlevslot;  // distinct (atom, level) pairs touched by the tile's slots
     int32_t partRow0;  // first row of the tile's Gamma partials (2 rows per slot: [i,j] then [j,i])
-    int32_t recOff;    // offset of the tile's record inside a depth row
+    int32_t recOff;    // offset of the tile's first record (depth 0) inside the column's table
     int32_t bgOff;     // record offset of bg chi[Lw] (eta, sca follow at +Lw, +2Lw)
-    int32_t vDir;      // distance between the direction-0 and direction-1 Vij rows (number of line slots * kVRow)
+    int32_t vDir;      // distance between the direction-0 and direction-1 Vij rows (line rows + fields)
+    int32_t stride;    // record size = distance between the tile's records of consecutive depth points
+    int32_t pad0, pad1, pad2;
 };
 
 constexpr int kVRow = 32;  // doubles per Vij row of a record (Lw * Nrays <= 32 lanes, zero padded)
@@ -66,7 +75,7 @@ struct FsParams {
     // strides (doubles per column)
     int64_t colStride, popStride, JStride, IStride, scratchStride;
     // offsets inside one column's colconst block
-    int64_t off_z, off_bbc, off_tab, rowStride;
+    int64_t off_z, off_bbc, off_tab;
     // offsets inside one column's scratch block
     int64_t off_jpart, off_part;
     int64_t upOff;  // the up sweep writes its partial sums this many doubles further on (no read-modify-write)

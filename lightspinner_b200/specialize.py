@@ -29,6 +29,7 @@ def tile_structures(p):
     lvloff = np.concatenate([[0], np.cumsum(Nlevel)])
     natom = len(Nlevel)
     Lw = 32 // Nrays
+    pw = (1 + int(Nlevel.sum()) + 3) // 4 * 4        # width of a popsT row (csrc/mali_types.cuh)
     keys = []
     for ti in range((Nspect + Lw - 1) // Lw):
         la0, la1 = ti * Lw, min(Nspect, ti * Lw + Lw)
@@ -45,8 +46,8 @@ def tile_structures(p):
             lvI[q], lvJ[q] = lev[(a, i)], lev[(a, j)]
             rowI[q], rowJ[q] = int(lvloff[a] + i), int(lvloff[a] + j)
         arr = lambda x: '{' + ','.join(str(v) for v in x) + '}'
-        keys.append('{%d,%d,%d,%d,%s,%s,%s,%s,%s,%s,%d}' % (Lw, len(slots), natom, len(lev), arr(kind), arr(atom),
-                                                          arr(lvI), arr(lvJ), arr(rowI), arr(rowJ), Nrays))
+        keys.append('{%d,%d,%d,%d,%s,%s,%s,%s,%s,%s,%d,%d}' % (Lw, len(slots), natom, len(lev), arr(kind), arr(atom),
+                                                             arr(lvI), arr(lvJ), arr(rowI), arr(rowJ), Nrays, pw))
     return keys
 
 
