@@ -206,6 +206,8 @@ def workload_config(args, base):
         'iters_per_solve': args.iters, 'Nspace': int(base['Nspace']), 'Nrays': int(base['Nrays']),
         'Nspect': int(base['Nspect']), 'Ntrans': int(np.asarray(base['trans']).shape[0]),
         'parallelism': 'columns sharded over %d GPU(s), no data-path collective' % args.gpus,
+        'arithmetic': 'fp64; formal-solution kernels in the library default mode (contracted a*b+c, shared reciprocals; '
+                      'MALI_ARITH=exact gives the reference\'s rounding, reported as exact_arith)',
         'l2_policy': 'inputs larger than L2 (%.1f GB of per-column tables per GPU)' % (
             args.ncol * algorithmic_bytes_per_column(base) / 1e9),
     }
@@ -329,6 +331,28 @@ def main():
     total_units = world * ncol * units_per_col_iter * iters * args.steps
     value = total_units / (ms * 1e-3)
 
+    # ---- the same resident solve with the reference's rounding (MALI_ARITH_EXACT): a side number next to the
+    # headline, which runs the library's default arithmetic (contracted; both modes are parity-tested)
+    arith_default = eng.arith
+    exact_side = None
+    try:
+        eng.set_arith('exact')
+        solve_resident()
+        barrier()
+        eng.profile_begin(iters)
+        e0.record()
+        solve_resident()
+        e1.record()
+        barrier()
+        ms_x = max_over_ranks(e0.elapsed_time(e1))
+        fx_ms, fx_n = eng.profile_end()
+        exact_side = {'arith': 'exact', 'value': world * ncol * units_per_col_iter * iters / (ms_x * 1e-3), 'unit': UNIT,
+                      'ms_per_step': ms_x, 'mean_launch_ms': fx_ms / max(fx_n, 1), 'steps': 1}
+    except Exception as ex:
+        exact_side = {'error': repr(ex)}
+    finally:
+        eng.set_arith(arith_default)
+
     # ---- roofline of the dominant kernel
     peak, peak_src = measured_peaks()
     fs_ms_mean = fs_ms / max(fs_n, 1)
@@ -347,7 +371,7 @@ def main():
                 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                 'frac': achieved / peak, 'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': alg_bytes, 'mean_launch_ms': fs_ms_mean, 'launches_timed': fs_n,
-                'share_of_step': fs_ms / ms if ms > 0 else None,
+                'share_of_step': fs_ms / ms if ms > 0 else None, 'arith': arith_default,
                 'note': 'fp64 CUDA-core work binds before HBM on this path (SURVEY.md 7.3-2); see DESIGN.md'}
     try:    # the roof that actually binds: unfused fp64 on the CUDA cores, peak measured live
         from lightspinner_b200.engine import fp64_peak
@@ -657,7 +681,8 @@ def main():
                 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
                 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': cfg, 'clocks': clocks,
                 'e2e': e2e, 'e2e_host_phi': e2e_host, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu,
-                'single_column': single, 'to_convergence': conv, 'response_function': rf, 'results_finite': finite}
+                'single_column': single, 'to_convergence': conv, 'response_function': rf, 'results_finite': finite,
+                'arith': arith_default, 'exact_arith': exact_side}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -16,6 +16,7 @@
  *   planck                      utils.py:17-22              mali_planck_bc (host helper for the lower boundary)
  *   Context.stat_equil          rh_method.py:710-745        mali_stat_equil
  *   test.py:20-29 / response_fn.py:11-21 (the MALI loop)    mali_iterate (device-resident loop, per-column convergence)
+ *   ComputationalTransition.compute_phi rh_method.py:198-243 mali_compute_phi (device Voigt profiles); mali_line_layout = read-back
  *
  * Conventions
  *   - plain C, no exceptions; every function returns 0 on success, a negative MALI_E* code on argument
@@ -116,6 +117,22 @@ int mali_device_count(void);
 
 int mali_model_create(const mali_model_desc *desc, int device, mali_model **out);
 void mali_model_destroy(mali_model *m);
+/* Arithmetic mode of the structure-specialised formal-solution kernels (csrc/mali_device.cuh, Arith):
+ *   MALI_ARITH_EXACT       every operation separately rounded in the reference's evaluation order: one ray's chi, S, I,
+ *                          PsiStar and Gamma integrands are bit-identical to the reference's numpy / numba arithmetic;
+ *   MALI_ARITH_CONTRACTED  the same expressions with a*b+c fused and quotients by a shared divisor taken as
+ *                          a * (1/b): fp64 throughout, every intermediate within ~2 ulp of the exact mode's, about a
+ *                          quarter fewer fp64 instructions.
+ * Both meet the parity bar (populations, J, I within 1e-10 of the reference after the same number of iterations;
+ * identical iteration counts) and both are tested against it.  A new model starts in MALI_ARITH_DEFAULT unless the
+ * environment variable MALI_ARITH=exact|contracted says otherwise.  The generic kernel (tiles without a specialised
+ * instance), the test hooks and the statistical-equilibrium solve always use the exact form. */
+#define MALI_ARITH_EXACT 0
+#define MALI_ARITH_CONTRACTED 1
+#define MALI_ARITH_DEFAULT MALI_ARITH_CONTRACTED
+int mali_model_set_arith(mali_model *m, int32_t mode);
+int mali_model_get_arith(const mali_model *m);
+
 int mali_model_layout(const mali_model *m, mali_layout *out);
 /* out8: ntile, tiles on structure-specialised kernels, tiles on the generic kernel, max transitions per tile,
  * max levels per tile, doubles per depth row of the tile-major table, shared-memory bytes per warp, TMA staging on/off */
@@ -169,6 +186,15 @@ int mali_iterate(const mali_model *m, const mali_buffers *bufs, int32_t col0, in
 int mali_profile_begin(const mali_model *m, int32_t max_launches);
 int mali_profile_end(const mali_model *m, double *fs_ms_total, int32_t *fs_launches);
 long long mali_launch_count(const mali_model *m);
+
+/* Where the profile of line t lives inside a column's device table (read-back of ComputationalTransition.phi / wphi,
+ * rh_method.py:224,235): the line spans *ntile wavelength tiles starting at tile *tile0 (tile = lambda_per_warp
+ * consecutive wavelengths); for the q-th of them entries[4q..4q+3] = {v0, vDir, f, stride}: at depth k the row of 32
+ * doubles hc/4pi*Bij*phi[(lambda, mu) in lane order] of direction 0 starts at colconst + *off_tab + v0 + k*stride (direction
+ * 1: + vDir), and the field wlambda*wphi/HC [lambda_per_warp] at colconst + *off_tab + f + k*stride.  entries may be NULL
+ * (query *ntile first). */
+int mali_line_layout(const mali_model *m, int32_t t, int32_t *tile0, int32_t *ntile, int32_t *entries, int32_t cap,
+                     int64_t *off_tab);
 
 /* fp64 CUDA-core peak probe: unfused mul + add operations per second on the current device (roofline denominator;
  * MEASURED_PEAKS.json has no fp64 entry). */

@@ -41,7 +41,9 @@ class Buffers(C.Structure):
 EXPORTS = ['mali_last_error', 'mali_device_count', 'mali_model_create', 'mali_model_destroy', 'mali_model_layout', 'mali_model_info',
            'mali_planck_bc', 'mali_upload_columns', 'mali_upload_columns_nophi', 'mali_compute_phi', 'mali_formal_sol_gamma', 'mali_stat_equil', 'mali_iterate',
            'mali_piecewise_linear_1d', 'mali_uv', 'mali_exp_hook', 'mali_div_hook', 'mali_profile_begin',
-           'mali_profile_end', 'mali_launch_count', 'mali_fp64_peak']
+           'mali_profile_end', 'mali_launch_count', 'mali_fp64_peak', 'mali_line_layout', 'mali_model_set_arith', 'mali_model_get_arith']
+
+ARITH_EXACT, ARITH_CONTRACTED = 0, 1
 
 _libs = {}
 
@@ -77,6 +79,9 @@ def load(path=None):
     L.mali_profile_begin.argtypes = [C.c_void_p, C.c_int32]
     L.mali_profile_end.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int32)]
     L.mali_launch_count.argtypes = [C.c_void_p]
+    L.mali_model_set_arith.argtypes = [C.c_void_p, C.c_int32]
+    L.mali_model_get_arith.argtypes = [C.c_void_p]
+    L.mali_line_layout.argtypes = [C.c_void_p, C.c_int32, _ip, _ip, _ip, C.c_int32, C.POINTER(C.c_int64)]
     L.mali_launch_count.restype = C.c_longlong
     L.mali_div_hook.argtypes = [C.c_int32] + [C.c_void_p] * 5
     L.mali_fp64_peak.argtypes = [C.c_int32, C.c_void_p, C.POINTER(C.c_double)]

@@ -3,8 +3,8 @@
     python -m lightspinner_b200.build [--force] [--verbose]
 
 --fmad=false is part of the numerical contract (see csrc/mali_device.cuh); -lineinfo keeps the ncu source page
-usable.  Four translation units -- the host API with the small kernels, and one per register class of the
-structure-specialised formal-solution kernels -- are compiled in parallel and linked into one shared library, which
+usable.  Seven translation units -- the host API with the small kernels, and one per register class and arithmetic
+mode of the structure-specialised formal-solution kernels -- are compiled in parallel and linked into one shared library, which
 lives in lightspinner_b200/_lib/ (git-ignored, travels with gpurun).
 """
 import os
@@ -25,8 +25,10 @@ EXTRA = os.environ.get('MALI_NVCC_EXTRA', '').split()
 NVCC_FLAGS = EXTRA + ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '--fmad=false', '-std=c++20',
                       '-Xcompiler', '-fPIC', '-Xcompiler', '-ffp-contract=off', '-Xcompiler', '-O2']
 # (object name, source, extra flags)
-UNITS = [('api', 'mali_api.cu', []), ('fs0', 'mali_fs_class.cu', ['-DMALI_CLS=0']),
-         ('fs1', 'mali_fs_class.cu', ['-DMALI_CLS=1']), ('fs2', 'mali_fs_class.cu', ['-DMALI_CLS=2'])]
+UNITS = [('fs1', 'mali_fs_class.cu', ['-DMALI_CLS=1']), ('fs1f', 'mali_fs_class.cu', ['-DMALI_CLS=1', '-DMALI_FAST=1']),
+         ('fs2', 'mali_fs_class.cu', ['-DMALI_CLS=2']), ('fs2f', 'mali_fs_class.cu', ['-DMALI_CLS=2', '-DMALI_FAST=1']),
+         ('fs0', 'mali_fs_class.cu', ['-DMALI_CLS=0']), ('fs0f', 'mali_fs_class.cu', ['-DMALI_CLS=0', '-DMALI_FAST=1']),
+         ('api', 'mali_api.cu', [])]
 
 
 def nvcc_path():

@@ -7,24 +7,19 @@
     ctx.I, ctx.J, ctx.activeAtoms[0].n, .Gamma        # same names, shapes and aliasing as the reference
 
 Only the hot path moves to the GPU.  Everything in this file is the host-side mirror of the reference's per-Context
-SET-UP (ComputationalTransition / ComputationalAtom construction: line profiles, wavelength weights, collisional
-rates -- rh_method.py:93-131,198-243,366-423,474-487): it calls the same methods on the same model objects
-(`line.damping`, `atom.v_broad`, `collision.compute_rates`) with the reference's own numpy expressions, flattens the
-result (lightspinner_b200/tables.py) and uploads it once.  The iteration itself never touches the host except for
+SET-UP (ComputationalTransition / ComputationalAtom construction, rh_method.py:93-131,366-423,474-487): it asks the
+model objects for what only they know (`line.damping`, `atom.v_broad`, `collision.compute_rates`), flattens the
+result (lightspinner_b200/tables.py) and uploads it once; the Voigt line profiles (rh_method.py:198-243) are formed on
+the GPU from the damping parameters (mali_compute_phi) and the wavelength weights by tables.ModelTables.  The iteration itself never touches the host except for
 the two scalars the reference's loop reads (dJ, dPops) and the population write-back that keeps
 `eqPops[name].pops is atom.n` true.
 """
 from dataclasses import dataclass
 
 import numpy as np
-from scipy import special
 
 from . import tables
 from .engine import MaliEngine, piecewise_linear_1d_batch
-
-CLight = tables.CLight
-HC = tables.HC
-
 
 @dataclass
 class UV:
@@ -34,18 +29,15 @@ class UV:
     Vji: np.ndarray
 
 
-def voigt_H(a, v):
-    """utils.py:13-15"""
-    return special.wofz(v + 1j * a).real
-
-
 def _is_line(trans):
     # reference: isinstance(trans, AtomicLine); lines carry Einstein coefficients, continua a cross-section
     return hasattr(trans, 'Aji') and hasattr(trans, 'lambda0')
 
 
 class ComputationalTransition:
-    """Host mirror of rh_method.ComputationalTransition (state + set-up only; `uv` evaluates on the GPU tables)."""
+    """Host-side handle of one radiative transition (rh_method.ComputationalTransition's role): the model constants
+    the flattening needs plus views of what lives on the device.  The line profiles are formed on the GPU
+    (mali_compute_phi); `phi` / `wphi` read them back on first use, `uv` evaluates on the GPU tables."""
 
     def __init__(self, trans, compAtom, atmos, spect):
         self.transModel = trans
@@ -53,91 +45,49 @@ class ComputationalTransition:
         self.wavelength = trans.wavelength
         self.isLine = _is_line(trans)
         if self.isLine:
-            self.Aji = trans.Aji
-            self.Bji = trans.Bji
-            self.Bij = trans.Bij
-            self.lambda0 = trans.lambda0
+            self.Aji, self.Bji, self.Bij, self.lambda0 = trans.Aji, trans.Bji, trans.Bij, trans.lambda0
+            # the one per-depth quantity of a line the device needs from the model objects (atomic_model.py:491-502)
+            self.aDamp = trans.damping(atmos, compAtom.vBroad, compAtom.hPops.n[0])[0]
         else:
             self.alpha = trans.alpha
+            self.aDamp = None
         self.i = trans.i
         self.j = trans.j
         self.Nblue = int(np.searchsorted(spect.wavelength, self.wavelength[0]))     # rh_method.py:122
-        self._phi = None
-        self._wphi = None
-        self._atmos = atmos
-        self.aDamp = None
-        if getattr(compAtom.ctx, 'device_phi', False):
-            # the profiles are formed on the device (mali_compute_phi); the host only evaluates the damping parameter
-            if self.isLine:
-                self.aDamp = trans.damping(atmos, compAtom.vBroad, compAtom.hPops.n[0])[0]
-        else:
-            self.compute_phi(atmos)
-        self.active = np.zeros(spect.wavelength.shape[0], bool)
-        for i, s in enumerate(spect.activeSet):                                     # rh_method.py:125-127
+        Nlam = int(self.wavelength.shape[0])
+        self.active = np.zeros(spect.wavelength.shape[0], bool)                     # rh_method.py:125-127
+        for la, s in enumerate(spect.activeSet):
             if trans in s:
-                self.active[i] = True
+                self.active[la] = True
         self.gij = None
         self.Rij = np.zeros(atmos.Nspace)    # dead outputs of the reference (never zeroed, never read): not maintained
         self.Rji = np.zeros(atmos.Nspace)
         self.index = None                    # position in the flattened transition table
+        self._profile = None
+        del Nlam
 
     def lt(self, la):
         return la - self.Nblue
 
     def wlambda(self, la=None):
-        """rh_method.py:157-196"""
-        dopplerWidth = CLight / self.lambda0 if self.isLine else 1.0
-        wl = self.wavelength
-        if la is not None:
-            if la == 0:
-                return 0.5 * (wl[1] - wl[0]) * dopplerWidth
-            elif la == wl.shape[0] - 1:
-                return 0.5 * (wl[-1] - wl[-2]) * dopplerWidth
-            return 0.5 * (wl[la + 1] - wl[la - 1]) * dopplerWidth
-        wla = np.zeros_like(wl)
-        wla[0] = 0.5 * (wl[1] - wl[0])
-        wla[-1] = 0.5 * (wl[-1] - wl[-2])
-        wla[1:-1] = 0.5 * (wl[2:] - wl[:-2])
-        return dopplerWidth * wla
+        """Wavelength quadrature weights (rh_method.py:157-196), from the model tables the device uses."""
+        mt = self.atom.ctx._engine.mt
+        w = mt.wlambda[mt.toff[self.index]:mt.toff[self.index + 1]]
+        return np.array(w) if la is None else float(w[la])
 
-    def compute_phi(self, atmos):
-        """rh_method.py:198-243 (set-up; next-row candidate for a device Voigt kernel)."""
-        if not self.isLine:
-            return
-        sqrtPi = np.sqrt(np.pi)
-        aDamp, Qelast = self.transModel.damping(atmos, self.atom.vBroad, self.atom.hPops.n[0])
-        Nlambda = self.wavelength.shape[0]
-        phi = np.zeros((Nlambda, atmos.Nrays, 2, atmos.Nspace))
-        wPhi = np.zeros(atmos.Nspace)
-        wLambda = self.wlambda()
-        vlosDop = np.zeros((atmos.Nrays, atmos.Nspace))
-        for mu in range(atmos.Nrays):
-            vlosDop[mu, :] = atmos.muz[mu] * atmos.vlos / self.atom.vBroad
-        for la in range(Nlambda):
-            v = (self.wavelength[la] - self.lambda0) * CLight / (self.atom.vBroad * self.lambda0)
-            for mu in range(atmos.Nrays):
-                wlamu = wLambda * 0.5 * atmos.wmu[mu]
-                for toFrom, sign in enumerate([-1.0, 1.0]):
-                    vk = v + sign * vlosDop[mu]
-                    phi[la, mu, toFrom, :] = voigt_H(aDamp, vk) / (sqrtPi * self.atom.vBroad)
-                    wPhi[:] += phi[la, mu, toFrom, :] * wlamu[la]
-        self.aDamp = aDamp
-        self._wphi = 1.0 / wPhi
-        self._phi = phi
+    def _line_profile(self):
+        if self._profile is None:
+            self._profile = self.atom.ctx._engine.line_profile(self.atom.ctx._col, self.index)
+        return self._profile
 
     @property
     def phi(self):
-        """[Nlambda, Nrays, 2, Nspace] (rh_method.py:224); evaluated on first use when the Context forms its
-        profiles on the device."""
-        if self.isLine and self._phi is None:
-            self.compute_phi(self._atmos)
-        return self._phi
+        """[Nlambda, Nrays, 2, Nspace] (rh_method.py:224), read back from the device tables on first use."""
+        return self._line_profile()[0] if self.isLine else None
 
     @property
     def wphi(self):
-        if self.isLine and self._wphi is None:
-            self.compute_phi(self._atmos)
-        return self._wphi
+        return self._line_profile()[1] if self.isLine else None
 
     def uv(self, la, mu, toFrom):
         """rh_method.py:245-288, evaluated by the GPU from the packed tables (mali_uv)."""
@@ -196,12 +146,10 @@ class Context:
     same kernels over many columns per launch.
     """
 
-    def __init__(self, atmos, spect, eqPops, background, device=None, _host_only=False, device_phi=False):
-        """device_phi=True: the Voigt line profiles (ComputationalTransition.compute_phi, rh_method.py:198-243) are
-        formed on the GPU from the damping parameters instead of by the host loops -- same results to ~1e-13 (the
-        accuracy of the reference's scipy wofz) and most of the constructor's time saved; `trans.phi` / `trans.wphi`
-        are then evaluated on the host only if somebody reads them."""
-        self.device_phi = bool(device_phi)
+    def __init__(self, atmos, spect, eqPops, background, device=None, _host_only=False):
+        """The Voigt line profiles (ComputationalTransition.compute_phi, rh_method.py:198-243) are formed on the GPU
+        from the damping parameters -- same values to ~1e-13 (the accuracy of the scipy wofz the reference calls);
+        `trans.phi` / `trans.wphi` are read back from the device if somebody asks for them."""
         self.atmos = atmos
         self.atmos.nondimensionalise()                                    # rh_method.py:553
         self.spect = spect
@@ -217,10 +165,7 @@ class Context:
         if _host_only:      # unit tests of the host-side flattening only; every compute method then fails
             return
         self._engine = MaliEngine(self._problem, 1, device=device)
-        if self.device_phi:
-            self._engine.upload_device_phi([self._problem])
-        else:
-            self._engine.upload([self._problem])
+        self._engine.upload_device_phi([self._problem])
 
     # -- lazily fetched results (numpy, C order, the reference's shapes)
     def _get(self, key, fn):
@@ -279,10 +224,10 @@ class BatchContext:
     methods of the reference exist in batched form too: formal_sol_gamma_matrices() and stat_equil() return one
     value per column."""
 
-    def __init__(self, columns, device=None, device_phi=False):
+    def __init__(self, columns, device=None):
         if not columns:
             raise ValueError('BatchContext needs at least one column')
-        self.contexts = [Context(*c, _host_only=True, device_phi=device_phi) for c in columns]
+        self.contexts = [Context(*c, _host_only=True) for c in columns]
         problems = [c._problem for c in self.contexts]
         p0 = problems[0]
         for q in problems[1:]:
@@ -293,10 +238,7 @@ class BatchContext:
                 if not np.array_equal(np.asarray(q[key]), np.asarray(p0[key])):
                     raise ValueError('columns of a batch must share the radiative model (%s differs)' % key)
         self._engine = MaliEngine(p0, len(problems), device=device)
-        if device_phi:
-            self._engine.upload_device_phi(problems)
-        else:
-            self._engine.upload(problems)
+        self._engine.upload_device_phi(problems)
         for k, c in enumerate(self.contexts):
             c._engine, c._col, c._borrowed = self._engine, k, True
 
@@ -350,14 +292,13 @@ class BatchContext:
 
 
 def flatten_context(ctx):
-    """Reference-layout problem dict (lightspinner_b200/tables.py) from the host mirrors of a Context."""
+    """Reference-layout problem dict (lightspinner_b200/tables.py) from the host mirrors of a Context: everything but
+    the line profiles, for which it carries what compute_phi consumes (aDamp, vBroad, vlos)."""
     atmos, spect, bg = ctx.atmos, ctx.spect, ctx.background
     N = atmos.Nspace
-    Nlevel, trans, linepar, alpha, phi, phioff, wphi = [], [], [], [], [], [], []
+    Nlevel, trans, linepar, alpha = [], [], [], []
     nStar, nTotal, Cs, ns = [], [], [], []
     aDamp, vBroad = [], []
-    dev_phi = bool(getattr(ctx, 'device_phi', False))
-    off = 0
     it = 0
     for ia, atom in enumerate(ctx.activeAtoms):
         vBroad.append(np.asarray(atom.vBroad, dtype=np.float64))
@@ -382,19 +323,10 @@ def flatten_context(ctx):
             if t.isLine:
                 linepar.append([t.Aji, t.Bji, t.Bij, t.lambda0])
                 alpha.append(np.zeros(Nlam))
-                phioff.append(off)
-                if not dev_phi:
-                    phi.append(np.ascontiguousarray(t.phi).ravel())
-                    off += t.phi.size
-                    wphi.append(np.asarray(t.wphi, dtype=np.float64))
-                else:
-                    wphi.append(np.zeros(N))
                 aDamp.append(np.asarray(t.aDamp, dtype=np.float64))
             else:
                 linepar.append([0.0, 0.0, 0.0, 0.0])
                 alpha.append(np.asarray(t.alpha, dtype=np.float64))
-                phioff.append(0)
-                wphi.append(np.zeros(N))
                 aDamp.append(np.zeros(N))
     return dict(
         Nspace=N, Nrays=atmos.Nrays, Nspect=int(spect.wavelength.shape[0]),
@@ -405,8 +337,7 @@ def flatten_context(ctx):
         height=np.asarray(atmos.height, dtype=np.float64), temperature=np.asarray(atmos.temperature, dtype=np.float64),
         bg_chi=np.asarray(bg.chi), bg_eta=np.asarray(bg.eta), bg_sca=np.asarray(bg.sca),
         nStar=np.concatenate(nStar, axis=0), nTotal=np.stack(nTotal), C=np.concatenate(Cs, axis=0),
-        n=np.concatenate(ns, axis=0), phi=np.concatenate(phi) if phi else np.zeros(0),
-        phioff=np.array(phioff, dtype=np.int64), wphi=np.stack(wphi) if wphi else np.zeros((0, N)),
+        n=np.concatenate(ns, axis=0),
         aDamp=np.stack(aDamp) if aDamp else np.zeros((0, N)), vBroad=np.stack(vBroad),
         vlos=np.asarray(atmos.vlos, dtype=np.float64))
 

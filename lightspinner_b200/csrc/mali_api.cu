@@ -122,6 +122,7 @@ static const SpecEntry *find_spec(const std::string &key)
 // ---------------------------------------------------------------------------------------------------------
 struct mali_model {
     int device = 0;
+    int arith = MALI_ARITH_EXACT;   // arithmetic mode of the specialised formal-solution kernels (mali_model_set_arith)
     int N = 0, Nrays = 0, Nspect = 0, Natom = 0, Ntrans = 0, Lw = 0, ntile = 0, Dmax = 0, Tmax = 0;
     int sumNlevel = 0, sumNlevel2 = 0, maxNlevel = 0, nPartRows = 0;
     std::vector<int32_t> Nlevel, lvlOff, g2Off, trans, toff;
@@ -152,6 +153,8 @@ struct mali_model {
     PhiLine *d_phiLines = nullptr;
     double *d_wavelength = nullptr, *d_muz = nullptr, *d_wmu = nullptr;
     int nPhiLines = 0;
+    std::vector<std::vector<PhiTile>> phiTilesHost;   // per transition: where its profile entries live (mali_line_layout)
+    std::vector<int32_t> phiTile0Host;
     bool haveLambda0 = false;
     CopyJob *d_cjobs = nullptr;
     PackChunk *d_pchunks = nullptr;
@@ -215,10 +218,15 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
     CU(mali_fs_set_attr_0());
     CU(mali_fs_set_attr_1());
     CU(mali_fs_set_attr_2());
+    CU(mali_fs_set_attr_0_fast());
+    CU(mali_fs_set_attr_1_fast());
+    CU(mali_fs_set_attr_2_fast());
     CU(cudaFuncSetAttribute(fs_gamma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 
     auto *m = new mali_model();
     m->device = device;
+    if (const char *a = getenv("MALI_ARITH")) m->arith = (strcmp(a, "exact") == 0) ? MALI_ARITH_EXACT : MALI_ARITH_CONTRACTED;
+    else m->arith = MALI_ARITH_DEFAULT;
     m->N = d->Nspace;
     m->Nrays = d->Nrays;
     m->Nspect = d->Nspect;
@@ -468,12 +476,23 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
         }
     };
     const bool noSpec = getenv("MALI_NO_SPEC") != nullptr;
+    // heaviest tiles first (the light ones fill the tail of a launch), and tiles of one structure next to each other
+    // (co-resident blocks then run the same kernel instance: one instruction stream per SM)
+    std::vector<const SpecEntry *> specOf(m->ntile, nullptr);
+    for (int ti = 0; ti < m->ntile; ++ti) {
+        const TileDesc &td = m->tiles[ti];
+        if (!noSpec && td.nslot <= kSpecMaxSlots && d->Natom <= 4) specOf[ti] = find_spec(structure_key(td));
+    }
     std::vector<int> order(m->ntile);
     for (int ti = 0; ti < m->ntile; ++ti) order[ti] = ti;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return m->tiles[a].nslot > m->tiles[b].nslot; });
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        if (m->tiles[a].nslot != m->tiles[b].nslot) return m->tiles[a].nslot > m->tiles[b].nslot;
+        const int ia = specOf[a] ? specOf[a]->id : -1, ib = specOf[b] ? specOf[b]->id : -1;
+        return ia < ib;
+    });
     for (int ti : order) {
         const TileDesc &td = m->tiles[ti];
-        const SpecEntry *e = (!noSpec && td.nslot <= kSpecMaxSlots && d->Natom <= 4) ? find_spec(structure_key(td)) : nullptr;
+        const SpecEntry *e = specOf[ti];
         if (!e) {
             m->genericTiles.push_back(ti);
             continue;
@@ -564,6 +583,8 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
             tv.insert(tv.end(), phiT[t].begin(), phiT[t].end());
         }
         m->nPhiLines = (int)lines.size();
+        m->phiTilesHost = phiT;
+        m->phiTile0Host = phiTile0;
         m->haveLambda0 = d->lambda0 != nullptr;
         up(to_device(lines, &m->d_phiLines));
         up(to_device(tv, &m->d_phiTiles));
@@ -615,6 +636,15 @@ void mali_model_destroy(mali_model *m)
     if (m->forkEvent) cudaEventDestroy(m->forkEvent);
     delete m;
 }
+
+int mali_model_set_arith(mali_model *m, int32_t mode)
+{
+    if (!m || (mode != MALI_ARITH_EXACT && mode != MALI_ARITH_CONTRACTED)) return fail(MALI_EINVAL, "mali_model_set_arith: bad argument");
+    m->arith = mode;
+    return MALI_OK;
+}
+
+int mali_model_get_arith(const mali_model *m) { return m ? m->arith : MALI_EINVAL; }
 
 int mali_model_layout(const mali_model *m, mali_layout *out)
 {
@@ -860,11 +890,16 @@ static int launch_fs(const mali_model *m, const mali_buffers *b, int col0, int n
             CU(cudaStreamWaitEvent(s0, m->forkEvent, 0));
         }
         cudaError_t e = cudaSuccess;
-        if (!m->spec2.empty()) e = mali_fs_launch_2(cc, m->spec2.data(), (int)m->spec2.size(), ncol, smem[2], st, &m->launches);
+        const bool fast = m->arith == MALI_ARITH_CONTRACTED;
+        if (!m->spec2.empty())
+            e = (fast ? mali_fs_launch_2_fast : mali_fs_launch_2)(cc, m->spec2.data(), (int)m->spec2.size(), ncol, smem[2], st,
+                                                                  &m->launches);
         if (e == cudaSuccess && !m->spec1.empty())
-            e = mali_fs_launch_1(cc, m->spec1.data(), (int)m->spec1.size(), ncol, smem[1], s1, &m->launches);
+            e = (fast ? mali_fs_launch_1_fast : mali_fs_launch_1)(cc, m->spec1.data(), (int)m->spec1.size(), ncol, smem[1], s1,
+                                                                  &m->launches);
         if (e == cudaSuccess && !m->spec0.empty())
-            e = mali_fs_launch_0(cc, m->spec0.data(), (int)m->spec0.size(), ncol, smem[0], s0, &m->launches);
+            e = (fast ? mali_fs_launch_0_fast : mali_fs_launch_0)(cc, m->spec0.data(), (int)m->spec0.size(), ncol, smem[0], s0,
+                                                                  &m->launches);
         if (e != cudaSuccess) return fail((int)e, "fs_gamma_kernel_m: %s", cudaGetErrorString(e));
         if (side1) {   // join
             CU(cudaEventRecord(m->joinEvent[0], s1));
@@ -998,6 +1033,26 @@ int mali_profile_end(const mali_model *m, double *fs_ms_total, int32_t *fs_launc
 }
 
 long long mali_launch_count(const mali_model *m) { return m ? m->launches : 0; }
+
+int mali_line_layout(const mali_model *m, int32_t t, int32_t *tile0, int32_t *ntile, int32_t *entries, int32_t cap,
+                     int64_t *off_tab)
+{
+    if (!m || !tile0 || !ntile || !off_tab || t < 0 || t >= m->Ntrans) return fail(MALI_EINVAL, "mali_line_layout: bad argument");
+    const std::vector<PhiTile> &v = m->phiTilesHost[t];
+    *tile0 = m->phiTile0Host[t];
+    *ntile = (int32_t)v.size();
+    *off_tab = m->off_tab;
+    if (entries) {
+        if (cap < (int32_t)v.size()) return fail(MALI_EINVAL, "mali_line_layout: room for %d tiles, the line spans %zu", cap, v.size());
+        for (size_t q = 0; q < v.size(); ++q) {
+            entries[4 * q + 0] = v[q].v0;
+            entries[4 * q + 1] = v[q].vDir;
+            entries[4 * q + 2] = v[q].f;
+            entries[4 * q + 3] = v[q].stride;
+        }
+    }
+    return MALI_OK;
+}
 
 int mali_div_hook(int32_t n, const double *a_dev, const double *b_dev, double *q_dev, int32_t *bad_dev, void *stream)
 {

@@ -10,7 +10,10 @@
 #include "mali_fs_launch.h"
 
 #ifndef MALI_CLS
-#error "compile with -DMALI_CLS=0|1|2"
+#error "compile with -DMALI_CLS=0|1|2 -DMALI_FAST=0|1"
+#endif
+#ifndef MALI_FAST
+#define MALI_FAST 0
 #endif
 
 using namespace mali;
@@ -29,24 +32,27 @@ using namespace mali;
 
 namespace mali {
 // One kernel per register class; the structure id of the tile and the sweep direction select the specialised body
-// (a block-uniform switch).  blockIdx.x runs over columns, blockIdx.y over (tile, sweep direction): co-resident blocks
-// share a structure and a direction, hence one instruction stream per SM.  The down and the up sweep of a tile are
-// independent warps (their partial sums go to separate scratch copies), which doubles the parallelism of small
-// launches and halves the tail of every wave.
-template <int CLS>
+// (a block-uniform switch).  blockIdx.x runs over columns, blockIdx.y over (sweep direction, tile) with the tiles
+// sorted by structure: blocks that are resident together share a structure and a direction, hence (nearly always)
+// ONE instruction stream per SM -- the depth loop of an instance is 5-12 KB of SASS, and a second or third stream on
+// the same SM overflows the 32 KB instruction cache level (ncu: no_instruction was the top stall with interleaved
+// directions).  The down and the up sweep of a tile are independent warps (their partial sums go to separate scratch
+// copies), which doubles the parallelism of small launches and halves the tail of every wave.
+template <int CLS, bool FAST>
 __global__ void __launch_bounds__(32, spec_class_warps(CLS)) fs_gamma_kernel_m(const __grid_constant__ MegaParams<CLS> P)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const TileR<MegaParams<CLS>::NSP> &T = P.tiles[blockIdx.y >> 1];
-    const int dir = blockIdx.y & 1;
+    const int nt = gridDim.y >> 1;
+    const int dir = blockIdx.y >= nt ? 1 : 0;
+    const TileR<MegaParams<CLS>::NSP> &T = P.tiles[blockIdx.y - dir * nt];
     switch (T.spec) {
 #define MALI_SPEC(ID, KEY, ...)                                                     \
     case ID:                                                                        \
         if constexpr (spec_class(SpecTag##ID::S.nslot) == CLS) {                    \
             if (dir == 0)                                                           \
-                fs_body<SpecTag##ID, MegaParams<CLS>::NSP, 0>(P.c, T, smem_raw);    \
+                fs_body<SpecTag##ID, MegaParams<CLS>::NSP, 0, FAST>(P.c, T, smem_raw); \
             else                                                                    \
-                fs_body<SpecTag##ID, MegaParams<CLS>::NSP, 1>(P.c, T, smem_raw);    \
+                fs_body<SpecTag##ID, MegaParams<CLS>::NSP, 1, FAST>(P.c, T, smem_raw); \
         }                                                                           \
         break;
 #include MALI_SPEC_INC
@@ -59,14 +65,20 @@ __global__ void __launch_bounds__(32, spec_class_warps(CLS)) fs_gamma_kernel_m(c
 
 #define MALI_CAT2(a, b) a##b
 #define MALI_CAT(a, b) MALI_CAT2(a, b)
+#if MALI_FAST
+#define MALI_FN(stem) MALI_CAT(MALI_CAT(stem, MALI_CLS), _fast)
+#else
+#define MALI_FN(stem) MALI_CAT(stem, MALI_CLS)
+#endif
 
-cudaError_t MALI_CAT(mali_fs_set_attr_, MALI_CLS)()
+cudaError_t MALI_FN(mali_fs_set_attr_)()
 {
-    return cudaFuncSetAttribute(fs_gamma_kernel_m<MALI_CLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    return cudaFuncSetAttribute(fs_gamma_kernel_m<MALI_CLS, MALI_FAST != 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                227 * 1024);
 }
 
-cudaError_t MALI_CAT(mali_fs_launch_, MALI_CLS)(const FsCommon &c, const void *tiles, int nt, int ncol, size_t smem,
-                                               cudaStream_t st, long long *launches)
+cudaError_t MALI_FN(mali_fs_launch_)(const FsCommon &c, const void *tiles, int nt, int ncol, size_t smem, cudaStream_t st,
+                                     long long *launches)
 {
     using MP = MegaParams<MALI_CLS>;
     using TR = TileR<MP::NSP>;
@@ -78,13 +90,13 @@ cudaError_t MALI_CAT(mali_fs_launch_, MALI_CLS)(const FsCommon &c, const void *t
         const int n = std::min(MP::kMaxTiles, nt - t0);
         memcpy(P->tiles, src + t0, sizeof(TR) * n);
         dim3 grid(ncol, 2 * n);
-        fs_gamma_kernel_m<MALI_CLS><<<grid, 32, smem, st>>>(*P);
+        fs_gamma_kernel_m<MALI_CLS, MALI_FAST != 0><<<grid, 32, smem, st>>>(*P);
         if (launches) *launches += 1;
     }
     return cudaGetLastError();
 }
 
-#if MALI_CLS == 0
+#if MALI_CLS == 0 && !MALI_FAST
 // registry of the ahead-of-time instances (structure key -> id), used by the host to route tiles
 #define MALI_SPEC(ID, KEY, ...) {KEY, SpecTag##ID::S.nslot, ID},
 static const SpecEntry kSpecRegistry[] = {

@@ -4,14 +4,16 @@
 
 #include "mali_fs_spec.cuh"
 
-cudaError_t mali_fs_set_attr_0();
-cudaError_t mali_fs_set_attr_1();
-cudaError_t mali_fs_set_attr_2();
-// tiles: array of TileR<2> / TileR<4> / TileR<8>
-cudaError_t mali_fs_launch_0(const mali::FsCommon &c, const void *tiles, int nt, int ncol, size_t smem, cudaStream_t st,
-                             long long *launches);
-cudaError_t mali_fs_launch_1(const mali::FsCommon &c, const void *tiles, int nt, int ncol, size_t smem, cudaStream_t st,
-                             long long *launches);
-cudaError_t mali_fs_launch_2(const mali::FsCommon &c, const void *tiles, int nt, int ncol, size_t smem, cudaStream_t st,
-                             long long *launches);
+// exact arithmetic (the reference's rounding) and, suffix _fast, contracted arithmetic (mali_device.cuh, Arith)
+#define MALI_FS_DECL(SUFFIX)                                                                                          \
+    cudaError_t mali_fs_set_attr_##SUFFIX();                                                                          \
+    cudaError_t mali_fs_launch_##SUFFIX(const mali::FsCommon &c, const void *tiles /* TileR<2|4|8>[] */, int nt,       \
+                                        int ncol, size_t smem, cudaStream_t st, long long *launches);
+MALI_FS_DECL(0)
+MALI_FS_DECL(1)
+MALI_FS_DECL(2)
+MALI_FS_DECL(0_fast)
+MALI_FS_DECL(1_fast)
+MALI_FS_DECL(2_fast)
+#undef MALI_FS_DECL
 const mali::SpecEntry *mali_fs_registry();

@@ -192,9 +192,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 
 // SPEC is a tag type with a `static constexpr TileStruct S` member (the structure travels inside a type).
 // DIR: 0 = downward sweep from the top (k = 0), 1 = upward sweep from the bottom (k = N - 1).
-template <class SPEC, int NSP, int DIR>
+// FAST: arithmetic mode (mali_device.cuh, Arith): false = the reference's rounding, true = contracted.
+template <class SPEC, int NSP, int DIR, bool FAST>
 __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, unsigned char *smem_raw)
 {
+    using A = Arith<FAST>;
     constexpr TileStruct S = SPEC::S;
     constexpr int NS = S.nslot;
     constexpr int NSA = NS > 0 ? NS : 1;
@@ -238,7 +240,7 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
 
     const double *__restrict__ cc = p.colconst + (size_t)col * p.colStride;
     double *scr = p.scratch + (size_t)col * p.scratchStride + (DIR ? p.upOff : 0);
-    double *jlane = scr + p.off_jpart + laC;                                   // + k * Nspect
+    double *jp = scr + p.off_jpart + laC + (size_t)(DIR ? p.N - 1 : 0) * p.Nspect;   // J partial of the current depth
     // ---- per-warp shared memory: TMA ring | Gamma reduce scratch | ring barriers | exp table
     double *ring = reinterpret_cast<double *>(smem_raw);
     double *red = ring + NST * STAGE;
@@ -313,7 +315,8 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
     const double hwG = valid ? hw : 0.0;
     const double bbc0 = cc[p.off_bbc + 2 * laC], bbc1 = cc[p.off_bbc + 2 * laC + 1];
     const double fourPi = 4.0 * kPi;
-    const double r3 = rcp_full(3.0);
+    const double hw4pi = hwG * fourPi;
+    const double r3 = A::rcp(3.0);
     double ca[NSA], cb[NSA], cw[NSA];   // continuum slots: alpha, 2hc/lambda^3, wlamu
 #pragma unroll
     for (int tt = 0; tt < NS; ++tt) {
@@ -338,27 +341,35 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
     // Gamma value owned by this lane after the reduce, and where its partial sums live
     const int eOwn = lane / RG;
     const bool writer = (lane % RG) == 0 && eOwn < M && NS > 0;
-    double *glane = scr + p.off_part + (size_t)(T.partRow0 + (eOwn < M ? eOwn : 0)) * N;   // + k
+    double *gp = scr + p.off_part + (size_t)(T.partRow0 + (eOwn < M ? eOwn : 0)) * N + (DIR ? N - 1 : 0);
+    const ptrdiff_t jstep = (ptrdiff_t)dk * Nspect;      // the partial-sum pointers advance with the sweep
 
-    SweepT<1> sw;
+    SweepT<1, FAST> sw;
     sw.r3 = r3;
     sw.stab = stab;
     double xP = 0.0;   // this lane's J term of the previous step: its mu-sum is taken during the next step
 
     // second half of the previous step's reductions (its depth: kq): Gamma partial of the lane's matrix entry and the
     // mu-sum of J, rh_method.py:640.  The down and the up sweep write separate partials; the finish kernels add them.
-    auto finish_prev = [&](int kq) {
+    auto finish_prev = [&]() {
         if constexpr (NS > 0) {
             const double tot = reduce_load<M>(lane, red);
-            if (writer) __stcg(glane + kq, tot);
+            if (writer) __stcg(gp, tot);
         }
         double sum = xP;
+        if constexpr (NR <= 6) {   // few angles: pull every other lane's term (no masking; only the leader's sum is used)
 #pragma unroll
-        for (int q = 0; (1 << q) < NR; ++q) {
-            const double t = __shfl_down_sync(0xffffffffu, sum, 1 << q);
-            if (jadd[q]) sum = sum + t;
+            for (int m = 1; m < NR; ++m) sum += __shfl_down_sync(0xffffffffu, xP, m);
+        } else {                   // many angles: a masked tree
+#pragma unroll
+            for (int q = 0; (1 << q) < NR; ++q) {
+                const double t = __shfl_down_sync(0xffffffffu, sum, 1 << q);
+                if (jadd[q]) sum = sum + t;
+            }
         }
-        if (leader) __stcg(jlane + (size_t)kq * Nspect, sum);
+        if (leader) __stcg(jp, sum);
+        gp += dk;
+        jp += jstep;
     };
 
     const int kS = DIR ? N - 1 : 0;
@@ -385,10 +396,10 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
             const double ni = nk[S.rowI[tt]], nj = nk[S.rowJ[tt]];
             if (S.kind[tt]) {
                 const double ld = sv[ST1 + line_index(tt) * kVRow];
-                chiTot += ni * ld - nj * (T.s[tt].cA * ld);
+                chiTot += A::nmad(nj, T.s[tt].cA * ld, ni * ld);
             } else {
                 const double ld = sf[ST1 + (3 + tt) * LW];
-                chiTot += ni * ca[tt] - nj * (ld * ca[tt]);
+                chiTot += A::nmad(nj, ld * ca[tt], ni * ca[tt]);
             }
         }
         chiProbe = chiTot + sf[ST1];
@@ -441,9 +452,9 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
 #undef STEP_SLOT
 #undef STEP_KIND
     }
-    finish_prev(k - dk);
+    finish_prev();
     if (DIR == 1 && valid) p.I[(size_t)col * p.IStride + (size_t)la * NR + mu] = sw.Iupw;
-    if (valid && sw.bad && p.status != nullptr) atomicOr(p.status + col, 2);
+    if (valid && sw.bad() && p.status != nullptr) atomicOr(p.status + col, 2);
 #undef line_index
 #undef SET_STAGE
 }

@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(128) fs_gamma_kernel(const FsParams p)
         }
         // emergent intensity: rh_method.py:638 (the upgoing value survives)
         if (d == 1 && valid) p.I[(size_t)col * p.IStride + (size_t)la * Nrays + mu] = sw.Iupw;
-        if (valid && sw.bad && p.status != nullptr) atomicOr(p.status + col, 2);
+        if (valid && sw.bad() && p.status != nullptr) atomicOr(p.status + col, 2);
     }
 
 #undef CHI_L

