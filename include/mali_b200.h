@@ -16,6 +16,8 @@
  *   planck                      utils.py:17-22              mali_planck_bc (host helper for the lower boundary)
  *   Context.stat_equil          rh_method.py:710-745        mali_stat_equil
  *   test.py:20-29 / response_fn.py:11-21 (the MALI loop)    mali_iterate (device-resident loop, per-column convergence)
+ *   lte_pops atomic_set.py:105-145, compute_collisions rh_method.py:474-487, v_broad atomic_model.py:241-245,
+ *   continuum g_ij rh_method.py:453-454                     mali_model_set_atoms + mali_setup_columns (device-side set-up)
  *   ComputationalTransition.compute_phi rh_method.py:198-243 mali_compute_phi (device Voigt profiles); mali_line_layout = read-back
  *
  * Conventions
@@ -83,7 +85,7 @@ typedef struct {
     int64_t hp_bbc;      /* [Nspect][2]  planck(T[-2:], wav)  (formal_solver.py:206) */
     int64_t hp_bg_chi, hp_bg_eta, hp_bg_sca; /* [Nspect][Nspace] */
     int64_t hp_C;        /* concat atoms [Nlevel][Nlevel][Nspace] */
-    int64_t hp_nTotal;   /* [Natom][Nspace] */
+    int64_t hp_nTotal;   /* [Natom][Nspace] (stored BEFORE hp_C: a caller using mali_setup_columns uploads only [0, hp_C)) */
     int64_t hp_gijcont;  /* concat [offset+lt][Nspace], continua rows only (rh_method.py:453-454) */
     int64_t hp_n;        /* [sumNlevel][Nspace] starting populations */
     /* the line profiles come last, so that a caller who lets the device compute them (mali_compute_phi) uploads
@@ -152,6 +154,45 @@ int mali_upload_columns(const mali_model *m, const mali_buffers *bufs, int32_t c
  * The profile entries of the device tables are zeroed; call mali_compute_phi before the first formal solution. */
 int mali_upload_columns_nophi(const mali_model *m, const mali_buffers *bufs, int32_t col0, int32_t ncol,
                               const double *host_pack_prefix, double *staging_dev, void *stream);
+
+/* Same again, for callers that let the device form everything it can from the atmosphere: host_pack_prefix holds
+ * [ncol][layout.hp_C] doubles (heights, boundary Planck values, background chi / eta / sca, nTotal); call
+ * mali_setup_columns and mali_compute_phi before the first formal solution. */
+int mali_upload_columns_atmos(const mali_model *m, const mali_buffers *bufs, int32_t col0, int32_t ncol,
+                              const double *host_pack_prefix, double *staging_dev, void *stream);
+
+/* Model-level data of the active atoms for the device-side column set-up (mali_setup_columns): what lte_pops
+ * (atomic_set.py:105-145), the collisional-rate terms (collisional_rates.py:36-96) and v_broad (atomic_model.py:241-245)
+ * read from the atomic-model objects.  Level arrays are concatenated over the atoms in the model's order. */
+typedef struct {
+    int32_t Natom;
+    const int32_t *Nlevel;   /* [Natom], must equal the model's */
+    const double *dE;        /* E_SI[l] - E_SI[0]                                  (atomic_set.py:131) */
+    const double *gi0;       /* g[l] / g[0]                                        (:132) */
+    const int32_t *dZ;       /* stage[l] - stage[0]                                (:133) */
+    const double *nDebye;    /* Debye shift count of the level                     (:113-119) */
+    const double *g;         /* statistical weights g[l] */
+    const double *vTherm;    /* [Natom] 2 k / (amu * atomic weight)                (atomic_model.py:242) */
+    double c1, c2;           /* atomic_set.py:107, :111 evaluated by the host */
+    int32_t Ncoll;
+    const int32_t *coll;     /* [Ncoll][8]: atom, kind (0 Omega, 1 CI, 2 CE), i, j (i < j), table points n, offset into
+                                knots, offset into coef, cubic (1) or linear (0); the model's order (rates are added in
+                                that order); offsets are running sums */
+    const double *knots;     /* the interpolant of collisional_rates.py:15-19 (scipy interp1d) per collision: cubic: the
+                                n + 4 knots of its not-a-knot B-spline; linear (2-point tables): the n temperatures */
+    const double *coef;      /* cubic: the n B-spline coefficients; linear: the n rates */
+    const double *fill;      /* [Ncoll][2]: values below / above the table (rates[0], rates[-1]) */
+    const double *par;       /* [Ncoll]: Omega: C0 (collisional_rates.py:35); CI: E_SI[j] - E_SI[i]; CE: g[i] / g[j] */
+} mali_atom_desc;
+int mali_model_set_atoms(mali_model *m, const mali_atom_desc *atoms);
+
+/* lte_pops + compute_collisions + v_broad + the continua's g_ij (rh_method.py:453-454) for columns [col0, col0+ncol),
+ * from T, ne, vturb [ncol][Nspace] (device) and the nTotal the upload put into colconst: writes C and the g_ij fields
+ * into colconst, nStar [ncol][sumNlevel][Nspace] and vBroad [ncol][Natom][Nspace] (device, caller-owned; vBroad is what
+ * mali_compute_phi takes), and -- start_from_lte != 0 -- the populations n = nStar (rh_method.py:415). */
+int mali_setup_columns(const mali_model *m, const mali_buffers *bufs, int32_t col0, int32_t ncol, const double *T_dev,
+                       const double *ne_dev, const double *vturb_dev, double *nStar_dev, double *vBroad_dev,
+                       int32_t start_from_lte, void *stream);
 
 /* ComputationalTransition.compute_phi (rh_method.py:198-243) on the device, for columns [col0, col0+ncol): Voigt
  * profiles phi[la][mu][toFrom][k] = H(aDamp, v -+ mu vlos / vBroad) / (sqrt(pi) vBroad) of every line and their

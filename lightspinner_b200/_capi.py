@@ -25,6 +25,12 @@ class ModelDesc(C.Structure):
                 ('wlacont', _dp), ('lambda0', _dp)]
 
 
+class AtomDesc(C.Structure):
+    _fields_ = [('Natom', C.c_int32), ('Nlevel', _ip), ('dE', _dp), ('gi0', _dp), ('dZ', _ip), ('nDebye', _dp), ('g', _dp),
+                ('vTherm', _dp), ('c1', C.c_double), ('c2', C.c_double), ('Ncoll', C.c_int32), ('coll', _ip),
+                ('knots', _dp), ('coef', _dp), ('fill', _dp), ('par', _dp)]
+
+
 class Layout(C.Structure):
     _fields_ = [(n, C.c_int64) for n in (
         'hostpack', 'colconst', 'pops', 'J', 'I', 'Gamma', 'scratch', 'hp_height', 'hp_bbc', 'hp_bg_chi',
@@ -41,7 +47,8 @@ class Buffers(C.Structure):
 EXPORTS = ['mali_last_error', 'mali_device_count', 'mali_model_create', 'mali_model_destroy', 'mali_model_layout', 'mali_model_info',
            'mali_planck_bc', 'mali_upload_columns', 'mali_upload_columns_nophi', 'mali_compute_phi', 'mali_formal_sol_gamma', 'mali_stat_equil', 'mali_iterate',
            'mali_piecewise_linear_1d', 'mali_uv', 'mali_exp_hook', 'mali_div_hook', 'mali_profile_begin',
-           'mali_profile_end', 'mali_launch_count', 'mali_fp64_peak', 'mali_line_layout', 'mali_model_set_arith', 'mali_model_get_arith']
+           'mali_profile_end', 'mali_launch_count', 'mali_fp64_peak', 'mali_line_layout', 'mali_model_set_arith', 'mali_model_get_arith',
+           'mali_upload_columns_atmos', 'mali_model_set_atoms', 'mali_setup_columns']
 
 ARITH_EXACT, ARITH_CONTRACTED = 0, 1
 
@@ -69,6 +76,10 @@ def load(path=None):
     L.mali_upload_columns.argtypes = [C.c_void_p, C.POINTER(Buffers), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                       C.c_void_p]
     L.mali_upload_columns_nophi.argtypes = L.mali_upload_columns.argtypes
+    L.mali_upload_columns_atmos.argtypes = L.mali_upload_columns.argtypes
+    L.mali_model_set_atoms.argtypes = [C.c_void_p, C.POINTER(AtomDesc)]
+    L.mali_setup_columns.argtypes = [C.c_void_p, C.POINTER(Buffers), C.c_int32, C.c_int32] + [C.c_void_p] * 5 + \
+        [C.c_int32, C.c_void_p]
     L.mali_compute_phi.argtypes = [C.c_void_p, C.POINTER(Buffers), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p]
     for name in ('mali_formal_sol_gamma', 'mali_stat_equil'):

@@ -24,6 +24,8 @@ DEPS = ['mali_api.cu', 'mali_fs_class.cu', 'mali_fs_launch.h', 'mali_kernels.cuh
 EXTRA = os.environ.get('MALI_NVCC_EXTRA', '').split()
 NVCC_FLAGS = EXTRA + ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '--fmad=false', '-std=c++20',
                       '-Xcompiler', '-fPIC', '-Xcompiler', '-ffp-contract=off', '-Xcompiler', '-O2']
+API_ONLY = {'mali_api.cu', 'mali_kernels.cuh', os.path.join('..', '..', 'include', 'mali_b200.h')}
+FS_ONLY = {'mali_fs_class.cu', 'mali_fs_step.inc', 'spec_instances.inc'}
 # (object name, source, extra flags)
 UNITS = [('fs1', 'mali_fs_class.cu', ['-DMALI_CLS=1']), ('fs1f', 'mali_fs_class.cu', ['-DMALI_CLS=1', '-DMALI_FAST=1']),
          ('fs2', 'mali_fs_class.cu', ['-DMALI_CLS=2']), ('fs2f', 'mali_fs_class.cu', ['-DMALI_CLS=2', '-DMALI_FAST=1']),
@@ -55,15 +57,27 @@ def build(force=False, verbose=False, lib=None, spec_inc=None, defines=()):
     nvcc = nvcc_path()
     ccbin = ['-ccbin', '/usr/bin/g++' if os.path.isfile('/usr/bin/g++') else 'g++']
     tag = os.path.basename(lib)
-    objdir = os.path.join(LIBDIR, 'obj_' + tag)
+    objdir = os.path.join(HERE, '_obj', tag)      # objects are kept for incremental builds (git- and gpurun-ignored)
     os.makedirs(objdir, exist_ok=True)
+
+    class _Ok:
+        returncode, stdout, stderr = 0, '', ''
 
     def compile_unit(u):
         name, src, flags = u
         obj = os.path.join(objdir, name + '.o')
         cmd = [nvcc] + NVCC_FLAGS + extra + flags + (['-Xptxas', '-v'] if verbose else []) + ccbin + \
             ['-c', '-o', obj, os.path.join(CSRC, src)]
+        # incremental: an object is kept while none of ITS sources (and no option) changed
+        deps = [d for d in DEPS if d not in (FS_ONLY if name == 'api' else API_ONLY)]
+        stamp = obj + '.cmd'
+        if (os.path.isfile(obj) and os.path.isfile(stamp) and open(stamp).read() == ' '.join(cmd)
+                and all(os.path.getmtime(os.path.join(CSRC, d)) <= os.path.getmtime(obj) for d in deps)
+                and (not spec_inc or os.path.getmtime(spec_inc) <= os.path.getmtime(obj))):
+            return obj, _Ok
         res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode == 0:
+            open(stamp, 'w').write(' '.join(cmd))
         return obj, res
 
     with ThreadPoolExecutor(max_workers=len(UNITS)) as ex:
@@ -83,7 +97,6 @@ def build(force=False, verbose=False, lib=None, spec_inc=None, defines=()):
     if res.returncode != 0:
         raise RuntimeError('link failed for %s' % os.path.basename(lib))
     os.replace(lib + '.tmp', lib)
-    shutil.rmtree(objdir, ignore_errors=True)
     return lib
 
 

@@ -53,26 +53,55 @@ cudaError_t to_device(const std::vector<T> &h, T **d)
     return e;
 }
 
-__global__ void col_zero_bits_kernel(unsigned long long *bits, const int32_t *done, const int32_t *iter, int iterMin,
-                                     int col0, int ncol)
+// First kernel of every statistical-equilibrium stage: inside mali_iterate it counts the iteration (test.py:24;
+// the formal solution of this iteration is done), then resets dPops of the columns that are about to be solved.
+__global__ void se_prepare_kernel(unsigned long long *bits, const int32_t *done, int32_t *iter, int iterMin, int count,
+                                  int col0, int ncol)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncol) return;
     const int col = col0 + c;
     if (done != nullptr && done[col] != 0) return;
-    if (iter != nullptr && iter[col] < iterMin) return;
+    if (iter != nullptr) {
+        if (count) iter[col] += 1;
+        if (iter[col] < iterMin) return;
+    }
     bits[col] = 0ull;
 }
 
 // First kernel of every formal solution, one block per column: resets dJ and rebuilds the depth-major popsT table
 // (mali_types.cuh) from the heights and the CURRENT populations n[level][k] -- the caller may have edited them since
 // the last call, as the reference's users do through the eqPops alias.
+// Inside mali_iterate (ctl.on) it also closes the previous iteration of the loop of test.py:20-29 for its column:
+// the convergence test on that iteration's (dJ, dPops), and a stop on a fault.
+struct IterCtl {
+    int32_t on;
+    double tolJ, tolPops;
+    int32_t *iter, *doneW;
+    const int32_t *status;
+    const double *dPops;
+};
+__device__ __forceinline__ void iterate_check(const IterCtl &c, int col, double dJ)
+{
+    if (c.iter[col] == 0) return;        // nothing to judge before the first iteration
+    const double a = dJ, b = c.dPops[col];
+    if (c.tolJ >= 0.0 && !(a > c.tolJ || b > c.tolPops)) c.doneW[col] = 1;  // the negation of `while dJ > 2e-3 or dPops > 1e-3`
+    // a singular system / a formal-solver domain fault (status) or a NaN: stop touching the column and flag it
+    // (the reference raises at this point; the host wrapper turns done == 2 into the same exceptions)
+    if (a != a || b != b || c.status[col] != 0) c.doneW[col] = 2;
+}
 __global__ void fs_prepare_kernel(unsigned long long *dJbits, const int32_t *done, int col0, double *colconst,
                                   int64_t colStride, int64_t off_z, int64_t off_popsT, int PW, int N, int sumNlevel,
-                                  const double *pops, int64_t popStride)
+                                  const double *pops, int64_t popStride, const IterCtl ctl)
 {
     const int col = col0 + blockIdx.x;
     if (done != nullptr && done[col] != 0) return;
+    if (ctl.on) {    // block-uniform outcome: every thread evaluates the same test on the same values
+        iterate_check(ctl, col, __longlong_as_double((long long)dJbits[col]));
+        __syncthreads();
+        if (ctl.doneW[col] != 0) return;
+    }
+    __syncthreads();
     if (threadIdx.x == 0) dJbits[col] = 0ull;
     double *cc = colconst + (size_t)col * colStride;
     const double *z = cc + off_z, *n = pops + (size_t)col * popStride;
@@ -83,24 +112,15 @@ __global__ void fs_prepare_kernel(unsigned long long *dJbits, const int32_t *don
     }
 }
 
-// Per-column loop control of mali_iterate (test.py:23-28): phase 0 = after the formal solution: ++iter;
-// phase 1 = after stat_equil: convergence test.
-__global__ void iterate_ctl_kernel(int phase, double *dJ, double *dPops, int32_t *iter, int32_t *done,
-                                   const int32_t *status, double tolJ, double tolPops, int col0, int ncol)
+// Closes the LAST iteration of a mali_iterate call (the earlier ones are closed by the next iteration's
+// fs_prepare_kernel): convergence test / fault stop per column.
+__global__ void iterate_close_kernel(const double *dJ, const IterCtl ctl, int col0, int ncol)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncol) return;
     const int col = col0 + c;
-    if (done[col] != 0) return;
-    if (phase == 0) {
-        iter[col] += 1;
-    } else {
-        const double a = dJ[col], b = dPops[col];
-        if (tolJ >= 0.0 && !(a > tolJ || b > tolPops)) done[col] = 1;  // the negation of `while dJ > 2e-3 or dPops > 1e-3`
-        // a singular system / a formal-solver domain fault (status) or a NaN: stop touching the column and flag it
-        // (the reference raises at this point; the host wrapper turns done == 2 into the same exceptions)
-        if (a != a || b != b || status[col] != 0) done[col] = 2;
-    }
+    if (ctl.doneW[col] != 0) return;
+    iterate_check(ctl, col, dJ[col]);
 }
 
 }  // namespace
@@ -120,8 +140,21 @@ static const SpecEntry *find_spec(const std::string &key)
 }
 
 // ---------------------------------------------------------------------------------------------------------
+struct IterGraphKey {
+    mali_buffers b;
+    int32_t col0, ncol;
+    double tolJ, tolPops;
+    int32_t arith;
+};
+struct IterGraph {
+    IterGraphKey key;
+    cudaGraphExec_t exec;
+    long long kernels;   // kernel nodes of one iteration
+};
+
 struct mali_model {
     int device = 0;
+    mutable std::vector<IterGraph> iterGraphs;   // captured iterations of mali_iterate
     int arith = MALI_ARITH_EXACT;   // arithmetic mode of the specialised formal-solution kernels (mali_model_set_arith)
     int N = 0, Nrays = 0, Nspect = 0, Natom = 0, Ntrans = 0, Lw = 0, ntile = 0, Dmax = 0, Tmax = 0;
     int sumNlevel = 0, sumNlevel2 = 0, maxNlevel = 0, nPartRows = 0;
@@ -153,6 +186,12 @@ struct mali_model {
     PhiLine *d_phiLines = nullptr;
     double *d_wavelength = nullptr, *d_muz = nullptr, *d_wmu = nullptr;
     int nPhiLines = 0;
+    AtomLevels atoms{};                 // model-level atom data of the device-side set-up (mali_model_set_atoms)
+    std::vector<void *> atomDev;
+    bool haveAtoms = false;
+    GijCont *d_gijCont = nullptr;
+    GijTile *d_gijTiles = nullptr;
+    int nGijCont = 0;
     std::vector<std::vector<PhiTile>> phiTilesHost;   // per transition: where its profile entries live (mali_line_layout)
     std::vector<int32_t> phiTile0Host;
     bool haveLambda0 = false;
@@ -275,8 +314,8 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
     L.hp_bg_chi = htake((int64_t)d->Nspect * N);
     L.hp_bg_eta = htake((int64_t)d->Nspect * N);
     L.hp_bg_sca = htake((int64_t)d->Nspect * N);
-    L.hp_C = htake((int64_t)m->sumNlevel2 * N);
     L.hp_nTotal = htake((int64_t)d->Natom * N);
+    L.hp_C = htake((int64_t)m->sumNlevel2 * N);   // from here on: blocks the device-side set-up can form itself
     std::vector<int64_t> hpPhi(d->Ntrans, 0), hpGij(d->Ntrans, 0);
     L.hp_gijcont = h;
     for (int t = 0; t < d->Ntrans; ++t)
@@ -313,6 +352,8 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
     std::vector<PackTile> ptiles;
     std::vector<TileJ> tileJ;        // per tile: J-dagger field of the depth-0 record, record stride
     std::vector<std::vector<PhiTile>> phiT(d->Ntrans);
+    std::vector<std::vector<GijTile>> gijT(d->Ntrans);
+    std::vector<int32_t> gijTile0(d->Ntrans, -1);
     std::vector<int32_t> phiTile0(d->Ntrans, -1);
     std::vector<PackSlot> pslots;
     std::vector<PackChunk> pchunks;
@@ -377,6 +418,10 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
             ps.wphiOff = L.hp_wphi + (int64_t)s.t * N;
             ps.c0 = s.c0;
             pslots.push_back(ps);
+            if (!s.isLine) {  // where setup_gij_kernel finds this continuum's g_ij field of this tile
+                gijT[s.t].push_back(GijTile{(int32_t)rowOff + s.fOff, pt.recSize});
+                if (gijTile0[s.t] < 0) gijTile0[s.t] = ti;
+            }
             if (s.isLine) {   // where compute_phi_kernel finds this line's entries of this tile
                 phiT[s.t].push_back(PhiTile{(int32_t)rowOff + s.vOff, vb + sf, (int32_t)rowOff + s.fOff, pt.recSize});
                 if (phiTile0[s.t] < 0) phiTile0[s.t] = ti;
@@ -523,19 +568,20 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
     }
 
     // ---- small copies of the upload path
-    auto add_copy = [&](int64_t src, int64_t dst, int64_t len, int toPops) {
+    auto add_copy = [&](int64_t src, int64_t dst, int64_t len, int toPops, int derived) {
         CopyJob c{};
         c.srcOff = src;
         c.dstOff = dst;
         c.len = len;
         c.toPops = toPops;
+        c.pad = derived;
         m->cjobs.push_back(c);
     };
-    add_copy(L.hp_height, m->off_z, N, 0);
-    add_copy(L.hp_bbc, m->off_bbc, 2 * (int64_t)d->Nspect, 0);
-    add_copy(L.hp_C, m->off_C, (int64_t)m->sumNlevel2 * N, 0);
-    add_copy(L.hp_nTotal, m->off_nTotal, (int64_t)d->Natom * N, 0);
-    add_copy(L.hp_n, 0, (int64_t)m->sumNlevel * N, 1);
+    add_copy(L.hp_height, m->off_z, N, 0, 0);
+    add_copy(L.hp_bbc, m->off_bbc, 2 * (int64_t)d->Nspect, 0, 0);
+    add_copy(L.hp_nTotal, m->off_nTotal, (int64_t)d->Natom * N, 0, 0);
+    add_copy(L.hp_C, m->off_C, (int64_t)m->sumNlevel2 * N, 0, 1);
+    add_copy(L.hp_n, 0, (int64_t)m->sumNlevel * N, 1, 1);
 
     // ---- device copies of the model tables
     std::vector<double> zmu(d->Nrays), hw(d->Nrays);
@@ -582,6 +628,26 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
             lines.push_back(ln);
             tv.insert(tv.end(), phiT[t].begin(), phiT[t].end());
         }
+        {   // tables of the device-side g_ij of the continua
+            std::vector<GijCont> conts;
+            std::vector<GijTile> gts;
+            for (int t = 0; t < d->Ntrans; ++t) {
+                const int32_t *tr = &m->trans[(size_t)t * 6];
+                if (tr[3]) continue;
+                GijCont gc{};
+                gc.rowI = m->lvlOff[tr[0]] + tr[1];
+                gc.rowJ = m->lvlOff[tr[0]] + tr[2];
+                gc.Nblue = tr[4];
+                gc.Nlam = tr[5];
+                gc.tile0 = gijTile0[t];
+                gc.tab0 = (int32_t)gts.size();
+                conts.push_back(gc);
+                gts.insert(gts.end(), gijT[t].begin(), gijT[t].end());
+            }
+            m->nGijCont = (int)conts.size();
+            up(to_device(conts, &m->d_gijCont));
+            up(to_device(gts, &m->d_gijTiles));
+        }
         m->nPhiLines = (int)lines.size();
         m->phiTilesHost = phiT;
         m->phiTile0Host = phiTile0;
@@ -625,9 +691,12 @@ void mali_model_destroy(mali_model *m)
     void *ptrs[] = {m->d_tiles, m->d_slots, m->d_alpha, m->d_twohc, m->d_wlacont, m->d_wlambda, m->d_zmu, m->d_hw,
                     m->d_Nlevel, m->d_lvlOff, m->d_g2Off, m->d_trans, m->d_trPartOff, m->d_trPartRows,
                     m->d_genericTiles, m->d_cjobs, m->d_pchunks, m->d_ptiles, m->d_pslots, m->d_tileJ, m->d_phiTiles,
-                    m->d_phiLines, m->d_wavelength, m->d_muz, m->d_wmu};
+                    m->d_phiLines, m->d_wavelength, m->d_muz, m->d_wmu, m->d_gijCont, m->d_gijTiles};
     for (void *p : ptrs)
         if (p) cudaFree(p);
+    for (void *p : m->atomDev)
+        if (p) cudaFree(p);
+    for (auto &g : m->iterGraphs) cudaGraphExecDestroy(g.exec);
     for (cudaEvent_t e : m->profEvents) cudaEventDestroy(e);
     for (int q = 0; q < 2; ++q) {
         if (m->sideStream[q]) cudaStreamDestroy(m->sideStream[q]);
@@ -674,9 +743,13 @@ static int check_range(const mali_model *m, const mali_buffers *b, int col0, int
     return MALI_OK;
 }
 
+// mode 0: whole host-pack blocks; 1: without the line profiles (mali_compute_phi forms them); 2: only the blocks'
+// first hp_C doubles -- heights, boundary Planck values, background, nTotal -- (mali_setup_columns forms C, the
+// continua's g_ij and the LTE populations as well)
 static int upload_columns(const mali_model *m, const mali_buffers *b, int32_t col0, int32_t ncol, const double *host_pack,
-                          double *staging_dev, void *stream, bool nophi)
+                          double *staging_dev, void *stream, int mode)
 {
+    const bool nophi = mode >= 1;
     if (int r = check_range(m, b, col0, ncol, "mali_upload_columns")) return r;
     if (!staging_dev || !b->colconst || !b->pops || !b->J) return fail(MALI_EINVAL, "mali_upload_columns: null buffer");
     cudaStream_t st = (cudaStream_t)stream;
@@ -684,20 +757,22 @@ static int upload_columns(const mali_model *m, const mali_buffers *b, int32_t co
     if (host_pack) {
         if (!nophi)
             CU(cudaMemcpyAsync(staging_dev, host_pack, (size_t)ncol * L.hostpack * sizeof(double), cudaMemcpyHostToDevice, st));
-        else   // only the blocks' prefix without the line profiles crosses the bus
-            CU(cudaMemcpy2DAsync(staging_dev, (size_t)L.hostpack * sizeof(double), host_pack, (size_t)L.hp_phi * sizeof(double),
-                                 (size_t)L.hp_phi * sizeof(double), (size_t)ncol, cudaMemcpyHostToDevice, st));
+        else {  // only the blocks' prefix without the line profiles (/ the derived blocks) crosses the bus
+            const size_t pre = (size_t)(mode == 2 ? L.hp_C : L.hp_phi) * sizeof(double);
+            CU(cudaMemcpy2DAsync(staging_dev, (size_t)L.hostpack * sizeof(double), host_pack, pre, pre, (size_t)ncol,
+                                 cudaMemcpyHostToDevice, st));
+        }
     }
     if (m->packChunks > 0) {
         dim3 grid(m->packChunks, (m->N + 31) / 32, ncol), block(32, 8);
         pack_tiles_kernel<<<grid, block, 0, st>>>(m->d_pchunks, m->d_ptiles, m->d_pslots, m->d_wlambda, m->N, m->Nrays,
                                                   m->Nspect, m->Lw, staging_dev, L.hostpack, L.hp_bg_chi, L.hp_bg_eta,
-                                                  L.hp_bg_sca, b->colconst, L.colconst, m->off_tab, col0, nophi ? 1 : 0);
+                                                  L.hp_bg_sca, b->colconst, L.colconst, m->off_tab, col0, mode);
     }
     {
         dim3 grid(32, ncol);
         pack_misc_kernel<<<grid, 256, 0, st>>>(m->d_cjobs, (int)m->cjobs.size(), staging_dev, L.hostpack, b->colconst,
-                                               L.colconst, b->pops, L.pops, b->J, L.J, col0);
+                                               L.colconst, b->pops, L.pops, b->J, L.J, col0, mode == 2 ? 1 : 0);
     }
     m->launches += 2;
     CU(cudaGetLastError());
@@ -707,13 +782,100 @@ static int upload_columns(const mali_model *m, const mali_buffers *b, int32_t co
 int mali_upload_columns(const mali_model *m, const mali_buffers *b, int32_t col0, int32_t ncol, const double *host_pack,
                         double *staging_dev, void *stream)
 {
-    return upload_columns(m, b, col0, ncol, host_pack, staging_dev, stream, false);
+    return upload_columns(m, b, col0, ncol, host_pack, staging_dev, stream, 0);
 }
 
 int mali_upload_columns_nophi(const mali_model *m, const mali_buffers *b, int32_t col0, int32_t ncol,
                               const double *host_pack_prefix, double *staging_dev, void *stream)
 {
-    return upload_columns(m, b, col0, ncol, host_pack_prefix, staging_dev, stream, true);
+    return upload_columns(m, b, col0, ncol, host_pack_prefix, staging_dev, stream, 1);
+}
+
+int mali_upload_columns_atmos(const mali_model *m, const mali_buffers *b, int32_t col0, int32_t ncol,
+                              const double *host_pack_prefix, double *staging_dev, void *stream)
+{
+    return upload_columns(m, b, col0, ncol, host_pack_prefix, staging_dev, stream, 2);
+}
+
+int mali_model_set_atoms(mali_model *m, const mali_atom_desc *a)
+{
+    if (!m || !a) return fail(MALI_EINVAL, "mali_model_set_atoms: null argument");
+    if (a->Natom != m->Natom) return fail(MALI_EINVAL, "mali_model_set_atoms: %d atoms, the model has %d", a->Natom, m->Natom);
+    for (int q = 0; q < m->Natom; ++q)
+        if (a->Nlevel[q] != m->Nlevel[q]) return fail(MALI_EINVAL, "mali_model_set_atoms: atom %d has %d levels, the model %d", q, a->Nlevel[q], m->Nlevel[q]);
+    CU(cudaSetDevice(m->device));
+    const int nl = m->sumNlevel;
+    int nk = 0, ncf = 0;
+    for (int c = 0; c < a->Ncoll; ++c) {
+        const int32_t *cd = a->coll + 8 * c;
+        const bool bad = cd[0] < 0 || cd[0] >= m->Natom || cd[1] < 0 || cd[1] > 2 || cd[2] < 0 || cd[3] < 0 ||
+                         cd[2] >= m->Nlevel[cd[0]] || cd[3] >= m->Nlevel[cd[0]] || cd[4] < 2 || cd[5] != nk || cd[6] != ncf ||
+                         (cd[7] && cd[4] < 4);
+        if (bad) return fail(MALI_EINVAL, "mali_model_set_atoms: collision %d: inconsistent descriptor", c);
+        nk += cd[7] ? cd[4] + 4 : cd[4];
+        ncf += cd[4];
+    }
+    for (void *p : m->atomDev)
+        if (p) cudaFree(p);
+    m->atomDev.clear();
+    cudaError_t e = cudaSuccess;
+    auto put = [&](const void *src, size_t bytes) -> void * {
+        void *d = nullptr;
+        if (e == cudaSuccess) e = cudaMalloc(&d, std::max<size_t>(bytes, 8));
+        if (e == cudaSuccess && bytes) e = cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice);
+        m->atomDev.push_back(d);
+        return d;
+    };
+    AtomLevels &A = m->atoms;
+    A = AtomLevels{};
+    A.Nlevel = m->d_Nlevel;
+    A.lvlOff = m->d_lvlOff;
+    A.g2Off = m->d_g2Off;
+    A.dE = (const double *)put(a->dE, nl * sizeof(double));
+    A.gi0 = (const double *)put(a->gi0, nl * sizeof(double));
+    A.nDebye = (const double *)put(a->nDebye, nl * sizeof(double));
+    A.g = (const double *)put(a->g, nl * sizeof(double));
+    A.dZ = (const int32_t *)put(a->dZ, nl * sizeof(int32_t));
+    A.vTherm = (const double *)put(a->vTherm, m->Natom * sizeof(double));
+    A.coll = (const int32_t *)put(a->coll, (size_t)a->Ncoll * 8 * sizeof(int32_t));
+    A.knots = (const double *)put(a->knots, nk * sizeof(double));
+    A.coef = (const double *)put(a->coef, (size_t)ncf * sizeof(double));
+    A.fill = (const double *)put(a->fill, (size_t)a->Ncoll * 2 * sizeof(double));
+    A.par = (const double *)put(a->par, (size_t)a->Ncoll * sizeof(double));
+    A.c1 = a->c1;
+    A.c2 = a->c2;
+    A.Ncoll = a->Ncoll;
+    A.Natom = m->Natom;
+    if (e != cudaSuccess) return fail((int)e, "mali_model_set_atoms: %s", cudaGetErrorString(e));
+    m->haveAtoms = true;
+    return MALI_OK;
+}
+
+int mali_setup_columns(const mali_model *m, const mali_buffers *b, int32_t col0, int32_t ncol, const double *T,
+                       const double *ne, const double *vturb, double *nStar, double *vBroad, int32_t start_from_lte,
+                       void *stream)
+{
+    if (int r = check_range(m, b, col0, ncol, "mali_setup_columns")) return r;
+    if (!T || !ne || !vturb || !nStar || !vBroad || !b->colconst || !b->pops) return fail(MALI_EINVAL, "mali_setup_columns: null buffer");
+    if (!m->haveAtoms) return fail(MALI_EINVAL, "mali_setup_columns: call mali_model_set_atoms first");
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid((m->N + 63) / 64, m->Natom, ncol);
+    double *pops = start_from_lte ? b->pops : nullptr;
+    if (m->maxNlevel <= 8)
+        setup_levels_kernel<8><<<grid, 64, 0, st>>>(m->atoms, m->N, T, ne, vturb, b->colconst, m->lay.colconst, m->off_C,
+                                                    m->off_nTotal, nStar, vBroad, pops, m->lay.pops, m->sumNlevel, col0);
+    else
+        setup_levels_kernel<16><<<grid, 64, 0, st>>>(m->atoms, m->N, T, ne, vturb, b->colconst, m->lay.colconst, m->off_C,
+                                                     m->off_nTotal, nStar, vBroad, pops, m->lay.pops, m->sumNlevel, col0);
+    m->launches += 1;
+    if (m->nGijCont > 0) {
+        dim3 g2(8, m->nGijCont, ncol);
+        setup_gij_kernel<<<g2, 256, 0, st>>>(m->d_gijCont, m->d_gijTiles, m->d_wavelength, m->N, m->Lw, m->sumNlevel, T, nStar,
+                                             b->colconst, m->lay.colconst, m->off_tab, col0);
+        m->launches += 1;
+    }
+    CU(cudaGetLastError());
+    return MALI_OK;
 }
 
 int mali_compute_phi(const mali_model *m, const mali_buffers *b, int32_t col0, int32_t ncol, const double *aDamp,
@@ -846,11 +1008,15 @@ static FinishParams make_finish_params(const mali_model *m, const mali_buffers *
     return p;
 }
 
-static int launch_fs(const mali_model *m, const mali_buffers *b, int col0, int ncol, cudaStream_t st)
+// ctl.on: called from mali_iterate -- the prepare kernel closes the previous iteration, and j_finish_kernel (which only
+// the NEXT formal solution and the convergence test depend on) runs on a side stream next to the statistical
+// equilibrium; *jJoin then tells the caller to join that stream (event joinEvent[0]) at the end of the iteration.
+static int launch_fs(const mali_model *m, const mali_buffers *b, int col0, int ncol, cudaStream_t st, const IterCtl &ctl,
+                     bool *jJoin)
 {
     fs_prepare_kernel<<<ncol, 128, 0, st>>>(reinterpret_cast<unsigned long long *>(b->dJ), b->done, col0, b->colconst,
                                             m->lay.colconst, m->off_z, m->off_popsT, m->popsW, m->N, m->sumNlevel, b->pops,
-                                            m->lay.pops);
+                                            m->lay.pops, ctl);
     m->launches += 1;
     const bool rec = m->profOn && m->profUsed + 2 <= (int)m->profEvents.size();
     if (rec) cudaEventRecord(m->profEvents[m->profUsed], st);
@@ -916,25 +1082,36 @@ static int launch_fs(const mali_model *m, const mali_buffers *b, int col0, int n
     }
     FinishParams f = make_finish_params(m, b, col0, ncol);
     dim3 grid((m->N + 31) / 32, m->Natom, ncol);
+    cudaStream_t sj = st;
+    if (jJoin) {
+        *jJoin = false;
+        if (ctl.on && m->sideStream[0]) {
+            sj = m->sideStream[0];
+            CU(cudaEventRecord(m->forkEvent, st));
+            CU(cudaStreamWaitEvent(sj, m->forkEvent, 0));
+            *jJoin = true;
+        }
+    }
     gamma_finish_kernel<<<grid, dim3(32, 8), 0, st>>>(f);
     {
         const int nb = std::min(m->N, 41);   // depth rows are dealt round-robin to the blocks of a column
-        j_finish_kernel<<<dim3(nb, ncol), 256, 0, st>>>(b->J, m->lay.J, b->scratch, m->lay.scratch, m->off_jpart, m->upOff, b->colconst, m->lay.colconst, m->off_tab, m->d_tileJ, m->Nspect, m->Lw,
+        j_finish_kernel<<<dim3(nb, ncol), 256, 0, sj>>>(b->J, m->lay.J, b->scratch, m->lay.scratch, m->off_jpart, m->upOff, b->colconst, m->lay.colconst, m->off_tab, m->d_tileJ, m->Nspect, m->Lw,
                                                       reinterpret_cast<unsigned long long *>(b->dJ), b->done, col0);
+        if (sj != st) CU(cudaEventRecord(m->joinEvent[0], sj));
     }
     m->launches += 2;
     CU(cudaGetLastError());
     return MALI_OK;
 }
 
-static int launch_se(const mali_model *m, const mali_buffers *b, int col0, int ncol, const int32_t *iter, int iterMin,
+static int launch_se(const mali_model *m, const mali_buffers *b, int col0, int ncol, int32_t *iter, int iterMin,
                      cudaStream_t st)
 {
     FinishParams f = make_finish_params(m, b, col0, ncol);
     // inside mali_iterate, columns whose own iteration counter is still <= 3 only iterate J (test.py:27)
     f.iter = iter;
     f.iterMin = iterMin;
-    col_zero_bits_kernel<<<(ncol + 127) / 128, 128, 0, st>>>(f.dPopsBits, b->done, iter, iterMin, col0, ncol);
+    se_prepare_kernel<<<(ncol + 127) / 128, 128, 0, st>>>(f.dPopsBits, b->done, iter, iterMin, iter != nullptr, col0, ncol);
     dim3 grid((m->N + 63) / 64, m->Natom, ncol);
     if (m->maxNlevel <= 8)
         stat_equil_kernel<8><<<grid, 64, 0, st>>>(f);
@@ -954,7 +1131,7 @@ int mali_formal_sol_gamma(const mali_model *m, const mali_buffers *b, int32_t co
     mali_buffers bb = *b;
     bb.done = nullptr;
     bb.iter = nullptr;
-    return launch_fs(m, &bb, col0, ncol, (cudaStream_t)stream);
+    return launch_fs(m, &bb, col0, ncol, (cudaStream_t)stream, IterCtl{}, nullptr);
 }
 
 int mali_stat_equil(const mali_model *m, const mali_buffers *b, int32_t col0, int32_t ncol, void *stream)
@@ -976,14 +1153,85 @@ int mali_iterate(const mali_model *m, const mali_buffers *b, int32_t col0, int32
         !b->iter || !b->done)
         return fail(MALI_EINVAL, "mali_iterate: null buffer");
     cudaStream_t st = (cudaStream_t)stream;
-    const int nb = (ncol + 127) / 128;
-    for (int it = 0; it < max_iter; ++it) {
-        if (int r = launch_fs(m, b, col0, ncol, st)) return r;
-        iterate_ctl_kernel<<<nb, 128, 0, st>>>(0, b->dJ, b->dPops, b->iter, b->done, b->status, tolJ, tolPops, col0, ncol);
+    if (max_iter < 1) return MALI_OK;
+    IterCtl ctl{};
+    ctl.on = 1;
+    ctl.tolJ = tolJ;
+    ctl.tolPops = tolPops;
+    ctl.iter = b->iter;
+    ctl.doneW = b->done;
+    ctl.status = b->status;
+    ctl.dPops = b->dPops;
+    // one iteration of test.py:20-29: formal solution + Gamma, then (J finish on a side stream) || (statistical equilibrium)
+    auto one_iteration = [&]() -> int {
+        bool jJoin = false;
+        if (int r = launch_fs(m, b, col0, ncol, st, ctl, &jJoin)) return r;
         if (int r = launch_se(m, b, col0, ncol, b->iter, 4, st)) return r;
-        iterate_ctl_kernel<<<nb, 128, 0, st>>>(1, b->dJ, b->dPops, b->iter, b->done, b->status, tolJ, tolPops, col0, ncol);
-        m->launches += 2;
+        if (jJoin) CU(cudaStreamWaitEvent(st, m->joinEvent[0], 0));
+        return MALI_OK;
+    };
+    // The iteration is captured ONCE into a CUDA graph and replayed: a column batch of a response function or a single
+    // column is bound by launch gaps, not by arithmetic (a CaII/FALC iteration is ~10 short kernels).  The graph is
+    // cached per (buffers, column range, tolerances, arithmetic mode).  Profiling and MALI_NO_GRAPH=1 use plain launches.
+    static const bool noGraph = getenv("MALI_NO_GRAPH") != nullptr;
+    bool done_by_graph = false;
+    if (!noGraph && !m->profOn && max_iter >= 2) {
+        IterGraphKey key;
+        memset(&key, 0, sizeof key);     // the key is compared bytewise: no indeterminate padding
+        key.b.ncol = b->ncol;
+        key.b.colconst = b->colconst;
+        key.b.pops = b->pops;
+        key.b.J = b->J;
+        key.b.I = b->I;
+        key.b.Gamma = b->Gamma;
+        key.b.scratch = b->scratch;
+        key.b.dJ = b->dJ;
+        key.b.dPops = b->dPops;
+        key.b.status = b->status;
+        key.b.iter = b->iter;
+        key.b.done = b->done;
+        key.col0 = col0;
+        key.ncol = ncol;
+        key.tolJ = tolJ;
+        key.tolPops = tolPops;
+        key.arith = m->arith;
+        cudaGraphExec_t exec = nullptr;
+        for (auto &g : m->iterGraphs)
+            if (memcmp(&g.key, &key, sizeof key) == 0) exec = g.exec;
+        if (!exec) {
+            const long long l0 = m->launches;
+            cudaGraph_t graph = nullptr;
+            if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                const int r = one_iteration();
+                const cudaError_t e = cudaStreamEndCapture(st, &graph);
+                if (r == MALI_OK && e == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+                    if (m->iterGraphs.size() >= 8) {     // small cache: drop the oldest
+                        cudaGraphExecDestroy(m->iterGraphs.front().exec);
+                        m->iterGraphs.erase(m->iterGraphs.begin());
+                    }
+                    m->iterGraphs.push_back(IterGraph{key, exec, m->launches - l0});
+                } else {
+                    exec = nullptr;
+                }
+                if (graph) cudaGraphDestroy(graph);
+            }
+            cudaGetLastError();      // a failed capture falls back to plain launches below
+            m->launches = l0;
+        }
+        if (exec) {
+            long long per = 0;
+            for (auto &g : m->iterGraphs)
+                if (g.exec == exec) per = g.kernels;
+            for (int it = 0; it < max_iter; ++it) CU(cudaGraphLaunch(exec, st));
+            m->launches += per * max_iter;
+            done_by_graph = true;
+        }
     }
+    if (!done_by_graph)
+        for (int it = 0; it < max_iter; ++it)
+            if (int r = one_iteration()) return r;
+    iterate_close_kernel<<<(ncol + 127) / 128, 128, 0, st>>>(b->dJ, ctl, col0, ncol);
+    m->launches += 1;
     CU(cudaGetLastError());
     return MALI_OK;
 }

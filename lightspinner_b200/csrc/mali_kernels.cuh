@@ -481,7 +481,7 @@ __global__ void pack_tiles_kernel(const PackChunk *chunks, const PackTile *tiles
                     if (la < Nspect && lt >= 0 && lt < ps.Nlam) {
                         if (ps.isLine) {  // wla = wlambda(lt) * wphi[k] / HC   (rh_method.py:451)
                             if (!skipPhi) v = wlambda[ps.toff + lt] * src[ps.wphiOff + k] / kHC;
-                        } else
+                        } else if (skipPhi < 2)     // (2: setup_gij_kernel forms the continua's g_ij on the device)
                             v = src[ps.srcOff + (size_t)lt * N + k];
                     }
                 }
@@ -559,14 +559,160 @@ __global__ void compute_phi_kernel(const PhiLine *lines, const PhiTile *ptile, c
     }
 }
 
+// --------------------------------------------------------------------------------------------------------
+// Per-column set-up on the device: LTE populations (lte_pops, atomic_set.py:105-145), collisional
+// rates (compute_collisions, rh_method.py:474-487 over collisional_rates.py:36-96), Doppler widths (v_broad,
+// atomic_model.py:241-245) and the continua's g_ij (rh_method.py:453-454) from T, ne, nTotal, vturb of each column.
+struct AtomLevels {     // model-level data, device arrays concatenated over the atoms' levels
+    const int32_t *Nlevel, *lvlOff, *g2Off;   // [Natom], [Natom+1], [Natom+1]
+    const double *dE, *gi0, *nDebye, *g;      // E_SI[l]-E_SI[0]; g[l]/g[0]; Debye shift count; g[l]
+    const int32_t *dZ;                        // stage[l]-stage[0]
+    const double *vTherm;                     // [Natom]
+    const int32_t *coll;                      // [Ncoll][8]: atom, kind, i, j, table points, knot offset, coefficient offset, cubic
+    const double *knots, *coef, *fill, *par;
+    double c1, c2;                            // atomic_set.py:107, :111 (evaluated on the host with the reference's expressions)
+    int32_t Ncoll, Natom;
+};
+
+// the table interpolant of collisional_rates.py:15-19 -- scipy interp1d: constant fill values outside the table; inside,
+// a cubic not-a-knot B-spline (make_interp_spline) evaluated with de Boor's recurrence exactly as scipy's
+// _bspl.evaluate_spline does (same operations, same order), or the linear form for a 2-point table
+__device__ __forceinline__ double coll_table(const AtomLevels &A, int c, double x)
+{
+    const int32_t *cd = A.coll + 8 * c;
+    const int n = cd[4];
+    const double *t = A.knots + cd[5], *cf = A.coef + cd[6];
+    if (!cd[7]) {     // linear: interp1d._call_linear
+        if (x < t[0]) return A.fill[2 * c];
+        if (x > t[n - 1]) return A.fill[2 * c + 1];
+        int hi = 1;
+        while (hi < n - 1 && t[hi] < x) ++hi;            // searchsorted(x, x_new) clipped to [1, n-1]
+        const double slope = (cf[hi] - cf[hi - 1]) / (t[hi] - t[hi - 1]);
+        return slope * (x - t[hi - 1]) + cf[hi - 1];
+    }
+    // knots t[0 .. n+3]; table range [t[3], t[n]]
+    if (x < t[3]) return A.fill[2 * c];
+    if (x > t[n]) return A.fill[2 * c + 1];
+    int ell = 3;
+    while (ell < n - 1 && x >= t[ell + 1]) ++ell;        // t[ell] <= x < t[ell+1]; the right end belongs to the last interval
+    double h[4], hh[4];
+    h[0] = 1.0;
+    for (int j = 1; j <= 3; ++j) {
+        for (int q = 0; q < j; ++q) hh[q] = h[q];
+        h[0] = 0.0;
+        for (int q = 1; q <= j; ++q) {
+            const double xb = t[ell + q], xa = t[ell + q - j];
+            if (xb == xa) {
+                h[q] = 0.0;
+                continue;
+            }
+            const double w = hh[q - 1] / (xb - xa);
+            h[q - 1] += w * (xb - x);
+            h[q] = w * (x - xa);
+        }
+    }
+    double out = 0.0;
+    for (int a = 0; a <= 3; ++a) out += cf[ell + a - 3] * h[a];
+    return out;
+}
+
+template <int NLMAX>
+__global__ void setup_levels_kernel(const AtomLevels A, int N, const double *T, const double *ne, const double *vturb,
+                                    double *colconst, int64_t colStride, int64_t off_C, int64_t off_nTotal, double *nStar,
+                                    double *vBroad, double *pops, int64_t popStride, int sumNlevel, int col0)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= N) return;
+    const int a = blockIdx.y, c = blockIdx.z;
+    const double t = T[(size_t)c * N + k], xne = ne[(size_t)c * N + k], vt = vturb[(size_t)c * N + k];
+    double *cc = colconst + (size_t)(col0 + c) * colStride;
+    const double nTot = cc[off_nTotal + (size_t)a * N + k];
+    const int NL = A.Nlevel[a], l0 = A.lvlOff[a];
+    // ---- lte_pops, atomic_set.py:105-145
+    const double dEion = A.c2 * sqrt(xne / t);
+    const double cNe_T = 0.5 * xne * pow(A.c1 / t, 1.5);
+    double ns[NLMAX];
+    double total = 1.0;
+    for (int i = 1; i < NL; ++i) {
+        const double dE_kT = (A.dE[l0 + i] - A.nDebye[l0 + i] * dEion) / (kKBoltzmann * t);
+        double v = A.gi0[l0 + i] * exp(-dE_kT);
+        const int dZ = A.dZ[l0 + i];
+        const double den = dZ == 0 ? 1.0 : (dZ == 1 ? cNe_T : (dZ == 2 ? cNe_T * cNe_T : pow(cNe_T, (double)dZ)));
+        v /= den;
+        ns[i] = v;
+        total += v;
+    }
+    ns[0] = nTot / total;
+    for (int i = 1; i < NL; ++i) ns[i] *= ns[0];
+    for (int i = 0; i < NL; ++i) {
+        nStar[((size_t)c * sumNlevel + l0 + i) * N + k] = ns[i];
+        if (pops) pops[(size_t)(col0 + c) * popStride + (size_t)(l0 + i) * N + k] = ns[i];   // start from LTE (rh_method.py:415)
+    }
+    // ---- compute_collisions, rh_method.py:474-487: C[i][j] = rate from j to i, terms added in the model's order
+    double Cm[NLMAX * NLMAX];
+    for (int e = 0; e < NL * NL; ++e) Cm[e] = 0.0;
+    const double sqT = sqrt(t);
+    for (int q = 0; q < A.Ncoll; ++q) {
+        const int32_t *cd = A.coll + 8 * q;
+        if (cd[0] != a) continue;
+        const int kind = cd[1], i = cd[2], j = cd[3];
+        const double Cv = coll_table(A, q, t);
+        if (kind == 0) {          // Omega, collisional_rates.py:43-46
+            const double Cdown = A.par[q] * xne * Cv / (A.g[l0 + j] * sqT);
+            Cm[i * NL + j] += Cdown;
+            Cm[j * NL + i] += Cdown * ns[j] / ns[i];
+        } else if (kind == 1) {   // CI, :70-72
+            const double Cup = Cv * xne * exp(-A.par[q] / (kKBoltzmann * t)) * sqT;
+            Cm[j * NL + i] += Cup;
+            Cm[i * NL + j] += Cup * ns[i] / ns[j];
+        } else {                  // CE, :94-96
+            const double Cdown = Cv * xne * A.par[q] * sqT;
+            Cm[i * NL + j] += Cdown;
+            Cm[j * NL + i] += Cdown * ns[j] / ns[i];
+        }
+    }
+    double *Cdst = cc + off_C + (size_t)A.g2Off[a] * N + k;
+    for (int e = 0; e < NL * NL; ++e) Cdst[(size_t)e * N] = Cm[e] < 0.0 ? 0.0 : Cm[e];
+    // ---- v_broad, atomic_model.py:241-245
+    vBroad[((size_t)c * A.Natom + a) * N + k] = sqrt(A.vTherm[a] * t + vt * vt);
+}
+
+// g_ij of the continua (rh_method.py:453-454): nStar_i / nStar_j * exp(-(hc/k) / lambda / T), written into the slot
+// fields of the tile records.  One block row per (continuum, column); threads run over (wavelength, depth).
+struct GijCont {
+    int32_t rowI, rowJ, Nblue, Nlam, tile0, tab0;   // level rows in nStar; wavelength range; first tile; first GijTile
+};
+struct GijTile {
+    int32_t f, stride;    // depth-0 offset of the continuum's field in that tile's records; record stride
+};
+__global__ void setup_gij_kernel(const GijCont *conts, const GijTile *gt, const double *wavelength, int N, int Lw,
+                                 int sumNlevel, const double *T, const double *nStar, double *colconst, int64_t colStride,
+                                 int64_t offTab, int col0)
+{
+    const GijCont ct = conts[blockIdx.y];
+    const int c = blockIdx.z;
+    const double hc_k = kHC / (kKBoltzmann * kNmToM);
+    double *tab = colconst + (size_t)(col0 + c) * colStride + offTab;
+    const double *ns = nStar + (size_t)c * sumNlevel * N;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < ct.Nlam * N; idx += gridDim.x * blockDim.x) {
+        const int lt = idx / N, k = idx - lt * N;
+        const int la = ct.Nblue + lt;
+        const int ti = la / Lw, ls = la - ti * Lw;
+        const GijTile g = gt[ct.tab0 + ti - ct.tile0];
+        const double v = ns[(size_t)ct.rowI * N + k] / ns[(size_t)ct.rowJ * N + k] *
+                         exp(-hc_k / wavelength[la] / T[(size_t)c * N + k]);
+        tab[g.f + (size_t)k * g.stride + ls] = v;
+    }
+}
+
 struct CopyJob {
     int64_t srcOff, dstOff, len;
     int32_t toPops;  // destination is the pops buffer instead of colconst
-    int32_t pad;
+    int32_t pad;     // non-zero: a block the device-side set-up produces itself (C, n)
 };
 __global__ void pack_misc_kernel(const CopyJob *copies, int ncopies, const double *staging, int64_t hpStride,
                                  double *colconst, int64_t colStride, double *pops, int64_t popStride, double *J,
-                                 int64_t JStride, int col0)
+                                 int64_t JStride, int col0, int skipDerived)
 {
     const int col = col0 + blockIdx.y;
     const double *src = staging + (size_t)blockIdx.y * hpStride;
@@ -574,6 +720,7 @@ __global__ void pack_misc_kernel(const CopyJob *copies, int ncopies, const doubl
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     for (int c = 0; c < ncopies; ++c) {
         const CopyJob cj = copies[c];
+        if (skipDerived && cj.pad) continue;      // C and the starting populations come from setup_levels_kernel
         double *dst = cj.toPops ? pops + (size_t)col * popStride + cj.dstOff : cc + cj.dstOff;
         for (int64_t q = tid; q < cj.len; q += nth) dst[q] = src[cj.srcOff + q];
     }

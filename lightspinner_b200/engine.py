@@ -48,7 +48,7 @@ class MaliEngine:
         f64 = dict(dtype=torch.float64, device=self.device)
         i32 = dict(dtype=torch.int32, device=self.device)
         n = self.ncol
-        self.t_colconst = torch.empty(n * L.colconst, **f64)
+        self.t_colconst = torch.zeros(n * L.colconst, **f64)
         self.t_pops = torch.zeros(n * L.pops, **f64)
         self.t_J = torch.zeros(n * L.J, **f64)
         self.t_I = torch.zeros(n * L.I, **f64)
@@ -143,6 +143,51 @@ class MaliEngine:
                 self._check(self.lib.mali_compute_phi(self._handle, C.byref(self.bufs), col0 + c0, len(chunk),
                                                       *(C.c_void_p(t.data_ptr()) for t in dev), self._stream()))
             torch.cuda.current_stream(self.device).synchronize()
+
+    def set_atoms(self, atom_tables):
+        """Registers the model-level atom data (lightspinner_b200.atoms.AtomTables) the device-side column set-up needs."""
+        self._atom_tables = atom_tables
+        desc = atom_tables.desc()
+        self._check(self.lib.mali_model_set_atoms(self._handle, C.byref(desc)))
+
+    def upload_atmos(self, problems, col0=0, start_from_lte=True):
+        """Like upload_device_phi(), with everything the device can form from the atmosphere formed there: each
+        problem supplies height, temperature, ne, vturb, vlos, nTotal, the background (bg_chi / bg_eta / bg_sca) and the
+        lines' damping parameters aDamp; LTE populations, collisional rates, Doppler widths, the continua's g_ij
+        (mali_setup_columns) and the Voigt profiles (mali_compute_phi) are computed on the GPU.  start_from_lte=False
+        keeps the populations given in problem['n'] (a warm start, response_fn.py:33).  Needs set_atoms()."""
+        staging, pinned = self._staging_bufs()
+        hpc = int(self.lay.hp_C)
+        pin_np = pinned.numpy()
+        N = self.mt.Nspace
+        self.nStar = getattr(self, 'nStar', None)
+        if self.nStar is None:
+            self.nStar = torch.zeros(self.ncol * self.lay.sumNlevel * N, dtype=torch.float64, device=self.device)
+        for c0 in range(0, len(problems), self.chunk):
+            chunk = problems[c0:c0 + self.chunk]
+            nc = len(chunk)
+            torch.cuda.current_stream(self.device).synchronize()  # pinned buffer reuse
+            for q, p in enumerate(chunk):
+                pack_column(self.mt, self.lay, p, out=pin_np[q * hpc:(q + 1) * hpc], with_derived=False)
+            aux = {k: torch.from_numpy(np.ascontiguousarray(np.stack(
+                [np.asarray(p[k], dtype=np.float64).reshape(-1, N) for p in chunk]))).to(self.device)
+                for k in ('temperature', 'ne', 'vturb', 'vlos', 'aDamp')}
+            vBroad = torch.empty((nc, self.mt.Natom, N), dtype=torch.float64, device=self.device)
+            ns = self.nStar[(col0 + c0) * self.lay.sumNlevel * N:(col0 + c0 + nc) * self.lay.sumNlevel * N]
+            P = lambda t: C.c_void_p(t.data_ptr())
+            with torch.cuda.device(self.device):
+                self._check(self.lib.mali_upload_columns_atmos(self._handle, C.byref(self.bufs), col0 + c0, nc,
+                                                               P(pinned), P(staging), self._stream()))
+                self._check(self.lib.mali_setup_columns(self._handle, C.byref(self.bufs), col0 + c0, nc,
+                                                        P(aux['temperature']), P(aux['ne']), P(aux['vturb']), P(ns),
+                                                        P(vBroad), 1 if start_from_lte else 0, self._stream()))
+                self._check(self.lib.mali_compute_phi(self._handle, C.byref(self.bufs), col0 + c0, nc, P(aux['aDamp']),
+                                                      P(vBroad), P(aux['vlos']), self._stream()))
+            if not start_from_lte:
+                for q, p in enumerate(chunk):
+                    self.set_n(col0 + c0 + q, p['n'])
+            torch.cuda.current_stream(self.device).synchronize()
+            self._last_vBroad = vBroad
 
     def upload_packed_device_phi(self, host_prefix_pinned, aDamp, vBroad, vlos, col0, ncol, staging=None):
         """Asynchronous form of upload_device_phi: `host_prefix_pinned` holds [ncol][lay.hp_phi] doubles (pinned),

@@ -151,15 +151,19 @@ def planck_bc(wavelength, temperature):
     return out
 
 
-def pack_column(mt, lay, p, out=None, with_phi=True):
+def pack_column(mt, lay, p, out=None, with_phi=True, with_derived=True):
     """Concatenate one column's reference-layout arrays into the host staging block (`mali_layout.hp_*`).
 
     No transposition happens on the host: mali_upload_columns re-lays the data out on the device.
     with_phi=False: only the first `lay.hp_phi` doubles (everything but the line profiles phi / wphi, which
     mali_compute_phi then forms on the device).
+    with_derived=False: only the first `lay.hp_C` doubles -- heights, boundary Planck values, background, nTotal --
+    (mali_setup_columns forms C, the continua's g_ij and the LTE populations on the device as well).
     """
     N, Nspect = mt.Nspace, mt.Nspect
-    size = lay.hostpack if with_phi else lay.hp_phi
+    if not with_derived:
+        with_phi = False
+    size = lay.hostpack if with_phi else (lay.hp_phi if with_derived else lay.hp_C)
     if out is None:
         out = np.empty(size)
     if out.shape[0] != size:
@@ -176,8 +180,10 @@ def pack_column(mt, lay, p, out=None, with_phi=True):
     put(lay.hp_bg_chi, p['bg_chi'], Nspect * N)
     put(lay.hp_bg_eta, p['bg_eta'], Nspect * N)
     put(lay.hp_bg_sca, p['bg_sca'], Nspect * N)
-    put(lay.hp_C, p['C'], lay.sumNlevel2 * N)
     put(lay.hp_nTotal, p['nTotal'], mt.Natom * N)
+    if not with_derived:
+        return out
+    put(lay.hp_C, p['C'], lay.sumNlevel2 * N)
     if with_phi:
         phi = _f64(p['phi'])
         o = lay.hp_phi

@@ -21,6 +21,8 @@ Fixtures
                     profiles are stored once per (wavelength, depth) (`p_phi_compact`; helpers.load_golden expands them)
   c1v_jitter_ca3    CaII active, 3 rays, config-4 jitter recipe column 0 (T, ne, non-zero vlos): phi differs up/down
   rf_k40p, rf_k10m  response_fn.py columns: T[k] +/- 25 K, warm-started from the converged c1 populations
+  setup_inputs      model-level atom data (levels, collisional-rate tables) and per-fixture ne / nHTot: inputs of the
+                    device-side lte_pops / compute_collisions (their outputs nStar, C are in the column fixtures)
   units             formal-solver / w2 / planck / uv known answers
 """
 import os
@@ -172,6 +174,55 @@ def make_rf(ref, start_n, k, pert, name):
     save(name, p, r)
 
 
+def make_setup_inputs(ref):
+    """Inputs of the per-column set-up that precedes the hot path (lte_pops atomic_set.py:105-145,
+    compute_collisions rh_method.py:474-487 / collisional_rates.py): the model-level data of the CaII and H6 atoms
+    (levels, collisional-rate tables, abundances) and, for every column fixture, the electron and total hydrogen
+    densities its atmosphere had (the fixtures already hold T, vturb and the reference's nStar, C, vBroad)."""
+    from oracle.refharness import falc_interpolated_constructor
+    out = {}
+    models = {'CA': ref['rh_atoms'].CaII_atom(), 'H': ref['rh_atoms'].H_6_atom()}
+    at = ref['atomic_set'].RadiativeSet(list(models.values())).atomicTable
+    for nm, m in models.items():
+        out['atom_%s_E_SI' % nm] = np.array([l.E_SI for l in m.levels])
+        out['atom_%s_g' % nm] = np.array([l.g for l in m.levels])
+        out['atom_%s_stage' % nm] = np.array([l.stage for l in m.levels], dtype=np.int32)
+        out['atom_%s_abundance' % nm] = np.array(at[m.name].abundance)
+        out['atom_%s_weight' % nm] = np.array(at[m.name].weight)
+        kinds = {'Omega': 0, 'CI': 1, 'CE': 2}
+        meta, T, R = [], [], []
+        for c in m.collisions:
+            meta.append([kinds[type(c).__name__], c.i, c.j, len(c.temperature)])
+            T.append(np.asarray(c.temperature, dtype=np.float64))
+            R.append(np.asarray(c.rates, dtype=np.float64))
+        out['atom_%s_coll' % nm] = np.array(meta, dtype=np.int32)
+        out['atom_%s_coll_T' % nm] = np.concatenate(T)
+        out['atom_%s_coll_rates' % nm] = np.concatenate(R)
+
+    def put(name, atmos):
+        atmos.nondimensionalise()
+        out[name + '_ne'] = np.array(atmos.ne)
+        out[name + '_nHTot'] = np.array(atmos.nHTot)
+        out[name + '_temperature'] = np.array(atmos.temperature)
+
+    u = sys.modules['astropy.units']
+    put('c1_falc_ca', build_falc_setup(active=('Ca',), nrays=5)[0])
+    put('c2_falc_cah', build_falc_setup(active=('Ca', 'H'), nrays=5)[0])
+    put('c1v_jitter_ca3', build_falc_setup(active=('Ca',), nrays=3, modify_constructor=jitter_modifier(0, ref))[0])
+    for col in (0, 1):
+        put('c2v_jitter_cah_%d' % col,
+            build_falc_setup(active=('Ca', 'H'), nrays=5, modify_constructor=jitter_modifier(col, ref))[0])
+    for k, pert, name in ((40, +25.0, 'rf_k40p'), (10, -25.0, 'rf_k10m')):
+        def mod(ac, k=k, pert=pert):
+            ac.temperature[k] += pert << u.K
+            return ac
+        put(name, build_falc_setup(active=('Ca',), nrays=5, modify_constructor=mod)[0])
+    put('stress_r10_d512', build_falc_setup(active=('Ca',), nrays=10,
+                                            constructor=lambda: falc_interpolated_constructor(512))[0])
+    np.savez_compressed(os.path.join(HERE, 'setup_inputs.npz'), **out)
+    print('setup_inputs       %8.2f MB' % (os.path.getsize(os.path.join(HERE, 'setup_inputs.npz')) / 1e6))
+
+
 def make_units(ref):
     fs = ref['formal_solver']
     rng = np.random.default_rng(12345)
@@ -233,4 +284,6 @@ if __name__ == '__main__':
         make_c2v(ref, 1, False)
     if not which or 'stress' in which:
         make_stress(ref)
+    if not which or 'setup' in which:
+        make_setup_inputs(ref)
     print('done in %.0f s' % (time.time() - t0))

@@ -57,6 +57,20 @@ def recompute_phi(p):
     return (np.concatenate(phis) if phis else np.zeros(0)), wphi
 
 
+def load_setup_inputs(name):
+    """(atoms, column): model-level data of the CaII / H6 atoms {'CA': {...}, 'H': {...}} and the ne, nHTot, temperature
+    of fixture `name`'s atmosphere (tests/golden/setup_inputs.npz)."""
+    z = np.load(os.path.join(GOLDEN, 'setup_inputs.npz'))
+    atoms = {}
+    for nm in ('CA', 'H'):
+        pre = 'atom_%s_' % nm
+        atoms[nm] = {k[len(pre):]: z[k] for k in z.files if k.startswith(pre)}
+        atoms[nm]['abundance'] = float(atoms[nm]['abundance'])
+        atoms[nm]['weight'] = float(atoms[nm]['weight'])
+    col = {k: z['%s_%s' % (name, k)] for k in ('ne', 'nHTot', 'temperature')}
+    return atoms, col
+
+
 def load_units():
     return np.load(os.path.join(GOLDEN, 'units.npz'))
 
