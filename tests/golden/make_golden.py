@@ -23,6 +23,8 @@ Fixtures
   rf_k40p, rf_k10m  response_fn.py columns: T[k] +/- 25 K, warm-started from the converged c1 populations
   setup_inputs      model-level atom data (levels, collisional-rate tables) and per-fixture ne / nHTot: inputs of the
                     device-side lte_pops / compute_collisions (their outputs nStar, C are in the column fixtures)
+  eos               Wittmann EOS / background opacity / scale conversion known answers (FALC, a jitter column, a
+                    response-function column) with the state of the witt() instance that produced them
   units             formal-solver / w2 / planck / uv known answers
 """
 import os
@@ -223,6 +225,81 @@ def make_setup_inputs(ref):
     print('setup_inputs       %8.2f MB' % (os.path.getsize(os.path.join(HERE, 'setup_inputs.npz')) / 1e6))
 
 
+def make_eos(ref):
+    """Known answers of the column set-up in front of everything else: the Wittmann EOS
+    (witt.py:226-310, 342-432, 541-742), the background opacity (witt.py:744-1365 `cop`, background.py:21-53) and the
+    column-mass -> height conversion (atmosphere.py:70-112), produced by ONE instrumented witt() instance whose state
+    (abundances as normalised at that moment -- witt.__init__ renormalises the class-level table in place on every
+    instantiation --, partition-function tables) is stored with its outputs."""
+    import witt as W
+    Const = ref['constants']
+    at = ref['atomic_table'].get_global_atomic_table()
+    eos = W.witt()
+    out = {'ABUND': np.array(eos.ABUND), 'AMASS': np.array(eos.AMASS), 'avw': np.array(eos.avw), 'muH': np.array(eos.muH),
+           'rho_from_H': np.array(eos.rho_from_H), 'ab_others': np.array(eos.ab_others), 'tpf': np.array(eos.tpf),
+           'weightPerH': np.array(at.weightPerH)}
+    nel = 28
+    pf, eion, off = [], [], [0]
+    for ii in range(nel):
+        pf.append(np.array(eos.el[ii].pf))
+        eion.append(np.array(eos.el[ii].eion))
+        off.append(off[-1] + eos.el[ii].nstage)
+    out['pf'] = np.concatenate(pf, axis=0)          # [sum nstage, npf]
+    out['eion'] = np.concatenate(eion)
+    out['stage_off'] = np.array(off, dtype=np.int32)
+    u = sys.modules['astropy.units']
+    cases = {'falc': None, 'jitter0': jitter_modifier(0, ref)}
+
+    def rf(ac):
+        ac.temperature[40] += 25.0 << u.K
+        return ac
+    cases['rf_k40p'] = rf
+    wav = np.load(os.path.join(HERE, 'c2_falc_cah.npz'))['p_wavelength']
+    out['wavelength'] = wav
+    for name, mod in cases.items():
+        ac = ref['fal'].Falc82()
+        if mod is not None:
+            ac = mod(ac) or ac
+        ac.nondimensionalise()
+        T, nHTot, ne, cmass = (np.array(x) for x in (ac.temperature, ac.nHTot, ac.ne, ac.depthScale))
+        rho = Const.Amu * at.weightPerH * nHTot * Const.CM_TO_M**3 / Const.G_TO_KG        # background.py:33
+        rhoSI = Const.Amu * at.weightPerH * nHTot                                             # atmosphere.py:82
+        N = T.shape[0]
+        pgas, pe = np.zeros(N), np.zeros(N)
+        for k in range(N):
+            pgas[k] = eos.pg_from_rho(T[k], rho[k])
+            pe[k] = eos.pe_from_rho(T[k], rho[k])
+        chi = np.zeros((wav.shape[0], N))
+        chi_c = np.zeros(N)
+        parts = np.zeros((N, 17))
+        for k in range(N):
+            chi[:, k] = eos.contOpacity(T[k], pgas[k], pe[k], wav * 10) / Const.CM_TO_M
+            chi_c[k] = eos.contOpacity(T[k], pgas[k], pe[k], np.array([5000.0]))[0] / Const.CM_TO_M
+            parts[k] = eos.getBackgroundPartials(T[k], pgas[k], pe[k], divide_by_u=True)
+        eta = np.zeros_like(chi)
+        for k in range(N):
+            eta[:, k] = ref['utils'].planck(T[k], wav) * chi[:, k]
+        height = np.zeros(N)
+        tau_ref = np.zeros(N)
+        tau_ref[0] = chi_c[0] / rhoSI[0] * cmass[0]                                          # atmosphere.py:98-106
+        for k in range(1, N):
+            height[k] = height[k - 1] - 2.0 * (cmass[k] - cmass[k - 1]) / (rhoSI[k - 1] + rhoSI[k])
+            tau_ref[k] = tau_ref[k - 1] + 0.5 * (chi_c[k - 1] + chi_c[k]) * (height[k - 1] - height[k])
+        hTau1 = np.interp(1.0, tau_ref, height)
+        height -= hTau1
+        class A:
+            pass
+        a = A()
+        a.ne = ne
+        sca1 = ref['background'].thomson_scattering(a)
+        for k, v in (('T', T), ('nHTot', nHTot), ('ne', ne), ('cmass', cmass), ('rho', rho), ('pgas', pgas), ('pe', pe),
+                     ('chi', chi), ('eta', eta), ('thomson', sca1), ('chi_c', chi_c), ('partials', parts),
+                     ('height', height), ('tau_ref', tau_ref)):
+            out['%s_%s' % (name, k)] = v
+    np.savez_compressed(os.path.join(HERE, 'eos.npz'), **out)
+    print('eos                %8.2f MB' % (os.path.getsize(os.path.join(HERE, 'eos.npz')) / 1e6))
+
+
 def make_units(ref):
     fs = ref['formal_solver']
     rng = np.random.default_rng(12345)
@@ -286,4 +363,6 @@ if __name__ == '__main__':
         make_stress(ref)
     if not which or 'setup' in which:
         make_setup_inputs(ref)
+    if not which or 'eos' in which:
+        make_eos(ref)
     print('done in %.0f s' % (time.time() - t0))
