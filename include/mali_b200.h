@@ -18,6 +18,8 @@
  *   test.py:20-29 / response_fn.py:11-21 (the MALI loop)    mali_iterate (device-resident loop, per-column convergence)
  *   lte_pops atomic_set.py:105-145, compute_collisions rh_method.py:474-487, v_broad atomic_model.py:241-245,
  *   continuum g_ij rh_method.py:453-454                     mali_model_set_atoms + mali_setup_columns (device-side set-up)
+ *   Background.compute_background_eos background.py:21-53 (witt.py EOS + cop), AtmosphereConstructor.convert_scales
+ *   atmosphere.py:70-112 (column mass)                      mali_model_set_eos + mali_background
  *   ComputationalTransition.compute_phi rh_method.py:198-243 mali_compute_phi (device Voigt profiles); mali_line_layout = read-back
  *
  * Conventions
@@ -85,7 +87,7 @@ typedef struct {
     int64_t hp_bbc;      /* [Nspect][2]  planck(T[-2:], wav)  (formal_solver.py:206) */
     int64_t hp_bg_chi, hp_bg_eta, hp_bg_sca; /* [Nspect][Nspace] */
     int64_t hp_C;        /* concat atoms [Nlevel][Nlevel][Nspace] */
-    int64_t hp_nTotal;   /* [Natom][Nspace] (stored BEFORE hp_C: a caller using mali_setup_columns uploads only [0, hp_C)) */
+    int64_t hp_nTotal;   /* [Natom][Nspace] (stored before hp_bg_chi: see mali_upload_columns_atmos / _thermo) */
     int64_t hp_gijcont;  /* concat [offset+lt][Nspace], continua rows only (rh_method.py:453-454) */
     int64_t hp_n;        /* [sumNlevel][Nspace] starting populations */
     /* the line profiles come last, so that a caller who lets the device compute them (mali_compute_phi) uploads
@@ -160,6 +162,40 @@ int mali_upload_columns_nophi(const mali_model *m, const mali_buffers *bufs, int
  * mali_setup_columns and mali_compute_phi before the first formal solution. */
 int mali_upload_columns_atmos(const mali_model *m, const mali_buffers *bufs, int32_t col0, int32_t ncol,
                               const double *host_pack_prefix, double *staging_dev, void *stream);
+
+/* And for callers that hand over the thermodynamic state only: host_pack_prefix holds [ncol][layout.hp_bg_chi] doubles
+ * (heights -- overwritten by mali_background when it is given a column-mass scale --, boundary Planck values, nTotal);
+ * call mali_background, mali_setup_columns and mali_compute_phi before the first formal solution. */
+int mali_upload_columns_thermo(const mali_model *m, const mali_buffers *bufs, int32_t col0, int32_t ncol,
+                               const double *host_pack_prefix, double *staging_dev, void *stream);
+
+/* State of the reference's EOS object (witt.witt(), witt.py:152-195) and the constants around it, for the device-side
+ * Background.compute_background_eos (background.py:21-53) and AtmosphereConstructor.convert_scales (atmosphere.py:70-112,
+ * column-mass branch). */
+typedef struct {
+    int32_t npf;               /* temperatures of the partition-function tables */
+    const double *tpf;         /* [npf] */
+    const double *pf;          /* [stage_off[28]][npf]: first 28 elements, every ionisation stage */
+    const double *eion;        /* [stage_off[28]] ionisation energies in eV */
+    const int32_t *stage_off;  /* [29] running sum of the elements' stage counts */
+    const double *abund;       /* [99] abundances as the instance holds them (normalised) */
+    double avw, rho_from_H, ab_others;   /* witt.py:172-181 */
+    double saha_fac;           /* witt.py:52 */
+    double prec;               /* witt.py:155 */
+    double amu_weight_per_H;   /* Const.Amu * atomicTable.weightPerH   (background.py:33) */
+    double cm_to_m_cubed;      /* Const.CM_TO_M**3 as Python evaluates it */
+    double thomson_sigma;      /* background.py:11 */
+} mali_eos_desc;
+int mali_model_set_eos(mali_model *m, const mali_eos_desc *eos);
+
+/* Background.compute_background_eos for columns [col0, col0+ncol): gas / electron pressure from (T, nHTot) through the
+ * Wittmann EOS, background opacity chi, emissivity eta = B_nu(T) chi and Thomson scattering on the model's wavelength
+ * grid, written into the bg fields of the tile records.  T, ne, nHTot: [ncol][Nspace] device, SI units as
+ * Atmosphere holds them after nondimensionalise().  cmass != NULL ([ncol][Nspace], kg m^-2): also the heights of
+ * convert_scales' column-mass branch (tau_500 = 1 at height 0) into colconst.  work: device scratch of
+ * ncol * Nspace * 21 doubles. */
+int mali_background(const mali_model *m, const mali_buffers *bufs, int32_t col0, int32_t ncol, const double *T_dev,
+                    const double *ne_dev, const double *nHTot_dev, const double *cmass_dev, double *work_dev, void *stream);
 
 /* Model-level data of the active atoms for the device-side column set-up (mali_setup_columns): what lte_pops
  * (atomic_set.py:105-145), the collisional-rate terms (collisional_rates.py:36-96) and v_broad (atomic_model.py:241-245)

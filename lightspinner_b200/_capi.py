@@ -31,6 +31,13 @@ class AtomDesc(C.Structure):
                 ('knots', _dp), ('coef', _dp), ('fill', _dp), ('par', _dp)]
 
 
+class EosDesc(C.Structure):
+    _fields_ = [('npf', C.c_int32), ('tpf', _dp), ('pf', _dp), ('eion', _dp), ('stage_off', _ip), ('abund', _dp),
+                ('avw', C.c_double), ('rho_from_H', C.c_double), ('ab_others', C.c_double), ('saha_fac', C.c_double),
+                ('prec', C.c_double), ('amu_weight_per_H', C.c_double), ('cm_to_m_cubed', C.c_double),
+                ('thomson_sigma', C.c_double)]
+
+
 class Layout(C.Structure):
     _fields_ = [(n, C.c_int64) for n in (
         'hostpack', 'colconst', 'pops', 'J', 'I', 'Gamma', 'scratch', 'hp_height', 'hp_bbc', 'hp_bg_chi',
@@ -48,7 +55,8 @@ EXPORTS = ['mali_last_error', 'mali_device_count', 'mali_model_create', 'mali_mo
            'mali_planck_bc', 'mali_upload_columns', 'mali_upload_columns_nophi', 'mali_compute_phi', 'mali_formal_sol_gamma', 'mali_stat_equil', 'mali_iterate',
            'mali_piecewise_linear_1d', 'mali_uv', 'mali_exp_hook', 'mali_div_hook', 'mali_profile_begin',
            'mali_profile_end', 'mali_launch_count', 'mali_fp64_peak', 'mali_line_layout', 'mali_model_set_arith', 'mali_model_get_arith',
-           'mali_upload_columns_atmos', 'mali_model_set_atoms', 'mali_setup_columns']
+           'mali_upload_columns_atmos', 'mali_model_set_atoms', 'mali_setup_columns',
+           'mali_upload_columns_thermo', 'mali_model_set_eos', 'mali_background']
 
 ARITH_EXACT, ARITH_CONTRACTED = 0, 1
 
@@ -78,6 +86,9 @@ def load(path=None):
     L.mali_upload_columns_nophi.argtypes = L.mali_upload_columns.argtypes
     L.mali_upload_columns_atmos.argtypes = L.mali_upload_columns.argtypes
     L.mali_model_set_atoms.argtypes = [C.c_void_p, C.POINTER(AtomDesc)]
+    L.mali_upload_columns_thermo.argtypes = L.mali_upload_columns.argtypes
+    L.mali_model_set_eos.argtypes = [C.c_void_p, C.POINTER(EosDesc)]
+    L.mali_background.argtypes = [C.c_void_p, C.POINTER(Buffers), C.c_int32, C.c_int32] + [C.c_void_p] * 6
     L.mali_setup_columns.argtypes = [C.c_void_p, C.POINTER(Buffers), C.c_int32, C.c_int32] + [C.c_void_p] * 5 + \
         [C.c_int32, C.c_void_p]
     L.mali_compute_phi.argtypes = [C.c_void_p, C.POINTER(Buffers), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,

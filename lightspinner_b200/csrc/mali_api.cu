@@ -189,6 +189,9 @@ struct mali_model {
     AtomLevels atoms{};                 // model-level atom data of the device-side set-up (mali_model_set_atoms)
     std::vector<void *> atomDev;
     bool haveAtoms = false;
+    EosParams eos{};                    // EOS / background tables (mali_model_set_eos)
+    std::vector<void *> eosDev;
+    bool haveEos = false;
     GijCont *d_gijCont = nullptr;
     GijTile *d_gijTiles = nullptr;
     int nGijCont = 0;
@@ -311,11 +314,11 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
     auto htake = [&](int64_t n) { int64_t r = h; h += n; return r; };
     L.hp_height = htake(N);
     L.hp_bbc = htake(2 * (int64_t)d->Nspect);
-    L.hp_bg_chi = htake((int64_t)d->Nspect * N);
+    L.hp_nTotal = htake((int64_t)d->Natom * N);
+    L.hp_bg_chi = htake((int64_t)d->Nspect * N);  // from here on: blocks mali_background can form on the device
     L.hp_bg_eta = htake((int64_t)d->Nspect * N);
     L.hp_bg_sca = htake((int64_t)d->Nspect * N);
-    L.hp_nTotal = htake((int64_t)d->Natom * N);
-    L.hp_C = htake((int64_t)m->sumNlevel2 * N);   // from here on: blocks the device-side set-up can form itself
+    L.hp_C = htake((int64_t)m->sumNlevel2 * N);   // from here on: blocks mali_setup_columns can form on the device
     std::vector<int64_t> hpPhi(d->Ntrans, 0), hpGij(d->Ntrans, 0);
     L.hp_gijcont = h;
     for (int t = 0; t < d->Ntrans; ++t)
@@ -696,6 +699,8 @@ void mali_model_destroy(mali_model *m)
         if (p) cudaFree(p);
     for (void *p : m->atomDev)
         if (p) cudaFree(p);
+    for (void *p : m->eosDev)
+        if (p) cudaFree(p);
     for (auto &g : m->iterGraphs) cudaGraphExecDestroy(g.exec);
     for (cudaEvent_t e : m->profEvents) cudaEventDestroy(e);
     for (int q = 0; q < 2; ++q) {
@@ -744,8 +749,9 @@ static int check_range(const mali_model *m, const mali_buffers *b, int col0, int
 }
 
 // mode 0: whole host-pack blocks; 1: without the line profiles (mali_compute_phi forms them); 2: only the blocks'
-// first hp_C doubles -- heights, boundary Planck values, background, nTotal -- (mali_setup_columns forms C, the
-// continua's g_ij and the LTE populations as well)
+// first hp_C doubles -- heights, boundary Planck values, nTotal, background -- (mali_setup_columns forms C, the
+// continua's g_ij and the LTE populations as well); 3: only the first hp_bg_chi doubles (mali_background forms the
+// background opacities, too)
 static int upload_columns(const mali_model *m, const mali_buffers *b, int32_t col0, int32_t ncol, const double *host_pack,
                           double *staging_dev, void *stream, int mode)
 {
@@ -758,7 +764,7 @@ static int upload_columns(const mali_model *m, const mali_buffers *b, int32_t co
         if (!nophi)
             CU(cudaMemcpyAsync(staging_dev, host_pack, (size_t)ncol * L.hostpack * sizeof(double), cudaMemcpyHostToDevice, st));
         else {  // only the blocks' prefix without the line profiles (/ the derived blocks) crosses the bus
-            const size_t pre = (size_t)(mode == 2 ? L.hp_C : L.hp_phi) * sizeof(double);
+            const size_t pre = (size_t)(mode == 3 ? L.hp_bg_chi : (mode == 2 ? L.hp_C : L.hp_phi)) * sizeof(double);
             CU(cudaMemcpy2DAsync(staging_dev, (size_t)L.hostpack * sizeof(double), host_pack, pre, pre, (size_t)ncol,
                                  cudaMemcpyHostToDevice, st));
         }
@@ -772,7 +778,7 @@ static int upload_columns(const mali_model *m, const mali_buffers *b, int32_t co
     {
         dim3 grid(32, ncol);
         pack_misc_kernel<<<grid, 256, 0, st>>>(m->d_cjobs, (int)m->cjobs.size(), staging_dev, L.hostpack, b->colconst,
-                                               L.colconst, b->pops, L.pops, b->J, L.J, col0, mode == 2 ? 1 : 0);
+                                               L.colconst, b->pops, L.pops, b->J, L.J, col0, mode >= 2 ? 1 : 0);
     }
     m->launches += 2;
     CU(cudaGetLastError());
@@ -795,6 +801,79 @@ int mali_upload_columns_atmos(const mali_model *m, const mali_buffers *b, int32_
                               const double *host_pack_prefix, double *staging_dev, void *stream)
 {
     return upload_columns(m, b, col0, ncol, host_pack_prefix, staging_dev, stream, 2);
+}
+
+int mali_upload_columns_thermo(const mali_model *m, const mali_buffers *b, int32_t col0, int32_t ncol,
+                               const double *host_pack_prefix, double *staging_dev, void *stream)
+{
+    return upload_columns(m, b, col0, ncol, host_pack_prefix, staging_dev, stream, 3);
+}
+
+int mali_model_set_eos(mali_model *m, const mali_eos_desc *d)
+{
+    if (!m || !d || !d->tpf || !d->pf || !d->eion || !d->stage_off || !d->abund || d->npf < 2)
+        return fail(MALI_EINVAL, "mali_model_set_eos: bad argument");
+    CU(cudaSetDevice(m->device));
+    for (void *p : m->eosDev)
+        if (p) cudaFree(p);
+    m->eosDev.clear();
+    cudaError_t e = cudaSuccess;
+    auto put = [&](const void *src, size_t bytes) -> void * {
+        void *dv = nullptr;
+        if (e == cudaSuccess) e = cudaMalloc(&dv, std::max<size_t>(bytes, 8));
+        if (e == cudaSuccess && bytes) e = cudaMemcpy(dv, src, bytes, cudaMemcpyHostToDevice);
+        m->eosDev.push_back(dv);
+        return dv;
+    };
+    const int nst = d->stage_off[eos::kNcontr];
+    for (int q = 0; q < eos::kNcontr; ++q) {
+        const int ns = d->stage_off[q + 1] - d->stage_off[q];
+        if (ns < 2 || ns > eos::kMaxStage) return fail(MALI_ELIMIT, "mali_model_set_eos: element %d has %d stages (2..%d)", q, ns, eos::kMaxStage);
+    }
+    EosParams &P = m->eos;
+    P = EosParams{};
+    P.E.npf = d->npf;
+    P.E.tpf = (const double *)put(d->tpf, d->npf * sizeof(double));
+    P.E.pf = (const double *)put(d->pf, (size_t)nst * d->npf * sizeof(double));
+    P.E.eion = (const double *)put(d->eion, nst * sizeof(double));
+    P.E.stageOff = (const int32_t *)put(d->stage_off, (eos::kNcontr + 1) * sizeof(int32_t));
+    P.E.abund = (const double *)put(d->abund, 99 * sizeof(double));
+    P.E.avw = d->avw;
+    P.E.rho_from_H = d->rho_from_H;
+    P.E.ab_others = d->ab_others;
+    P.E.saha_fac = d->saha_fac;
+    P.E.prec = d->prec;
+    P.amu_wph = d->amu_weight_per_H;
+    P.cm3 = d->cm_to_m_cubed;
+    P.g_to_kg = 1.0E-03;
+    P.cm_to_m = 1.0E-02;
+    P.thomson = d->thomson_sigma;
+    if (e != cudaSuccess) return fail((int)e, "mali_model_set_eos: %s", cudaGetErrorString(e));
+    m->haveEos = true;
+    return MALI_OK;
+}
+
+int mali_background(const mali_model *m, const mali_buffers *b, int32_t col0, int32_t ncol, const double *T,
+                    const double *ne, const double *nHTot, const double *cmass, double *work, void *stream)
+{
+    if (int r = check_range(m, b, col0, ncol, "mali_background")) return r;
+    if (!T || !ne || !nHTot || !work || !b->colconst) return fail(MALI_EINVAL, "mali_background: null buffer");
+    if (!m->haveEos) return fail(MALI_EINVAL, "mali_background: call mali_model_set_eos first");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = m->N * ncol;
+    eos_kernel<<<(n + 63) / 64, 64, 0, st>>>(m->eos, m->N, ncol, T, nHTot, work);
+    dim3 grid((m->N + 63) / 64, m->Nspect, ncol);
+    background_kernel<<<grid, 64, 0, st>>>(m->eos, m->d_tiles, m->d_wavelength, m->N, m->Nspect, m->Lw, T, ne, work,
+                                           b->colconst, m->lay.colconst, m->off_tab, col0);
+    m->launches += 2;
+    if (cmass) {   // the caller's depth scale is column mass: heights come from here as well (atmosphere.py:94-111)
+        double *tau = work + (size_t)n * kEosWork;
+        convert_scales_kernel<<<(ncol + 31) / 32, 32, 0, st>>>(m->eos, m->N, ncol, cmass, nHTot, work, b->colconst,
+                                                               m->lay.colconst, m->off_z, col0, tau);
+        m->launches += 1;
+    }
+    CU(cudaGetLastError());
+    return MALI_OK;
 }
 
 int mali_model_set_atoms(mali_model *m, const mali_atom_desc *a)

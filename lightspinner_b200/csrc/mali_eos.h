@@ -730,3 +730,27 @@ MALI_EOS_HD void cop_one(double T, double TKEV, double HKT, double TLOG, double 
 
 }  // namespace eos
 }  // namespace mali
+
+#undef Z4LOG
+#undef A0
+#undef A1c
+#undef B1c
+#undef C1c
+#undef G0
+#undef HEFREQ0
+#undef CHI0
+#undef PEACH0
+#undef FREQMG
+#undef FLOG0
+#undef TLG0
+#undef PEACH1
+#undef FREQSI1
+#undef FLOG1
+#undef TLG1
+#undef G1
+#undef E1
+#undef WNO1
+#undef PEACH2
+#undef FREQSI2
+#undef FLOG2
+#undef TLG2

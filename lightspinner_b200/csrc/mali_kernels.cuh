@@ -3,6 +3,7 @@
 // structure-specialised formal-solution kernels live in mali_fs_spec.cuh / mali_fs_class.cu).
 #pragma once
 #include "mali_device.cuh"
+#include "mali_eos.h"
 
 namespace mali {
 
@@ -469,13 +470,10 @@ __global__ void pack_tiles_kernel(const PackChunk *chunks, const PackTile *tiles
                 const int f = ef / Lw, ls = ef - f * Lw;
                 const int la = pt.la0 + ls;
                 const int laClamp = la < Nspect ? la : Nspect - 1;
-                if (f == 0)
-                    v = src[hpBgChi + (size_t)laClamp * N + k];
-                else if (f == 1)
-                    v = src[hpBgEta + (size_t)laClamp * N + k];
-                else if (f == 2)
-                    v = src[hpBgSca + (size_t)laClamp * N + k];
-                else if (f - 3 < pt.nslot) {
+                if (f < 3) {
+                    if (skipPhi < 3)        // (3: background_kernel forms chi / eta / sca on the device)
+                        v = src[(f == 0 ? hpBgChi : (f == 1 ? hpBgEta : hpBgSca)) + (size_t)laClamp * N + k];
+                } else if (f - 3 < pt.nslot) {
                     const PackSlot ps = slots[pt.slot0 + f - 3];
                     const int lt = la - ps.Nblue;
                     if (la < Nspect && lt >= 0 && lt < ps.Nlam) {
@@ -703,6 +701,118 @@ __global__ void setup_gij_kernel(const GijCont *conts, const GijTile *gt, const 
                          exp(-hc_k / wavelength[la] / T[(size_t)c * N + k]);
         tab[g.f + (size_t)k * g.stride + ls] = v;
     }
+}
+
+// --------------------------------------------------------------------------------------------------------
+// Background / EOS on the device: Background.compute_background_eos (background.py:21-53) and the
+// column-mass branch of AtmosphereConstructor.convert_scales (atmosphere.py:70-112) for a batch of columns.
+struct EosParams {
+    eos::Tables E;
+    double amu_wph;        // Amu * weightPerH                                  (background.py:33, atmosphere.py:81-82)
+    double cm3, g_to_kg;   // CM_TO_M**3, G_TO_KG
+    double cm_to_m;        // CM_TO_M
+    double thomson;        // the Thomson cross-section of background.py:11
+};
+// per (column, depth) thermodynamic state: work[(c * N + k) * kEosWork + ...]
+constexpr int kEosWork = 20;   // pgas, pe, chi_c (per m at 5000 A), then the 17 background partials
+
+// one thread per (column, depth): gas and electron pressure from (T, rho), the background partial densities, and the
+// 5000 A opacity the scale conversion needs
+__global__ void eos_kernel(const EosParams P, int N, int ncol, const double *T, const double *nHTot, double *work)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= N * ncol) return;
+    const double t = T[idx];
+    const double rho = P.amu_wph * nHTot[idx] * P.cm3 / P.g_to_kg;                       // background.py:33
+    double *w = work + (size_t)idx * kEosWork;
+    const double pgas = eos::pg_from_rho(P.E, t, rho);
+    const double pe = eos::pe_from_rho(P.E, t, rho);
+    w[0] = pgas;
+    w[1] = pe;
+    eos::background_partials(P.E, t, pgas, pe, w + 3);
+    const double TK = t * eos::BK, TKEV = TK / eos::EV, HTK = eos::HH / TK, TLOG = log(t), xne = pe / TK;
+    double op, sc;
+    eos::cop_one(t, TKEV, HTK, TLOG, xne, 5000.0, w + 3, op, sc);
+    w[2] = op / P.cm_to_m;                                                                // atmosphere.py:92
+}
+
+// one thread per (column, wavelength, depth): chi = cop / CM_TO_M, eta = planck(T, lambda) * chi (utils.py:17-22 as numpy
+// evaluates it for an array of wavelengths), sca = ne * sigma_T  -- written into the bg fields of the tile records
+__global__ void background_kernel(const EosParams P, const TileDesc *tiles, const double *wavelength, int N, int Nspect,
+                                  int Lw, const double *T, const double *ne, const double *work, double *colconst,
+                                  int64_t colStride, int64_t offTab, int col0)
+{
+    const int c = blockIdx.z;
+    const int la = blockIdx.y;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= N) return;
+    const size_t idx = (size_t)c * N + k;
+    const double t = T[idx];
+    const double *w = work + idx * kEosWork;
+    const double TK = t * eos::BK, TKEV = TK / eos::EV, HTK = eos::HH / TK, TLOG = log(t), xne = w[1] / TK;
+    const double wav = wavelength[la];
+    double op, sc;
+    eos::cop_one(t, TKEV, HTK, TLOG, xne, wav * 10, w + 3, op, sc);
+    const double chi = op / P.cm_to_m;
+    // utils.planck with an array argument: numpy power / exp
+    const double hc_Tkla = kHC / (kKBoltzmann * kNmToM * wav) / t;
+    const double twohnu3_c2 = (2.0 * kHC) / pow(kNmToM * wav, 3.0);
+    const double eta = twohnu3_c2 / (exp(hc_Tkla) - 1.0) * chi;
+    const int ti = la / Lw, ls = la - ti * Lw;
+    const TileDesc td = tiles[ti];
+    double *f = colconst + (size_t)(col0 + c) * colStride + offTab + td.recOff + (size_t)k * td.stride + td.bgOff + ls;
+    f[0] = chi;
+    f[Lw] = eta;
+    f[2 * Lw] = ne[idx] * P.thomson;
+    // lanes of the last tile past the end of the spectrum carry the last wavelength's values (as the host pack does)
+    if (la == Nspect - 1)
+        for (int q = ls + 1; q < Lw; ++q) {
+            f[q - ls] = chi;
+            f[Lw + q - ls] = eta;
+            f[2 * Lw + q - ls] = ne[idx] * P.thomson;
+        }
+}
+
+// one thread per column: the column-mass branch of convert_scales (atmosphere.py:94-111): heights from the column
+// mass and density, the 5000 A optical depth, and the shift that puts tau_500 = 1 at height 0 (numpy.interp)
+__global__ void convert_scales_kernel(const EosParams P, int N, int ncol, const double *cmass, const double *nHTot,
+                                      const double *work, double *colconst, int64_t colStride, int64_t off_z, int col0,
+                                      double *tau_out)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncol) return;
+    const double *cm = cmass + (size_t)c * N, *nh = nHTot + (size_t)c * N;
+    const double *w = work + (size_t)c * N * kEosWork;
+    double *z = colconst + (size_t)(col0 + c) * colStride + off_z;
+    double *tau = tau_out + (size_t)c * N;
+    double hPrev = 0.0, rhoPrev = P.amu_wph * nh[0], chiPrev = w[2];
+    double tauPrev = chiPrev / rhoPrev * cm[0];
+    z[0] = 0.0;
+    tau[0] = tauPrev;
+    for (int k = 1; k < N; ++k) {
+        const double rho = P.amu_wph * nh[k], chi = w[(size_t)k * kEosWork + 2];
+        const double h = hPrev - 2.0 * (cm[k] - cm[k - 1]) / (rhoPrev + rho);
+        const double ta = tauPrev + 0.5 * (chiPrev + chi) * (hPrev - h);
+        z[k] = h;
+        tau[k] = ta;
+        hPrev = h;
+        rhoPrev = rho;
+        chiPrev = chi;
+        tauPrev = ta;
+    }
+    // numpy.interp(1.0, tau, height): tau increases with depth
+    double h1;
+    if (1.0 <= tau[0])
+        h1 = z[0];
+    else if (1.0 >= tau[N - 1])
+        h1 = z[N - 1];
+    else {
+        int j = 0;
+        while (!(tau[j + 1] > 1.0)) ++j;        // tau[j] <= 1 < tau[j+1]
+        const double slope = (z[j + 1] - z[j]) / (tau[j + 1] - tau[j]);
+        h1 = slope * (1.0 - tau[j]) + z[j];
+    }
+    for (int k = 0; k < N; ++k) z[k] -= h1;
 }
 
 struct CopyJob {

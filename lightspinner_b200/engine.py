@@ -189,6 +189,56 @@ class MaliEngine:
             torch.cuda.current_stream(self.device).synchronize()
             self._last_vBroad = vBroad
 
+    def set_eos(self, eos_tables):
+        """Registers the EOS / background tables (lightspinner_b200.eos.EosTables) mali_background needs."""
+        self._eos_tables = eos_tables
+        desc = eos_tables.desc()
+        self._check(self.lib.mali_model_set_eos(self._handle, C.byref(desc)))
+
+    def upload_thermo(self, problems, col0=0, start_from_lte=True):
+        """The whole per-column set-up on the device, from the thermodynamic state: each problem supplies temperature,
+        ne, nHTot, vturb, vlos, nTotal, the lines' damping parameters aDamp and either `cmass` (a column-mass depth
+        scale: the heights come from convert_scales' recurrence on the device) or `height`.  The EOS, the background
+        opacities (mali_background), LTE populations, collisional rates, Doppler widths, the continua's g_ij
+        (mali_setup_columns) and the Voigt profiles (mali_compute_phi) are all formed on the GPU.
+        Needs set_eos() and set_atoms()."""
+        staging, pinned = self._staging_bufs()
+        hpb = int(self.lay.hp_bg_chi)
+        pin_np = pinned.numpy()
+        N = self.mt.Nspace
+        if getattr(self, 'nStar', None) is None:
+            self.nStar = torch.zeros(self.ncol * self.lay.sumNlevel * N, dtype=torch.float64, device=self.device)
+        for c0 in range(0, len(problems), self.chunk):
+            chunk = problems[c0:c0 + self.chunk]
+            nc = len(chunk)
+            torch.cuda.current_stream(self.device).synchronize()  # pinned buffer reuse
+            for q, p in enumerate(chunk):
+                pack_column(self.mt, self.lay, p, out=pin_np[q * hpb:(q + 1) * hpb], with_background=False)
+            keys = ['temperature', 'ne', 'nHTot', 'vturb', 'vlos', 'aDamp'] + (['cmass'] if 'cmass' in chunk[0] else [])
+            aux = {k: torch.from_numpy(np.ascontiguousarray(np.stack(
+                [np.asarray(p[k], dtype=np.float64).reshape(-1, N) for p in chunk]))).to(self.device) for k in keys}
+            vBroad = torch.empty((nc, self.mt.Natom, N), dtype=torch.float64, device=self.device)
+            work = torch.empty(nc * N * 21, dtype=torch.float64, device=self.device)
+            ns = self.nStar[(col0 + c0) * self.lay.sumNlevel * N:(col0 + c0 + nc) * self.lay.sumNlevel * N]
+            P = lambda t: C.c_void_p(t.data_ptr())
+            with torch.cuda.device(self.device):
+                self._check(self.lib.mali_upload_columns_thermo(self._handle, C.byref(self.bufs), col0 + c0, nc,
+                                                                P(pinned), P(staging), self._stream()))
+                self._check(self.lib.mali_background(self._handle, C.byref(self.bufs), col0 + c0, nc,
+                                                     P(aux['temperature']), P(aux['ne']), P(aux['nHTot']),
+                                                     P(aux['cmass']) if 'cmass' in aux else None, P(work), self._stream()))
+                self._check(self.lib.mali_setup_columns(self._handle, C.byref(self.bufs), col0 + c0, nc,
+                                                        P(aux['temperature']), P(aux['ne']), P(aux['vturb']), P(ns),
+                                                        P(vBroad), 1 if start_from_lte else 0, self._stream()))
+                self._check(self.lib.mali_compute_phi(self._handle, C.byref(self.bufs), col0 + c0, nc, P(aux['aDamp']),
+                                                      P(vBroad), P(aux['vlos']), self._stream()))
+            if not start_from_lte:
+                for q, p in enumerate(chunk):
+                    self.set_n(col0 + c0 + q, p['n'])
+            torch.cuda.current_stream(self.device).synchronize()
+            self._last_vBroad = vBroad
+            self._last_work = work
+
     def upload_packed_device_phi(self, host_prefix_pinned, aDamp, vBroad, vlos, col0, ncol, staging=None):
         """Asynchronous form of upload_device_phi: `host_prefix_pinned` holds [ncol][lay.hp_phi] doubles (pinned),
         aDamp / vBroad / vlos are device tensors [ncol][Ntrans|Natom|1][Nspace]."""

@@ -151,7 +151,7 @@ def planck_bc(wavelength, temperature):
     return out
 
 
-def pack_column(mt, lay, p, out=None, with_phi=True, with_derived=True):
+def pack_column(mt, lay, p, out=None, with_phi=True, with_derived=True, with_background=True):
     """Concatenate one column's reference-layout arrays into the host staging block (`mali_layout.hp_*`).
 
     No transposition happens on the host: mali_upload_columns re-lays the data out on the device.
@@ -159,11 +159,15 @@ def pack_column(mt, lay, p, out=None, with_phi=True, with_derived=True):
     mali_compute_phi then forms on the device).
     with_derived=False: only the first `lay.hp_C` doubles -- heights, boundary Planck values, background, nTotal --
     (mali_setup_columns forms C, the continua's g_ij and the LTE populations on the device as well).
+    with_background=False: only the first `lay.hp_bg_chi` doubles -- heights (zeros if the problem has none: a
+    column-mass scale that mali_background converts), boundary Planck values, nTotal.
     """
     N, Nspect = mt.Nspace, mt.Nspect
+    if not with_background:
+        with_derived = False
     if not with_derived:
         with_phi = False
-    size = lay.hostpack if with_phi else (lay.hp_phi if with_derived else lay.hp_C)
+    size = lay.hostpack if with_phi else (lay.hp_phi if with_derived else (lay.hp_C if with_background else lay.hp_bg_chi))
     if out is None:
         out = np.empty(size)
     if out.shape[0] != size:
@@ -175,12 +179,14 @@ def pack_column(mt, lay, p, out=None, with_phi=True, with_derived=True):
             raise ValueError('array of %d elements where %d were expected' % (a.size, size))
         out[off:off + size] = a.reshape(-1)
 
-    put(lay.hp_height, p['height'], N)
+    put(lay.hp_height, p['height'] if 'height' in p else np.zeros(N), N)
     put(lay.hp_bbc, planck_bc(mt.wavelength, _f64(p['temperature'])), 2 * Nspect)
+    put(lay.hp_nTotal, p['nTotal'], mt.Natom * N)
+    if not with_background:
+        return out
     put(lay.hp_bg_chi, p['bg_chi'], Nspect * N)
     put(lay.hp_bg_eta, p['bg_eta'], Nspect * N)
     put(lay.hp_bg_sca, p['bg_sca'], Nspect * N)
-    put(lay.hp_nTotal, p['nTotal'], mt.Natom * N)
     if not with_derived:
         return out
     put(lay.hp_C, p['C'], lay.sumNlevel2 * N)
