@@ -540,24 +540,28 @@ def main():
             e1.upload([c1])
             out = {}
             for mode in ('host_loop', 'device_loop'):
-                e1.upload([c1])
-                e1.reset_iteration_state()
-                torch.cuda.synchronize(dev)
-                t0 = time.perf_counter()
-                if mode == 'host_loop':       # test.py:20-29 driven from Python, two scalar reads per iteration
-                    dJ, dP, it = 1.0, 1.0, 0
-                    while (dJ > 2e-3 or dP > 1e-3) and it < 500:
-                        it += 1
-                        dJ = float(e1.formal_sol_gamma_matrices()[0])
-                        if it > 3:
-                            dP = float(e1.stat_equil()[0])
-                else:                         # mali_iterate: the loop stays on the device (a replayed CUDA graph);
-                    for _ in range(8):        # the host looks at the convergence flag every 16 iterations
-                        e1.iterate_async(16)
-                        if bool((e1.t_done != 0).all().item()):
-                            break
-                    it = int(e1.t_iter.cpu()[0])
-                out[mode] = {'iterations': it, 'seconds': time.perf_counter() - t0}
+                best = None
+                for rep in range(3):              # best of 3: the first device loop also captures its CUDA graph
+                    e1.upload([c1])
+                    e1.reset_iteration_state()
+                    torch.cuda.synchronize(dev)
+                    t0 = time.perf_counter()
+                    if mode == 'host_loop':       # test.py:20-29 driven from Python, two scalar reads per iteration
+                        dJ, dP, it = 1.0, 1.0, 0
+                        while (dJ > 2e-3 or dP > 1e-3) and it < 500:
+                            it += 1
+                            dJ = float(e1.formal_sol_gamma_matrices()[0])
+                            if it > 3:
+                                dP = float(e1.stat_equil()[0])
+                    else:                         # mali_iterate: the loop stays on the device (a replayed CUDA graph);
+                        for _ in range(8):        # the host looks at the convergence flag every 16 iterations
+                            e1.iterate_async(16)
+                            if bool((e1.t_done != 0).all().item()):
+                                break
+                        it = int(e1.t_iter.cpu()[0])
+                    dt = time.perf_counter() - t0
+                    best = dt if best is None else min(best, dt)
+                out[mode] = {'iterations': it, 'seconds': best}
             single = {'config': 'CaII/FALC single column (test.py problem), to convergence', **out}
             e1.close()
         except Exception as ex:   # never let the side measurement break the main line
