@@ -11,8 +11,9 @@ columns per GPU (default 1024; 8 GPUs = the config's 8192), CaII + H 6-level bot
 lightspinner_b200/synth.py.  Columns shard across ranks with no data-path collective (weak scaling); the only
 exchange is the final gather of the emergent intensities, done inside the e2e region when N > 1.
 
-A *step* is one fixed-length MALI solve of the whole batch: `iters` iterations, each = formal solution + Gamma
-(fs_gamma_kernel, gamma_finish_kernel) + statistical equilibrium (stat_equil_kernel).
+A *step* is one fixed-length MALI solve of the whole batch: `iters` iterations of the device-resident loop
+(mali_iterate, convergence test off), each = formal solution + Gamma (fs_gamma_kernel_m, gamma_finish_kernel,
+j_finish_kernel) + statistical equilibrium (stat_equil_kernel).
   value : units / s with the inputs already resident in HBM (units = ncol_total * Nspect * Nrays * Nspace * iters)
   e2e   : the same solve through the public API from pinned HOST buffers: every step copies every column's
           inputs host->device (chunked, a copy stream running ahead of the compute stream), re-lays them out on
@@ -198,6 +199,39 @@ def reference_numpy_side_number():
     return None
 
 
+def run_lambda_shard(args):
+    """BASELINE config 5 (an experiment, not the production path): one stress column -- 10x refined wavelength grid,
+    10-point quadrature, 512 depths -- split over the GPUs by wavelength; every iteration all-reduces Gamma over NCCL.
+    A step is one MALI iteration of the column (strong scaling: the column is fixed)."""
+    sys.path.insert(0, os.path.join(ROOT, 'tools'))
+    import lambda_shard_experiment as ls
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    json_fd = None
+    if world > 1:
+        os.environ.setdefault('NCCL_DEBUG', 'INFO')
+        sys.stdout.flush()
+        json_fd = os.dup(1)
+        os.dup2(2, 1)
+    q = ls.build_problem()
+    out = ls.run(q, iters=max(6, args.steps))
+    if rank == 0:
+        line = {'metric': METRIC, 'value': out['updates_per_s'], 'unit': UNIT, 'n_gpus': world, 'steps': max(6, args.steps),
+                'warmup': max(6, args.steps), 'ms_per_step': out['ms_per_iteration'], 'higher_is_better': True,
+                'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+                'config': {'workload': 'EXPERIMENT: wavelength-sharded single stress column (BASELINE config 5), Gamma '
+                                       'all-reduce over NCCL every iteration', 'Nspect': out['Nspect'], 'Nrays': out['Nrays'],
+                           'Nspace': out['Nspace'], 'parallelism': 'wavelengths sharded over %d GPU(s)' % world},
+                'lambda_shard': out, 'e2e': None, 'gpu_launches': None}
+        if json_fd is not None:
+            os.write(json_fd, (json.dumps(line) + '\n').encode())
+        else:
+            print(json.dumps(line))
+    import torch.distributed as dist
+    if dist.is_initialized():
+        dist.destroy_process_group()
+
+
 def workload_config(args, base):
     return {
         'workload': 'synthetic 1.5D batch of perturbed FALC columns, CaII + H 6-level active '
@@ -225,6 +259,9 @@ def main():
     ap.add_argument('--chunk', type=int, default=512, help='columns per upload chunk in the e2e path')
     ap.add_argument('--first-chunk', type=int, default=0,
                     help='e2e path: size of a smaller first chunk (shortens the exposed first host->device copy)')
+    ap.add_argument('--workload', default='columns', choices=['columns', 'lambda_shard'],
+                    help='columns: the headline column-sharded batch; lambda_shard: BASELINE config 5 experiment, one '
+                         'stress column wavelength-sharded over the GPUs with a Gamma all-reduce per iteration')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     args = ap.parse_args()
@@ -233,6 +270,9 @@ def main():
 
     if args.impl == 'reference':
         run_reference(args, base)
+        return
+    if args.workload == 'lambda_shard':
+        run_lambda_shard(args)
         return
 
     import torch
@@ -305,11 +345,14 @@ def main():
         torch.cuda.synchronize(dev)
 
     fill_batch(want_e2e)
+    eng.reset_iteration_state()
+    eng.iterate_async(4, tolJ=-1.0)      # brings every column's iteration counter past 3 (test.py:27)
 
     def solve_resident():
-        for _ in range(iters):
-            eng.formal_sol_gamma_async()
-            eng.stat_equil_async()
+        # the device-resident loop with the convergence test off: `iters` iterations of formal solution + Gamma +
+        # statistical equilibrium for every column (the columns' iteration counters are past 3 after the warm-up, so
+        # every iteration solves the populations, as in the CPU arm)
+        eng.iterate_async(iters, tolJ=-1.0)
 
     # ---- value: inputs resident in HBM
     for _ in range(args.warmup):
@@ -409,9 +452,7 @@ def main():
                     ready.record()
                 with torch.cuda.stream(streams[1]):      # compute stream: the solves, one chunk after the other
                     streams[1].wait_event(ready)
-                    for _ in range(iters):
-                        eng.formal_sol_gamma_async(c0, nc)
-                        eng.stat_equil_async(c0, nc)
+                    eng.iterate_async(iters, tolJ=-1.0, col0=c0, ncol=nc)
                     out_I[c0 * lay.I:(c0 + nc) * lay.I].copy_(eng.t_I[c0 * lay.I:(c0 + nc) * lay.I], non_blocking=True)
                     out_n[c0 * lay.pops:(c0 + nc) * lay.pops].copy_(eng.t_pops[c0 * lay.pops:(c0 + nc) * lay.pops],
                                                                   non_blocking=True)
@@ -483,9 +524,7 @@ def main():
                         ready.record()
                     with torch.cuda.stream(streams[1]):
                         streams[1].wait_event(ready)
-                        for _ in range(iters):
-                            eng.formal_sol_gamma_async(c0, nc)
-                            eng.stat_equil_async(c0, nc)
+                        eng.iterate_async(iters, tolJ=-1.0, col0=c0, ncol=nc)
                         out_I[c0 * lay.I:(c0 + nc) * lay.I].copy_(eng.t_I[c0 * lay.I:(c0 + nc) * lay.I], non_blocking=True)
                         out_n[c0 * lay.pops:(c0 + nc) * lay.pops].copy_(eng.t_pops[c0 * lay.pops:(c0 + nc) * lay.pops],
                                                                       non_blocking=True)

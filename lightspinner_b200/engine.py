@@ -20,9 +20,10 @@ from .tables import ModelTables, pack_column
 
 
 class MaliEngine:
-    def __init__(self, model, ncol, device=None, max_upload_chunk=64, specialize=False, arith=None):
+    def __init__(self, model, ncol, device=None, max_upload_chunk=64, specialize=False, arith=None, library=None):
         """arith: 'exact' | 'contracted' | None (the library's default / the MALI_ARITH environment variable) -- the
         arithmetic mode of the formal-solution kernels, see include/mali_b200.h (mali_model_set_arith).
+        library: path of another build of the library with the same ABI (e.g. the checked build of tools/build_variants.py).
         specialize=True: if the model has wavelength tiles without a specialised kernel instance and nvcc is
         available, build (once, cached) a model-specific variant of the library; otherwise those tiles run on the
         generic kernel.  specialize=<problem dict>: build / pick the variant that covers THAT model (e.g. the full
@@ -32,7 +33,7 @@ class MaliEngine:
         self.mt = model if isinstance(model, ModelTables) else ModelTables(model)
         self.ncol = int(ncol)
         self.device = torch.device('cuda', torch.cuda.current_device() if device is None else device)
-        lib_path = None
+        lib_path = library
         if isinstance(specialize, dict) or (specialize and not isinstance(model, ModelTables)):
             from . import specialize as _spec
             lib_path = _spec.library_for(specialize if isinstance(specialize, dict) else model)

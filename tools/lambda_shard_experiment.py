@@ -21,6 +21,78 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
 
 
+def build_problem(refine=10, nrays=10, ndepth=512, base_name='stress_r10_d512'):
+    """The stress column: the reference-made 10-ray / 512-depth CaII column (tests/golden/stress_r10_d512.npz, built by
+    the reference's own recipe with the x1 wavelength grid) with every wavelength interval refined `refine` times
+    (lightspinner_b200.synth.stress_problem; the reference's x10 grid refines the lines only: Nspect 2627)."""
+    from helpers import load_golden
+    from lightspinner_b200 import synth
+    base, _ = load_golden(base_name)
+    return synth.stress_problem(base, refine=refine, nrays=nrays, ndepth=ndepth)
+
+
+def run(q, iters=6, init_dist=True):
+    """Times `iters` MALI iterations of the wavelength-sharded column on the ranks of the current torchrun launch.
+    Returns a dict (rank 0) with per-iteration times, split into formal solution / all-reduce / statistical equilibrium."""
+    import torch
+    import torch.distributed as dist
+    from lightspinner_b200.lambda_shard import LambdaShardedColumn
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1 and init_dist and not dist.is_initialized():
+        dist.init_process_group('nccl', device_id=dev)
+    col = LambdaShardedColumn(q, device=local, specialize=True)
+    info = col.eng.model_info()
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def one_pass():
+        col.eng.upload([col.sub])
+        col.eng.reset_iteration_state()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        fs, ar, se, tot = [], [], [], []
+        for it in range(1, iters + 1):
+            e = [ev() for _ in range(4)]
+            e[0].record()
+            col.eng.formal_sol_gamma_async()
+            e[1].record()
+            if world > 1:
+                dist.all_reduce(col.eng.t_Gamma, op=dist.ReduceOp.SUM)
+                dist.all_reduce(col.eng.t_dJ, op=dist.ReduceOp.MAX)
+            e[2].record()
+            if it > 3:
+                col.eng.stat_equil_async()
+            e[3].record()
+            torch.cuda.synchronize(dev)
+            fs.append(e[0].elapsed_time(e[1]))
+            ar.append(e[1].elapsed_time(e[2]))
+            se.append(e[2].elapsed_time(e[3]))
+            tot.append(e[0].elapsed_time(e[3]))
+        return [float(np.median(x)) for x in (fs, ar, se, tot)]
+
+    one_pass()                                        # warm-up (library load, NCCL channels)
+    med = one_pass()
+    if world > 1:
+        t = torch.tensor(med, dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        med = [float(x) for x in t]
+    units = int(q['Nspect']) * int(q['Nrays']) * int(q['Nspace'])
+    out = {'experiment': 'wavelength-sharded single column (BASELINE config 5)', 'n_gpus': world,
+           'Nspect': int(q['Nspect']), 'Nrays': int(q['Nrays']), 'Nspace': int(q['Nspace']),
+           'units_per_iteration': units, 'wavelengths_this_rank': col.hi - col.lo, 'tiles_this_rank': info['ntile'],
+           'generic_tiles': info['generic_tiles'], 'ms_formal_solution': med[0], 'ms_gamma_allreduce': med[1],
+           'ms_stat_equil': med[2], 'ms_per_iteration': med[3],
+           'allreduce_share_of_iteration': med[1] / med[3] if med[3] > 0 else None,
+           'updates_per_s': units / (med[3] * 1e-3), 'exchange_bytes_per_iteration': int(col.eng.t_Gamma.numel()) * 8 + 8,
+           'finite': bool(np.isfinite(col.n()).all())}
+    col.close()
+    return out if rank == 0 else None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--refine', type=int, default=10)
