@@ -1031,6 +1031,14 @@ static FsCommon make_fs_common(const mali_model *m, const mali_buffers *b, int c
     c.col0 = col0;
     c.ncol = ncol;
     c.popsW = m->popsW;
+    // launch order (mali_fs_class.cu): slabs of 512 columns, the two directions of a tile next to each other: measured
+    // 17.2 GB of DRAM traffic per launch instead of 21.7 GB (a column's popsT rows are found in L2 by the later tiles)
+    // at the same or slightly better time; slabs of 128 columns cut the traffic to 15.8 GB but put ~14 kernel
+    // instances on an SM at once and lose 36 % to instruction-cache misses (profiles/r02_launch_order.txt)
+    static const int colChunk = getenv("MALI_COL_CHUNK") ? atoi(getenv("MALI_COL_CHUNK")) : 512;
+    static const int dirInter = getenv("MALI_DIR_INTERLEAVE") ? atoi(getenv("MALI_DIR_INTERLEAVE")) : 1;
+    c.colChunk = std::max(1, std::min(colChunk, ncol));
+    c.dirInterleave = dirInter;
     c.colStride = m->lay.colconst;
     c.IStride = m->lay.I;
     c.scratchStride = m->lay.scratch;

@@ -42,9 +42,12 @@ template <int CLS, bool FAST>
 __global__ void __launch_bounds__(32, spec_class_warps(CLS)) fs_gamma_kernel_m(const __grid_constant__ MegaParams<CLS> P)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    // blockIdx.z = slab of colChunk columns, blockIdx.x = column inside the slab, blockIdx.y = (tile, direction): all
+    // tiles and both directions of a slab of columns run within a short window, so that what they share -- a column's
+    // popsT rows (read by every tile), a tile's fields (read by both directions) -- is found in L2 the second time
     const int nt = gridDim.y >> 1;
-    const int dir = blockIdx.y >= nt ? 1 : 0;
-    const TileR<MegaParams<CLS>::NSP> &T = P.tiles[blockIdx.y - dir * nt];
+    const int dir = P.c.dirInterleave ? (blockIdx.y & 1) : (blockIdx.y >= nt ? 1 : 0);
+    const TileR<MegaParams<CLS>::NSP> &T = P.tiles[P.c.dirInterleave ? (blockIdx.y >> 1) : (blockIdx.y - dir * nt)];
     switch (T.spec) {
 #define MALI_SPEC(ID, KEY, ...)                                                     \
     case ID:                                                                        \
@@ -89,7 +92,8 @@ cudaError_t MALI_FN(mali_fs_launch_)(const FsCommon &c, const void *tiles, int n
     for (int t0 = 0; t0 < nt; t0 += MP::kMaxTiles) {
         const int n = std::min(MP::kMaxTiles, nt - t0);
         memcpy(P->tiles, src + t0, sizeof(TR) * n);
-        dim3 grid(ncol, 2 * n);
+        const int chunk = std::max(1, std::min(c.colChunk, ncol));
+        dim3 grid(chunk, 2 * n, (ncol + chunk - 1) / chunk);
         fs_gamma_kernel_m<MALI_CLS, MALI_FAST != 0><<<grid, 32, smem, st>>>(*P);
         if (launches) *launches += 1;
     }

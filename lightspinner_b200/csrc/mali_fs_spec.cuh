@@ -39,7 +39,8 @@ constexpr int kRingStages = MALI_NST;   // stages of the per-warp TMA ring; a st
 
 struct FsCommon {  // launch-invariant parameters of the specialised kernels (constant bank)
     int32_t N, Nrays, Nspect, Lw;
-    int32_t col0, ncol, popsW, pad0;
+    int32_t col0, ncol, popsW, colChunk;   // colChunk: columns per grid slab (blockIdx.z), see mali_fs_class.cu
+    int32_t dirInterleave, pad0;
     int64_t colStride, IStride, scratchStride;
     int64_t off_bbc, off_tab, off_popsT;
     int64_t off_jpart, off_part, upOff;
@@ -223,7 +224,7 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
 
     // one warp per block: the column (hence every base pointer) is block-uniform -> uniform-register addressing
     const int lane = threadIdx.x;
-    const int col = p.col0 + blockIdx.x;
+    const int col = p.col0 + blockIdx.z * p.colChunk + blockIdx.x;
     if (col >= p.col0 + p.ncol) return;
     if (p.done != nullptr && p.done[col] != 0) return;
 

@@ -29,6 +29,23 @@ def jitter_factors(col, N):
     return np.stack([np.exp(0.01 * g1), np.exp(0.05 * g2), 1.0 + 0.02 * g3])
 
 
+def jitter_atmosphere(col, temperature, ne):
+    """BASELINE config 4's own recipe for synthetic column `col`, applied to the thermodynamic
+    state as the reference applies it to its AtmosphereConstructor before convert_scales:
+        T *= exp(0.01 g1),  ne *= exp(0.05 g2),  vlos = 2 km/s * g3        (hydrogen populations unchanged)
+    with g1, g2, g3 = 5-point-boxcar-smoothed standard normals from default_rng(20260000 + col).
+    Returns (T, ne, vlos [m/s])."""
+    N = int(np.asarray(temperature).shape[0])
+    rng = np.random.default_rng(20260000 + int(col))
+
+    def smooth(g):
+        return np.convolve(np.pad(g, 2, 'edge'), np.ones(5) / 5, 'valid')
+
+    g1, g2, g3 = (smooth(rng.standard_normal(N)) for _ in range(3))
+    return (np.asarray(temperature, dtype=np.float64) * np.exp(0.01 * g1),
+            np.asarray(ne, dtype=np.float64) * np.exp(0.05 * g2), 2000.0 * g3)
+
+
 def jitter_problem(p, col):
     """numpy form: returns a new problem dict for synthetic column `col` derived from base problem `p`."""
     N = int(p['Nspace'])
