@@ -798,6 +798,71 @@ def main():
         except Exception as ex:
             rf_thermo = {'error': repr(ex)}
 
+    # ---- BASELINE config 4 by its own recipe, from the thermodynamic state: every column is FALC
+    # with T *= exp(0.01 g1), ne *= exp(0.05 g2), vlos = 2 km/s g3 (lightspinner_b200.synth.jitter_atmosphere -- bit
+    # identical to the reference's columns 0 and 1), set up entirely on the device (EOS, background, heights, LTE
+    # populations, collisional rates, profiles) and run to convergence by the device-resident loop.  Columns 0 and 1
+    # exist as reference fixtures (tests/golden/c2v_jitter_cah_*.npz): their iteration counts and converged I, n are
+    # checked against the reference's inside this run.  (The lines' damping parameters are host inputs: columns 0 and 1
+    # carry their own, the others the unperturbed column's.)
+    c4 = None
+    if not args.no_cpu:
+        try:
+            from helpers import load_golden, load_setup_inputs
+            from lightspinner_b200.atoms import AtomTables
+            from lightspinner_b200.eos import EosTables
+            zeos = np.load(os.path.join(ROOT, 'tests', 'golden', 'eos.npz'))
+            atoms4, _ = load_setup_inputs('c2_falc_cah')
+            fx = {c: load_golden('c2v_jitter_cah_%d' % c) for c in (0, 1)}
+            n4 = min(ncol, 1024)
+            names4 = [str(x).strip().upper() for x in base['atom_names']]
+            ab4 = [atoms4[nm]['abundance'] for nm in names4]
+            probs = []
+            for c in range(n4):
+                gc = col_global0 + c
+                T4, ne4, vl4 = synth.jitter_atmosphere(gc, zeos['falc_T'], zeos['falc_ne'])
+                probs.append(dict(temperature=T4, ne=ne4, vlos=vl4, nHTot=zeos['falc_nHTot'], cmass=zeos['falc_cmass'],
+                                  vturb=base['vturb'], nTotal=np.stack([a * zeos['falc_nHTot'] for a in ab4]),
+                                  aDamp=fx[gc][0]['aDamp'] if gc in fx else base['aDamp']))
+            e5 = MaliEngine(base, n4, device=local, max_upload_chunk=256)
+            e5.set_eos(EosTables.from_arrays(zeos))
+            e5.set_atoms(AtomTables.from_arrays([dict(atoms4[nm]) for nm in names4]))
+            barrier()
+            t0 = time.perf_counter()
+            e5.upload_thermo(probs)
+            torch.cuda.synchronize(dev)
+            t_setup = max_over_ranks(time.perf_counter() - t0)
+            e5.reset_iteration_state()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(25):
+                e5.iterate_async(16)
+                if bool((e5.t_done != 0).all().item()):
+                    break
+            barrier()
+            t_solve = max_over_ranks(time.perf_counter() - t0)
+            e5.raise_on_faults()
+            its5 = e5.t_iter.cpu().numpy().astype(np.int64)
+            ok, detail = True, {}
+            for c in range(n4):
+                gc = col_global0 + c
+                if gc in fx:
+                    r5 = fx[gc][1]
+                    eI = float(np.max(np.abs(e5.I(c) - r5['final_I']) / np.abs(r5['final_I'])))
+                    en = float(np.max(np.abs(e5.n(c) - r5['final_n']) / np.abs(r5['final_n'])))
+                    detail['column_%d' % gc] = {'iterations': int(its5[c]), 'reference_iterations': int(r5['niter']),
+                                                'rel_err_I': eI, 'rel_err_n': en}
+                    ok = ok and int(its5[c]) == int(r5['niter']) and eI < 1e-10 and en < 1e-10
+            c4 = {'config': 'BASELINE config 4 by its own recipe: %d columns per GPU from (cmass, T, ne, nHTot, vturb, vlos), '
+                            'device-side set-up, to convergence' % n4,
+                  'columns_per_gpu': n4, 'setup_seconds': t_setup, 'seconds_to_converge': t_solve,
+                  'iterations_min': int(its5.min()), 'iterations_max': int(its5.max()), 'iterations_mean': float(its5.mean()),
+                  'updates_per_s': float(its5.sum()) * units_per_col_iter * world / t_solve,
+                  'reference_columns': detail, 'matches_reference': bool(ok) if detail else None}
+            e5.close()
+        except Exception as ex:
+            c4 = {'error': repr(ex)}
+
     # headline e2e: the path a user of the batch API takes -- upload_device_phi (the host hands over what the
     # reference's compute_phi consumes; profiles are formed on the device inside the timed region).  The variant that
     # ships host-computed profiles over PCIe is reported beside it.
@@ -812,7 +877,8 @@ def main():
                 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': cfg, 'clocks': clocks,
                 'e2e': e2e, 'e2e_host_phi': e2e_host, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu,
                 'single_column': single, 'to_convergence': conv, 'response_function': rf,
-                'response_function_from_thermodynamic_state': rf_thermo, 'results_finite': finite,
+                'response_function_from_thermodynamic_state': rf_thermo, 'config4_from_thermodynamic_state': c4,
+                'results_finite': finite,
                 'arith': arith_default, 'exact_arith': exact_side}
         if json_fd is not None:
             sys.stdout.flush()

@@ -81,34 +81,58 @@ MALI_EOS_HD void molecb(double X, double &Y0, double &Y1)
     Y1 = -12.533505 + X * (4.9251644 + X * (-5.6191273E-2 + X * 3.2687661E-3));
 }
 
+// Everything pe_pg / gasc evaluate that depends on the temperature only -- the partition functions of the 28 electron
+// donors, the exponentials and the power of theta inside saha(), the molecular equilibrium constants -- is formed once
+// per (temperature) point: the EOS iterations call pe_pg / gasc dozens of times at one temperature, and the values
+// are the very same each time (same expressions, same bits; only the products with pe are redone).
+struct PointCache {
+    double theta, th25;              // 5040 / t, theta**2.5
+    double u[kNcontr][3];            // partition_f(ii, t, only=3)
+    double ex1[kNcontr], ex2[kNcontr];   // exp(2.302585093 * (9.0804625434325867 - theta * eion[0 | 1]));  H: eion[0], 0.754
+    double p10c[2], p10[2];          // 10**molecb (clamped to +-30 as pe_pg does / as gasc takes it)
+};
+
+MALI_EOS_HD void point_cache(const Tables &E, double t, PointCache &C)
+{
+    C.theta = 5040.0 / t;
+    C.th25 = pow(C.theta, 2.5);
+    for (int ii = 0; ii < kNcontr; ++ii) {
+        partition_f(E, ii, t, 3, C.u[ii]);
+        const double e0 = E.eion[E.stageOff[ii]];
+        const double e1 = ii == 0 ? 0.754 : E.eion[E.stageOff[ii] + 1];
+        C.ex1[ii] = exp(2.302585093 * (9.0804625434325867 - C.theta * e0));
+        C.ex2[ii] = exp(2.302585093 * (9.0804625434325867 - C.theta * e1));
+    }
+    double c0, c1;
+    molecb(C.theta, c0, c1);
+    C.p10[0] = pow(10.0, c0);
+    C.p10[1] = pow(10.0, c1);
+    C.p10c[0] = pow(10.0, acota(c0, -30., 30.));
+    C.p10c[1] = pow(10.0, acota(c1, -30., 30.));
+}
+// saha() with its temperature-only factors taken from the cache: u2 * ex / (u1 * pe * theta**2.5)
+MALI_EOS_HD double saha_c(double ex, double u1, double u2, double pe, double th25) { return u2 * ex / (u1 * pe * th25); }
+
 // witt.py:342-432
-MALI_EOS_HD double pe_pg(const Tables &E, double t, double pe, double pgas, double &fe_out)
+MALI_EOS_HD double pe_pg(const Tables &E, const PointCache &C, double pe, double pgas, double &fe_out)
 {
     double g1 = 0.0;
-    const double theta = 5040.0 / t;
     double g4, g5;
     if (pe < 0.0) {
         pe = 1.e-15;
         g4 = 0.0;
         g5 = 0.0;
     } else {
-        double c0, c1;
-        molecb(theta, c0, c1);
-        c0 = acota(c0, -30., 30.);
-        c1 = acota(c1, -30., 30.);
-        g4 = pe * pow(10.0, c0);
-        g5 = pe * pow(10.0, c1);
+        g4 = pe * C.p10c[0];
+        g5 = pe * C.p10c[1];
     }
-    double u[kMaxStage];
-    partition_f(E, 0, t, 3, u);
-    const double g2 = saha(theta, E.eion[E.stageOff[0]], u[0], u[1], pe);
-    double g3 = saha(theta, 0.754, 1.0, u[0], pe);
+    const double g2 = saha_c(C.ex1[0], C.u[0][0], C.u[0][1], pe, C.th25);
+    double g3 = saha_c(C.ex2[0], 1.0, C.u[0][0], pe, C.th25);
     g3 = 1.0 / acota(g3, 1.e-30, 1.0e30);
     for (int ii = 1; ii < kNcontr; ++ii) {
         const double alfai = E.abund[ii] / E.abund[0];
-        partition_f(E, ii, t, 3, u);
-        const double a = saha(theta, E.eion[E.stageOff[ii]], u[0], u[1], pe);
-        const double b = saha(theta, E.eion[E.stageOff[ii] + 1], u[1], u[2], pe);
+        const double a = saha_c(C.ex1[ii], C.u[ii][0], C.u[ii][1], pe, C.th25);
+        const double b = saha_c(C.ex2[ii], C.u[ii][1], C.u[ii][2], pe, C.th25);
         const double c = 1. + a * (1. + b);
         g1 += alfai / c * a * (1. + 2. * b);
     }
@@ -151,22 +175,16 @@ MALI_EOS_HD double pe_pg(const Tables &E, double t, double pe, double pgas, doub
 }
 
 // witt.py:541-621.  pp: the hydrogen entries only (f1, f2, f5, f3, phtot, fe) -- the per-species entries are never read
-MALI_EOS_HD double gasc(const Tables &E, double t, double pe, double *pp6)
+MALI_EOS_HD double gasc(const Tables &E, const PointCache &C, double pe, double *pp6)
 {
-    const double theta = 5040. / t;
-    double c0, c1m;
-    molecb(theta, c0, c1m);
-    const double g4 = pow(10.0, c0), g5 = pow(10.0, c1m);
-    double u[kMaxStage];
-    partition_f(E, 0, t, 0, u);
-    const double g2 = saha(theta, E.eion[E.stageOff[0]], u[0], u[1], pe);
-    const double g3 = 1.0 / saha(theta, 0.754, 1.0, u[0], pe);
+    const double g4 = C.p10[0], g5 = C.p10[1];
+    const double g2 = saha_c(C.ex1[0], C.u[0][0], C.u[0][1], pe, C.th25);
+    const double g3 = 1.0 / saha_c(C.ex2[0], 1.0, C.u[0][0], pe, C.th25);
     double g1 = 0.0;
     for (int ii = 1; ii < kNcontr; ++ii) {
         const double alfai = E.abund[ii] / E.abund[0];
-        partition_f(E, ii, t, 3, u);
-        const double a = saha(theta, E.eion[E.stageOff[ii]], u[0], u[1], pe);
-        const double b = saha(theta, E.eion[E.stageOff[ii] + 1], u[1], u[2], pe);
+        const double a = saha_c(C.ex1[ii], C.u[ii][0], C.u[ii][1], pe, C.th25);
+        const double b = saha_c(C.ex2[ii], C.u[ii][1], C.u[ii][2], pe, C.th25);
         const double c = 1. + a * (1. + b);
         const double ppi = alfai / c;
         g1 += ppi * a * (1. + 2. * b);
@@ -226,7 +244,7 @@ MALI_EOS_HD double init_pe_from_pg(const Tables &E, double t, double pg)
 }
 
 // witt.py:226-244
-MALI_EOS_HD double pe_from_pg(const Tables &E, double t, double pg, double *fe_out = nullptr)
+MALI_EOS_HD double pe_from_pg(const Tables &E, const PointCache &C, double t, double pg, double *fe_out = nullptr)
 {
     double dif = 1.1;
     double pe = init_pe_from_pg(E, t, pg);
@@ -235,7 +253,7 @@ MALI_EOS_HD double pe_from_pg(const Tables &E, double t, double pg, double *fe_o
     while ((fabs(dif) > E.prec) && (it < 250)) {
         pe = (ope + pe) * 0.5;
         ope = pe;
-        pe = pe_pg(E, t, pe, pg, fe);
+        pe = pe_pg(E, C, pe, pg, fe);
         dif = 2.0 * fabs(pe - ope) / (pe + ope);
         it += 1;
     }
@@ -247,7 +265,7 @@ MALI_EOS_HD double start_fraction(double t) { return t > 8000 ? 0.5 : (t > 4000 
 
 // witt.py:248-279 (the reference's loop counter never advances: the loop ends on convergence only; a hard cap keeps a
 // pathological input from hanging a GPU)
-MALI_EOS_HD double pe_from_rho(const Tables &E, double t, double rho)
+MALI_EOS_HD double pe_from_rho(const Tables &E, const PointCache &C, double t, double rho)
 {
     const double xna = rho / E.avw;
     const double BKT = BK * t;
@@ -257,7 +275,7 @@ MALI_EOS_HD double pe_from_rho(const Tables &E, double t, double rho)
     double dif = 1.0, Pe = 0.0;
     int guard = 0;
     while (fabs(dif) > E.prec && guard < 1000) {
-        Pe = pe_from_pg(E, t, Pgas);
+        Pe = pe_from_pg(E, C, t, Pgas);
         const double xna_guessed = (Pgas - Pe) / BKT;
         dif = fabs(xna - xna_guessed) / xna;
         Pgas *= xna / xna_guessed;
@@ -267,31 +285,31 @@ MALI_EOS_HD double pe_from_rho(const Tables &E, double t, double rho)
 }
 
 // witt.py:312-318
-MALI_EOS_HD double rho_from_pe(const Tables &E, double temp, double pe)
+MALI_EOS_HD double rho_from_pe(const Tables &E, const PointCache &C, double temp, double pe)
 {
     double pp[6];
-    gasc(E, temp, pe, pp);
+    gasc(E, C, pe, pp);
     return pe * E.rho_from_H / (pp[5] * temp);
 }
 
 // witt.py:283-308
-MALI_EOS_HD double pg_from_rho(const Tables &E, double temp, double rho)
+MALI_EOS_HD double pg_from_rho(const Tables &E, const PointCache &C, double temp, double rho)
 {
     const double xna = rho / E.avw;
     const double a = start_fraction(temp);
     const double xne = a * xna / (1.0 - a);
     const double pgas0 = (xna + xne) * BK * temp;
-    double Pe = pe_from_pg(E, temp, pgas0);
-    double irho = rho_from_pe(E, temp, Pe);
+    double Pe = pe_from_pg(E, C, temp, pgas0);
+    double irho = rho_from_pe(E, C, temp, Pe);
     double dif = 1.0;
     int it = 0;
     while ((dif >= E.prec) && (it < 100)) {
         Pe *= (1.0 + rho / irho) * 0.5;
-        irho = rho_from_pe(E, temp, Pe);
+        irho = rho_from_pe(E, C, temp, Pe);
         dif = fabs((irho - rho) / (rho));
         it += 1;
     }
-    return gasc(E, temp, Pe, nullptr);
+    return gasc(E, C, Pe, nullptr);
 }
 
 // witt.py:625-667 with divide_by_u (only = 0: every stage of the element); xpa[0..nLev-1]
@@ -311,7 +329,7 @@ MALI_EOS_HD int getXparts(const Tables &E, int iatom, double t, double pg, doubl
 }
 
 // witt.py:671-740 with divide_by_u = True: n[17]
-MALI_EOS_HD void background_partials(const Tables &E, double t, double pg, double pe, double *n)
+MALI_EOS_HD void background_partials(const Tables &E, const PointCache &C, double t, double pg, double pe, double *n)
 {
     const double tbk = t * BK;
     double x[kMaxStage];
@@ -339,7 +357,7 @@ MALI_EOS_HD void background_partials(const Tables &E, double t, double pg, doubl
     getXparts(E, 7, t, pg, pe, true, x);   // O
     n[16] = x[0];
     double pp[6];
-    gasc(E, t, pe, pp);
+    gasc(E, C, pe, pp);
     n[0] = pp[0] * pp[4] / tbk * 0.5;      // H / pf[H]
     n[1] = pp[1] * pp[4] / tbk;            // H+
     n[2] = pp[3] * pp[4] / tbk;            // H-

@@ -725,11 +725,13 @@ __global__ void eos_kernel(const EosParams P, int N, int ncol, const double *T, 
     const double t = T[idx];
     const double rho = P.amu_wph * nHTot[idx] * P.cm3 / P.g_to_kg;                       // background.py:33
     double *w = work + (size_t)idx * kEosWork;
-    const double pgas = eos::pg_from_rho(P.E, t, rho);
-    const double pe = eos::pe_from_rho(P.E, t, rho);
+    eos::PointCache C;                      // the temperature-only factors of the EOS iterations, formed once
+    eos::point_cache(P.E, t, C);
+    const double pgas = eos::pg_from_rho(P.E, C, t, rho);
+    const double pe = eos::pe_from_rho(P.E, C, t, rho);
     w[0] = pgas;
     w[1] = pe;
-    eos::background_partials(P.E, t, pgas, pe, w + 3);
+    eos::background_partials(P.E, C, t, pgas, pe, w + 3);
     const double TK = t * eos::BK, TKEV = TK / eos::EV, HTK = eos::HH / TK, TLOG = log(t), xne = pe / TK;
     double op, sc;
     eos::cop_one(t, TKEV, HTK, TLOG, xne, 5000.0, w + 3, op, sc);
