@@ -736,11 +736,11 @@ def main():
             cols = [(k, s) for k in range(N1) for s in (+1, -1)]          # response_fn.py:24: 164 perturbed columns
             lo, cnt = shard_range(len(cols), world, rank)
             mine = cols[lo:lo + cnt]
-            base = {k: c1p[k] for k in ('Nspace', 'Nrays', 'Nspect', 'wavelength', 'muz', 'wmu', 'Nlevel', 'trans',
-                                        'linepar', 'alpha', 'vturb', 'vlos', 'atom_names')}
+            base1 = {k: c1p[k] for k in ('Nspace', 'Nrays', 'Nspect', 'wavelength', 'muz', 'wmu', 'Nlevel', 'trans',
+                                         'linepar', 'alpha', 'vturb', 'vlos', 'atom_names')}
             probs = []
             for k, sgn in mine:
-                q = dict(base)
+                q = dict(base1)
                 T = np.array(zeos['falc_T'])
                 T[k] += 25.0 * sgn
                 q['temperature'], q['ne'], q['nHTot'], q['cmass'] = T, zeos['falc_ne'], zeos['falc_nHTot'], zeos['falc_cmass']

@@ -96,3 +96,37 @@ def test_batch_context_rejects_columns_of_different_models():
         BatchContext([fake_reference_objects(p), fake_reference_objects(q)])
     with pytest.raises(ValueError):
         BatchContext([])
+
+
+@pytest.mark.reference
+def test_atom_and_eos_tables_from_live_reference_objects():
+    """With /root/reference present: the model-level tables of the device-side set-up built from the REAL reference
+    objects (AtomTables.from_models, EosTables.from_witt) equal the ones built from the committed fixtures
+    (tests/golden/setup_inputs.npz, eos.npz) -- the path a user of the reference takes and the path the GPU tests take
+    are the same data."""
+    from oracle.refharness import reference_available, load_reference
+    if not reference_available():
+        pytest.skip('Lightspinner reference not present')
+    import os
+    from helpers import GOLDEN, load_setup_inputs
+    from lightspinner_b200.atoms import AtomTables
+    from lightspinner_b200.eos import EosTables
+    ref = load_reference()
+    models = [ref['rh_atoms'].H_6_atom(), ref['rh_atoms'].CaII_atom()]
+    table = ref['atomic_set'].RadiativeSet(models).atomicTable
+    live = AtomTables.from_models(models, table)
+    atoms, _ = load_setup_inputs('c2_falc_cah')
+    fix = AtomTables.from_arrays([dict(atoms['H']), dict(atoms['CA'])])
+    for k in ('Nlevel', 'dE', 'gi0', 'dZ', 'nDebye', 'g', 'vTherm', 'coll', 'knots', 'coef', 'fill', 'par'):
+        assert np.array_equal(getattr(live, k), getattr(fix, k)), k
+    assert live.c1 == fix.c1 and live.c2 == fix.c2
+    import witt as W
+    z = np.load(os.path.join(GOLDEN, 'eos.npz'))
+    e_live = EosTables.from_witt(W.witt(), ref['atomic_table'].get_global_atomic_table().weightPerH)
+    e_fix = EosTables.from_arrays(z)
+    for k in ('tpf', 'pf', 'eion', 'stage_off'):
+        assert np.array_equal(getattr(e_live, k), getattr(e_fix, k)), k
+    # witt.__init__ renormalises the class-level abundances in place on every instantiation: equal to rounding only
+    assert np.allclose(e_live.abund, e_fix.abund, rtol=1e-14, atol=0)
+    for k in ('avw', 'rho_from_H', 'ab_others', 'saha_fac', 'amu_wph', 'cm3', 'thomson'):
+        assert abs(getattr(e_live, k) / getattr(e_fix, k) - 1.0) < 1e-14, k
