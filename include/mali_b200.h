@@ -252,7 +252,9 @@ int mali_stat_equil(const mali_model *m, const mali_buffers *bufs, int32_t col0,
 /* The loop of test.py:20-29 kept on the device: up to max_iter iterations of formal solution (+ stat_equil once
  * a column's own iteration counter exceeds 3); a column whose (dJ, dPops) satisfy dJ <= tolJ && dPops <= tolPops
  * is flagged done and no longer touched.  tolJ < 0 disables the convergence test (fixed iteration count).
- * All launches are asynchronous on `stream`; no host synchronisation happens inside.  bufs->iter / done must be
+ * One iteration is captured into a CUDA graph (cached per buffers / range / tolerances / arithmetic mode) and replayed;
+ * a caller on the legacy default stream is served on a library-owned stream forked from / joined into it with events.
+ * All launches are asynchronous and ordered on `stream`; no host synchronisation happens inside.  bufs->iter / done must be
  * zeroed and bufs->dPops set to 1.0 by the caller first (dPops stays 1.0 until a column's first stat_equil). */
 int mali_iterate(const mali_model *m, const mali_buffers *bufs, int32_t col0, int32_t ncol, int32_t max_iter,
                  double tolJ, double tolPops, void *stream);
@@ -263,6 +265,8 @@ int mali_iterate(const mali_model *m, const mali_buffers *bufs, int32_t col0, in
 int mali_profile_begin(const mali_model *m, int32_t max_launches);
 int mali_profile_end(const mali_model *m, double *fs_ms_total, int32_t *fs_launches);
 long long mali_launch_count(const mali_model *m);
+/* iterations of mali_iterate that were replayed from a captured CUDA graph since the model was created */
+long long mali_graph_iterations(const mali_model *m);
 
 /* Where the profile of line t lives inside a column's device table (read-back of ComputationalTransition.phi / wphi,
  * rh_method.py:224,235): the line spans *ntile wavelength tiles starting at tile *tile0 (tile = lambda_per_warp

@@ -56,7 +56,7 @@ EXPORTS = ['mali_last_error', 'mali_device_count', 'mali_model_create', 'mali_mo
            'mali_piecewise_linear_1d', 'mali_uv', 'mali_exp_hook', 'mali_div_hook', 'mali_profile_begin',
            'mali_profile_end', 'mali_launch_count', 'mali_fp64_peak', 'mali_line_layout', 'mali_model_set_arith', 'mali_model_get_arith',
            'mali_upload_columns_atmos', 'mali_model_set_atoms', 'mali_setup_columns',
-           'mali_upload_columns_thermo', 'mali_model_set_eos', 'mali_background']
+           'mali_upload_columns_thermo', 'mali_model_set_eos', 'mali_background', 'mali_graph_iterations']
 
 ARITH_EXACT, ARITH_CONTRACTED = 0, 1
 
@@ -105,6 +105,8 @@ def load(path=None):
     L.mali_model_get_arith.argtypes = [C.c_void_p]
     L.mali_line_layout.argtypes = [C.c_void_p, C.c_int32, _ip, _ip, _ip, C.c_int32, C.POINTER(C.c_int64)]
     L.mali_launch_count.restype = C.c_longlong
+    L.mali_graph_iterations.argtypes = [C.c_void_p]
+    L.mali_graph_iterations.restype = C.c_longlong
     L.mali_div_hook.argtypes = [C.c_int32] + [C.c_void_p] * 5
     L.mali_fp64_peak.argtypes = [C.c_int32, C.c_void_p, C.POINTER(C.c_double)]
     L.mali_exp_hook.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]

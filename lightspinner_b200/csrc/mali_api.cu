@@ -207,6 +207,9 @@ struct mali_model {
     // the three register-class kernels of one formal solution are independent: they run on the caller's stream
     // and two side streams (fork / join by events), so that one kernel's tail overlaps the others
     cudaStream_t sideStream[2] = {nullptr, nullptr};
+    cudaStream_t iterStream = nullptr;      // mali_iterate's own stream when the caller is on the legacy default stream
+    cudaEvent_t iterFork = nullptr, iterJoin = nullptr;
+    mutable long long graphLaunches = 0;    // iterations replayed from a captured graph (mali_model_info-style diagnostics)
     cudaEvent_t forkEvent = nullptr, joinEvent[2] = {nullptr, nullptr};
     mutable int profUsed = 0;
     mutable bool profOn = false;
@@ -678,6 +681,9 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
             if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->joinEvent[q], cudaEventDisableTiming);
         }
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->forkEvent, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->iterStream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->iterFork, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->iterJoin, cudaEventDisableTiming);
         if (e != cudaSuccess) {
             mali_model_destroy(m);
             return fail((int)e, "mali_model_create: %s", cudaGetErrorString(e));
@@ -708,6 +714,9 @@ void mali_model_destroy(mali_model *m)
         if (m->joinEvent[q]) cudaEventDestroy(m->joinEvent[q]);
     }
     if (m->forkEvent) cudaEventDestroy(m->forkEvent);
+    if (m->iterStream) cudaStreamDestroy(m->iterStream);
+    if (m->iterFork) cudaEventDestroy(m->iterFork);
+    if (m->iterJoin) cudaEventDestroy(m->iterJoin);
     delete m;
 }
 
@@ -1239,8 +1248,18 @@ int mali_iterate(const mali_model *m, const mali_buffers *b, int32_t col0, int32
     if (!b->colconst || !b->pops || !b->J || !b->I || !b->Gamma || !b->scratch || !b->dJ || !b->dPops || !b->status ||
         !b->iter || !b->done)
         return fail(MALI_EINVAL, "mali_iterate: null buffer");
-    cudaStream_t st = (cudaStream_t)stream;
+    cudaStream_t caller = (cudaStream_t)stream;
     if (max_iter < 1) return MALI_OK;
+    // The legacy default stream cannot be captured into a graph: when the caller works on it (PyTorch's default), the
+    // loop runs on a library-owned stream that is forked from and joined back into the caller's stream with events,
+    // so the call stays stream-ordered.
+    cudaStream_t st = caller;
+    const bool detour = (caller == nullptr || caller == cudaStreamLegacy) && m->iterStream != nullptr;
+    if (detour) {
+        st = m->iterStream;
+        CU(cudaEventRecord(m->iterFork, caller));
+        CU(cudaStreamWaitEvent(st, m->iterFork, 0));
+    }
     IterCtl ctl{};
     ctl.on = 1;
     ctl.tolJ = tolJ;
@@ -1311,6 +1330,7 @@ int mali_iterate(const mali_model *m, const mali_buffers *b, int32_t col0, int32
                 if (g.exec == exec) per = g.kernels;
             for (int it = 0; it < max_iter; ++it) CU(cudaGraphLaunch(exec, st));
             m->launches += per * max_iter;
+            m->graphLaunches += max_iter;
             done_by_graph = true;
         }
     }
@@ -1319,6 +1339,10 @@ int mali_iterate(const mali_model *m, const mali_buffers *b, int32_t col0, int32
             if (int r = one_iteration()) return r;
     iterate_close_kernel<<<(ncol + 127) / 128, 128, 0, st>>>(b->dJ, ctl, col0, ncol);
     m->launches += 1;
+    if (detour) {
+        CU(cudaEventRecord(m->iterJoin, st));
+        CU(cudaStreamWaitEvent(caller, m->iterJoin, 0));
+    }
     CU(cudaGetLastError());
     return MALI_OK;
 }
@@ -1368,6 +1392,7 @@ int mali_profile_end(const mali_model *m, double *fs_ms_total, int32_t *fs_launc
 }
 
 long long mali_launch_count(const mali_model *m) { return m ? m->launches : 0; }
+long long mali_graph_iterations(const mali_model *m) { return m ? m->graphLaunches : 0; }
 
 int mali_line_layout(const mali_model *m, int32_t t, int32_t *tile0, int32_t *ntile, int32_t *entries, int32_t cap,
                      int64_t *off_tab)

@@ -43,6 +43,13 @@ class MaliEngine:
         self._check(self.lib.mali_model_create(C.byref(desc), self.device.index, C.byref(self._handle)))
         if arith is not None:
             self.set_arith(arith)
+        info = self.model_info()
+        if info['generic_tiles'] > 0 and lib_path is None:
+            import warnings
+            warnings.warn('%d of %d wavelength tiles of this model have no structure-specialised kernel instance and run '
+                          'on the generic kernel (~4x slower): pass specialize=True to build a model-specific library, '
+                          'or add the model to tools/gen_spec_instances.py' % (info['generic_tiles'], info['ntile']),
+                          RuntimeWarning, stacklevel=2)
         self.lay = _capi.Layout()
         self._check(self.lib.mali_model_layout(self._handle, C.byref(self.lay)))
         L = self.lay
@@ -355,6 +362,10 @@ class MaliEngine:
 
     def launch_count(self):
         return int(self.lib.mali_launch_count(self._handle))
+
+    def graph_iterations(self):
+        """Iterations of iterate_async that were replayed from a captured CUDA graph."""
+        return int(self.lib.mali_graph_iterations(self._handle))
 
     # ------------------------------------------------------------------ results, reference shapes
     def J(self, col=0):

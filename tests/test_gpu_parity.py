@@ -253,6 +253,7 @@ def test_device_loop_matches_host_loop(eng_mod, arith):
     eng.iterate_async(60)
     iters = eng.t_iter.cpu().numpy()
     done = eng.t_done.cpu().numpy()
+    assert eng.graph_iterations() == 60          # the loop was replayed from its captured CUDA graph
     assert list(iters) == [int(g[1]['niter']) for g in gold]
     assert (done == 1).all()
     for c, (p, r) in enumerate(gold):

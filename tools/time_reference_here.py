@@ -40,7 +40,32 @@ def main():
                              'formal_sol_gamma_matrices_seconds_median_of_3': fs, 'stat_equil_seconds': t_se,
                              'updates_per_s_one_core': units / (fs + t_se)})
         print(out['cases'][-1])
-    json.dump(out, open(os.path.join(ROOT, 'profiles', 'r01_reference_numpy_timing.json'), 'w'), indent=1)
+    # a multiprocessing.Pool over columns -- every worker builds its own reference Context (CaII+H /
+    # FALC) and times formal_sol_gamma_matrices + stat_equil calls; aggregate updates/s over all cores of this container
+    import multiprocessing as mp
+    ncore = os.cpu_count() or 1
+    with mp.get_context('fork').Pool(ncore) as pool:
+        res = pool.map(_pool_worker, range(ncore))
+    units = res[0][0]
+    agg = sum(u * n / t for u, n, t in res)
+    out['pool'] = {'processes': ncore, 'calls_per_process': res[0][1], 'updates_per_s_aggregate': agg,
+                   'updates_per_s_per_core': agg / ncore, 'case': 'C2 CaII+H/FALC, one Context per process'}
+    print(out['pool'])
+    json.dump(out, open(os.path.join(ROOT, 'profiles', 'r02_reference_numpy_timing.json'), 'w'), indent=1)
+
+
+def _pool_worker(i):
+    atmos, spect, eqPops, bg = rh.build_falc_setup(active=('Ca', 'H'), nrays=5)
+    ctx = rh.load_reference()['rh_method'].Context(atmos, spect, eqPops, bg)
+    units = ctx.I.shape[0] * ctx.I.shape[1] * ctx.J.shape[1]
+    for _ in range(4):                       # numba compile + the J-only iterations
+        ctx.formal_sol_gamma_matrices()
+    ncall = 3
+    t0 = time.perf_counter()
+    for _ in range(ncall):
+        ctx.formal_sol_gamma_matrices()
+        ctx.stat_equil()
+    return units, ncall, time.perf_counter() - t0
 
 
 if __name__ == '__main__':
