@@ -4,6 +4,7 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--ncol C] [--iters I]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
+    python bench.py --workload lambda_shard [--gpus N]        # BASELINE config 5 experiment (one column, wavelength-sharded)
 
 Workload (config.workload): BASELINE config 4's per-GPU share -- a synthetic 1.5D batch of `ncol` perturbed FALC
 columns per GPU (default 1024; 8 GPUs = the config's 8192), CaII + H 6-level both active (Nspect 777, 5 rays, 82 depths,
@@ -20,10 +21,19 @@ j_finish_kernel) + statistical equilibrium (stat_equil_kernel).
           the device, forms the Voigt line profiles there (upload_device_phi: the host hands over the damping
           parameters, Doppler widths and vlos the reference's compute_phi consumes), iterates, and reads I, n, dJ,
           dPops back to the host.  e2e_host_phi: the variant that ships host-computed profiles (2.5x the bytes).
-  roofline : fs_gamma_kernel only: algorithmic bytes per launch (SURVEY.md 8d formula) / its mean device time
-             measured with CUDA events around every launch inside the timed region, vs MEASURED_PEAKS.json hbm_gbs.
+  roofline : the fs_gamma_kernel_m launches only: algorithmic bytes per launch (SURVEY.md 8d formula) / their mean
+             device time measured with CUDA events around every launch inside the timed region, vs
+             MEASURED_PEAKS.json hbm_gbs; roofline.fp64: algorithmic flops vs the fp64 peak measured live.
+  arith / exact_arith : the headline runs the library's default arithmetic (contracted); the same resident solve
+             with the reference's rounding (MALI_ARITH_EXACT) is reported beside it.
   cpu_baseline : the oracle's C restatement (OpenMP over columns, all host cores) on a bounded sample of the same
-                 columns and the same `iters` (rank 0, N = 1 only).  --impl reference prints that arm alone.
+                 columns and the same `iters` (rank 0, N = 1 only); reference_numpy: the unmodified reference's own
+                 numpy path as timed in the build container (it does not exist on the GPU box).  --impl reference
+                 prints that arm alone.
+Side sections (N = 1 unless noted): single_column (configs 1/2), to_convergence (the batch run to the reference's
+tolerances), response_function (config 3 from host tables), response_function_from_thermodynamic_state and
+config4_from_thermodynamic_state (SURVEY.md 8f ranks 1-3 on the device: columns given as cmass, T, ne, nHTot, vturb,
+vlos; config 4 by the reference's own jitter recipe with columns 0 and 1 checked against the reference fixtures).
 """
 import argparse
 import json
