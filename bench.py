@@ -267,6 +267,7 @@ def main():
     ap.add_argument('--iters', type=int, default=16, help='MALI iterations per solve (= per step)')
     ap.add_argument('--fixture', default='c2_falc_cah')
     ap.add_argument('--chunk', type=int, default=512, help='columns per upload chunk in the e2e path')
+    ap.add_argument('--e2e-steps', type=int, default=0, help='timed steps of the e2e paths (default: min(steps, 3))')
     ap.add_argument('--first-chunk', type=int, default=0,
                     help='e2e path: size of a smaller first chunk (shortens the exposed first host->device copy)')
     ap.add_argument('--workload', default='columns', choices=['columns', 'lambda_shard'],
@@ -478,7 +479,7 @@ def main():
         solve_from_host()
         barrier()
         l0 = eng.launch_count()
-        k_e2e = max(1, min(args.steps, 3))
+        k_e2e = args.e2e_steps if args.e2e_steps > 0 else max(1, min(args.steps, 3))
         e0.record()
         for _ in range(k_e2e):
             solve_from_host()
@@ -556,10 +557,22 @@ def main():
             e1.record()
             barrier()
             ms_d = max_over_ranks(e0.elapsed_time(e1))
+            # diagnostic: the copy stream's work of one step on its own (H2D + re-layout + line profiles, no solve)
+            e0.record()
+            for ci, (c0, nc) in enumerate(sched):
+                dev_aux[ci & 1][:nc].copy_(host_aux[c0:c0 + nc], non_blocking=True)
+                aD, vB, vL = dev_split[ci & 1]
+                aD[:nc].copy_(dev_aux[ci & 1][:nc, :nT])
+                vB[:nc].copy_(dev_aux[ci & 1][:nc, nT:nT + nA])
+                vL[:nc].copy_(dev_aux[ci & 1][:nc, nT + nA:])
+                eng.upload_packed_device_phi(host_pre[c0 * hpp:(c0 + nc) * hpp], aD, vB, vL, c0, nc, staging=staging[ci & 1])
+            e1.record()
+            barrier()
+            ms_up = e0.elapsed_time(e1)
             e2e_dev = {'value': e_units / (ms_d * 1e-3), 'unit': UNIT,
                        'h2d_bytes_per_step': world * ncol * (hpp + (nT + nA + 1) * N) * 8,
                        'd2h_bytes_per_step': e2e['d2h_bytes_per_step'], 'steps': k_e2e, 'ms_per_step': ms_d / k_e2e,
-                       'gpu_launches': eng.launch_count() - l0,
+                       'gpu_launches': eng.launch_count() - l0, 'upload_only_ms_per_step': ms_up,
                        'finite': bool(np.isfinite(out_I.numpy()).all() and np.isfinite(out_n.numpy()).all()),
                        'pipeline': e2e['pipeline'] + '; line profiles computed on the device (mali_compute_phi) '
                                    'from aDamp / vBroad / vlos'}
@@ -837,11 +850,14 @@ def main():
             e5 = MaliEngine(base, n4, device=local, max_upload_chunk=256)
             e5.set_eos(EosTables.from_arrays(zeos))
             e5.set_atoms(AtomTables.from_arrays([dict(atoms4[nm]) for nm in names4]))
-            barrier()
-            t0 = time.perf_counter()
-            e5.upload_thermo(probs)
-            torch.cuda.synchronize(dev)
-            t_setup = max_over_ranks(time.perf_counter() - t0)
+            t_setups = []
+            for rep in range(2):      # the first call also allocates the engine's staging / pinned buffers
+                barrier()
+                t0 = time.perf_counter()
+                e5.upload_thermo(probs)
+                torch.cuda.synchronize(dev)
+                t_setups.append(max_over_ranks(time.perf_counter() - t0))
+            t_setup = min(t_setups)
             e5.reset_iteration_state()
             barrier()
             t0 = time.perf_counter()
@@ -865,7 +881,8 @@ def main():
                     ok = ok and int(its5[c]) == int(r5['niter']) and eI < 1e-10 and en < 1e-10
             c4 = {'config': 'BASELINE config 4 by its own recipe: %d columns per GPU from (cmass, T, ne, nHTot, vturb, vlos), '
                             'device-side set-up, to convergence' % n4,
-                  'columns_per_gpu': n4, 'setup_seconds': t_setup, 'seconds_to_converge': t_solve,
+                  'columns_per_gpu': n4, 'setup_seconds': t_setup, 'setup_seconds_all_reps': t_setups,
+                  'seconds_to_converge': t_solve,
                   'iterations_min': int(its5.min()), 'iterations_max': int(its5.max()), 'iterations_mean': float(its5.mean()),
                   'updates_per_s': float(its5.sum()) * units_per_col_iter * world / t_solve,
                   'reference_columns': detail, 'matches_reference': bool(ok) if detail else None}

@@ -195,6 +195,8 @@ struct mali_model {
     GijCont *d_gijCont = nullptr;
     GijTile *d_gijTiles = nullptr;
     int nGijCont = 0;
+    int32_t *d_groupTiles = nullptr;    // tiles with continuum groups (cont_group_kernel)
+    int nGroupTiles = 0;
     std::vector<std::vector<PhiTile>> phiTilesHost;   // per transition: where its profile entries live (mali_line_layout)
     std::vector<int32_t> phiTile0Host;
     bool haveLambda0 = false;
@@ -401,7 +403,21 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
         // record = [Vij rows dir 0 | fields | Vij rows dir 1]; fields = J-dagger (written by j_finish_kernel; padded to
         // whole 32-byte sectors), bg chi / eta / sca, one per-wavelength field per slot -- padded to whole sectors
         const int jw = (Lw + 3) & ~3;
-        const int sf = (int)align_up(jw + (3 + td.nslot) * Lw, 4);
+        // continuum groups of the tile (bound-free transitions sharing their upper level, mali_fs_spec.cuh): one more
+        // field each, after the slots' fields
+        int ng = 0;
+        for (int q = 0; q < td.nslot; ++q) {
+            const SlotDesc &sq = m->slots[td.slot0 + q];
+            if (sq.isLine) continue;
+            bool first = true;
+            for (int u = 0; u < q; ++u) {
+                const SlotDesc &su = m->slots[td.slot0 + u];
+                if (!su.isLine && su.lsJ == sq.lsJ) first = false;
+            }
+            if (first) ++ng;
+        }
+        td.ngroup = ng;
+        const int sf = (int)align_up(jw + (3 + td.nslot + ng) * Lw, 4);
         pt.recSize = 2 * vb + sf;
         tileJ.push_back(TileJ{(int32_t)rowOff + vb, pt.recSize});
         pt.la0 = la0;
@@ -570,7 +586,7 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
         const PackTile &pt = ptiles[ti];
         if (pt.nslot > kSpecMaxSlots) continue;
         int &sm = m->smemClass[spec_class(pt.nslot)];
-        sm = std::max(sm, fs_smem_bytes(pt.vb / kVRow, Lw, pt.nslot, m->popsW));
+        sm = std::max(sm, fs_smem_bytes(pt.vb / kVRow, Lw, pt.nslot, m->tiles[ti].ngroup, m->popsW));
     }
 
     // ---- small copies of the upload path
@@ -646,6 +662,7 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
                 gc.Nblue = tr[4];
                 gc.Nlam = tr[5];
                 gc.tile0 = gijTile0[t];
+                gc.toff = m->toff[t];
                 gc.tab0 = (int32_t)gts.size();
                 conts.push_back(gc);
                 gts.insert(gts.end(), gijT[t].begin(), gijT[t].end());
@@ -667,6 +684,13 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
         up(to_device(wm, &m->d_wmu));
     }
     up(to_device(m->genericTiles, &m->d_genericTiles));
+    {
+        std::vector<int32_t> gt;
+        for (int ti = 0; ti < m->ntile; ++ti)
+            if (m->tiles[ti].ngroup > 0) gt.push_back(ti);
+        m->nGroupTiles = (int)gt.size();
+        up(to_device(gt, &m->d_groupTiles));
+    }
     up(to_device(m->cjobs, &m->d_cjobs));
     up(to_device(pchunks, &m->d_pchunks));
     up(to_device(ptiles, &m->d_ptiles));
@@ -700,7 +724,7 @@ void mali_model_destroy(mali_model *m)
     void *ptrs[] = {m->d_tiles, m->d_slots, m->d_alpha, m->d_twohc, m->d_wlacont, m->d_wlambda, m->d_zmu, m->d_hw,
                     m->d_Nlevel, m->d_lvlOff, m->d_g2Off, m->d_trans, m->d_trPartOff, m->d_trPartRows,
                     m->d_genericTiles, m->d_cjobs, m->d_pchunks, m->d_ptiles, m->d_pslots, m->d_tileJ, m->d_phiTiles,
-                    m->d_phiLines, m->d_wavelength, m->d_muz, m->d_wmu, m->d_gijCont, m->d_gijTiles};
+                    m->d_phiLines, m->d_wavelength, m->d_muz, m->d_wmu, m->d_gijCont, m->d_gijTiles, m->d_groupTiles};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (void *p : m->atomDev)
@@ -757,6 +781,16 @@ static int check_range(const mali_model *m, const mali_buffers *b, int col0, int
     return MALI_OK;
 }
 
+// the continuum groups' U sums follow from the g_ij fields: called by whichever path has just (re)written those
+static void launch_cont_groups(const mali_model *m, const mali_buffers *b, int32_t col0, int32_t ncol, cudaStream_t st)
+{
+    if (m->nGroupTiles == 0) return;
+    dim3 grid((m->N * m->Lw + 127) / 128, m->nGroupTiles, ncol);
+    cont_group_kernel<<<grid, 128, 0, st>>>(m->d_tiles, m->d_slots, m->d_groupTiles, m->d_twohc, m->N, m->Nspect,
+                                            m->Lw, b->colconst, m->lay.colconst, m->off_tab, col0);
+    m->launches += 1;
+}
+
 // mode 0: whole host-pack blocks; 1: without the line profiles (mali_compute_phi forms them); 2: only the blocks'
 // first hp_C doubles -- heights, boundary Planck values, nTotal, background -- (mali_setup_columns forms C, the
 // continua's g_ij and the LTE populations as well); 3: only the first hp_bg_chi doubles (mali_background forms the
@@ -780,7 +814,7 @@ static int upload_columns(const mali_model *m, const mali_buffers *b, int32_t co
     }
     if (m->packChunks > 0) {
         dim3 grid(m->packChunks, (m->N + 31) / 32, ncol), block(32, 8);
-        pack_tiles_kernel<<<grid, block, 0, st>>>(m->d_pchunks, m->d_ptiles, m->d_pslots, m->d_wlambda, m->N, m->Nrays,
+        pack_tiles_kernel<<<grid, block, 0, st>>>(m->d_pchunks, m->d_ptiles, m->d_pslots, m->d_wlambda, m->d_alpha, m->N, m->Nrays,
                                                   m->Nspect, m->Lw, staging_dev, L.hostpack, L.hp_bg_chi, L.hp_bg_eta,
                                                   L.hp_bg_sca, b->colconst, L.colconst, m->off_tab, col0, mode);
     }
@@ -790,6 +824,7 @@ static int upload_columns(const mali_model *m, const mali_buffers *b, int32_t co
                                                L.colconst, b->pops, L.pops, b->J, L.J, col0, mode >= 2 ? 1 : 0);
     }
     m->launches += 2;
+    if (mode < 2) launch_cont_groups(m, b, col0, ncol, st);   // (otherwise mali_setup_columns forms the g_ij fields)
     CU(cudaGetLastError());
     return MALI_OK;
 }
@@ -958,9 +993,10 @@ int mali_setup_columns(const mali_model *m, const mali_buffers *b, int32_t col0,
     m->launches += 1;
     if (m->nGijCont > 0) {
         dim3 g2(8, m->nGijCont, ncol);
-        setup_gij_kernel<<<g2, 256, 0, st>>>(m->d_gijCont, m->d_gijTiles, m->d_wavelength, m->N, m->Lw, m->sumNlevel, T, nStar,
+        setup_gij_kernel<<<g2, 256, 0, st>>>(m->d_gijCont, m->d_gijTiles, m->d_wavelength, m->d_alpha, m->N, m->Lw, m->sumNlevel, T, nStar,
                                              b->colconst, m->lay.colconst, m->off_tab, col0);
         m->launches += 1;
+        launch_cont_groups(m, b, col0, ncol, st);
     }
     CU(cudaGetLastError());
     return MALI_OK;

@@ -94,21 +94,95 @@ __host__ __device__ constexpr int spec_line_index(const TileStruct &S, int tt)
     return n;
 }
 
-// ---- geometry of a record / a ring stage / the per-warp shared memory, shared by the kernel and the host's sizing
-__host__ __device__ constexpr int rec_jw(int lw) { return (lw + 3) / 4 * 4; }                          // J-dagger field
-__host__ __device__ constexpr int rec_fields(int lw, int ns) { return (rec_jw(lw) + (3 + ns) * lw + 3) / 4 * 4; }
-// doubles of one ring stage: two depth steps x (one direction's Vij rows + fields), two popsT rows
-__host__ __device__ constexpr int ring_stage_doubles(int nline, int lw, int ns, int pw)
+// ---- continuum groups: the bound-free transitions of a tile that share their upper level (all continua of one
+// ionisation stage end on the next stage's ground level).  For such a group the emissivity is n_j * sum_t Uji_t and
+// the upper level's U is sum_t Uji_t -- a sum that does not depend on the populations.  It is formed once per
+// (wavelength, depth) at upload (cont_group_kernel) and travels as one more field of the record, so that the
+// contracted-arithmetic kernels spend 3 instead of 12 operations per bound-free transition on the opacity stage.
+// A group is identified by its first slot; groups are numbered in slot order.
+__host__ __device__ constexpr int spec_group_first(const TileStruct &S, int tt)
 {
-    return 2 * (nline * kVRow + rec_fields(lw, ns)) + 2 * pw;
+    for (int u = 0; u < tt; ++u)
+        if (!S.kind[u] && S.lvJ[u] == S.lvJ[tt]) return u;
+    return tt;
+}
+__host__ __device__ constexpr int spec_group_last(const TileStruct &S, int tt)
+{
+    int r = tt;
+    for (int u = tt + 1; u < S.nslot; ++u)
+        if (!S.kind[u] && S.lvJ[u] == S.lvJ[tt]) r = u;
+    return r;
+}
+__host__ __device__ constexpr int spec_group_index(const TileStruct &S, int tt)
+{
+    const int f = spec_group_first(S, tt);
+    int n = 0;
+    for (int u = 0; u < f; ++u)
+        if (!S.kind[u] && spec_group_first(S, u) == u) ++n;
+    return n;
+}
+__host__ __device__ constexpr int spec_ngroup(const TileStruct &S)
+{
+    int n = 0;
+    for (int u = 0; u < S.nslot; ++u)
+        if (!S.kind[u] && spec_group_first(S, u) == u) ++n;
+    return n;
+}
+// The contracted opacity stage, planned at compile time (evaluated by the front end: one constexpr object per
+// instance, read with unrolled indices inside the depth loop).  Events, in slot order: a line touches chi of both its
+// levels, U of its upper level and its atom's emissivity; a continuum touches chi of its lower level; the LAST
+// continuum of a group then adds the group's sums to chi / U of the upper level and to the atom's emissivity.  The
+// flags say which of these writes is the first one of its accumulator (a plain store instead of an add).
+struct FastPlan {
+    bool firstI[kSpecMaxSlots], firstJ[kSpecMaxSlots], firstU[kSpecMaxSlots], firstA[kSpecMaxSlots];   // slot events
+    bool gOpen[kSpecMaxSlots], gClose[kSpecMaxSlots];     // continuum: first / last slot of its group
+    bool gFirstJ[kSpecMaxSlots], gFirstU[kSpecMaxSlots], gFirstA[kSpecMaxSlots];                      // group events
+    int grp[kSpecMaxSlots];                               // continuum: index of its group
+};
+__host__ __device__ constexpr FastPlan make_fast_plan(const TileStruct &S)
+{
+    FastPlan P{};
+    bool chiT[2 * kSpecMaxSlots] = {}, UT[2 * kSpecMaxSlots] = {}, atomT[8] = {};
+    for (int tt = 0; tt < S.nslot; ++tt) {
+        const int li = S.lvI[tt], lj = S.lvJ[tt], a = S.atom[tt];
+        P.firstI[tt] = !chiT[li];
+        chiT[li] = true;
+        if (S.kind[tt]) {
+            P.firstJ[tt] = !chiT[lj];
+            P.firstU[tt] = !UT[lj];
+            P.firstA[tt] = !atomT[a];
+            chiT[lj] = UT[lj] = atomT[a] = true;
+        } else {
+            P.grp[tt] = spec_group_index(S, tt);
+            P.gOpen[tt] = spec_group_first(S, tt) == tt;
+            P.gClose[tt] = spec_group_last(S, tt) == tt;
+            if (P.gClose[tt]) {
+                P.gFirstJ[tt] = !chiT[lj];
+                P.gFirstU[tt] = !UT[lj];
+                P.gFirstA[tt] = !atomT[a];
+                chiT[lj] = UT[lj] = atomT[a] = true;
+            }
+        }
+    }
+    return P;
+}
+
+// ---- geometry of a record / a ring stage / the per-warp shared memory, shared by the kernel and the host's sizing
+// (ns: transitions of the tile, ng: its continuum groups)
+__host__ __device__ constexpr int rec_jw(int lw) { return (lw + 3) / 4 * 4; }                          // J-dagger field
+__host__ __device__ constexpr int rec_fields(int lw, int ns, int ng) { return (rec_jw(lw) + (3 + ns + ng) * lw + 3) / 4 * 4; }
+// doubles of one ring stage: two depth steps x (one direction's Vij rows + fields), two popsT rows
+__host__ __device__ constexpr int ring_stage_doubles(int nline, int lw, int ns, int ng, int pw)
+{
+    return 2 * (nline * kVRow + rec_fields(lw, ns, ng)) + 2 * pw;
 }
 // lanes that end up sharing one Gamma value after the reduce-scatter: the largest power of two G with M * G <= 32
 __host__ __device__ constexpr int red_group(int m) { return m <= 2 ? 16 : (m <= 4 ? 8 : (m <= 8 ? 4 : 2)); }
-constexpr int kRedRow = 34;   // doubles per row of the reduce scratch (see reduce_store)
+constexpr int kRedRow = 36;   // doubles per row of the reduce scratch (see reduce_store)
 // bytes of shared memory of one warp: ring | reduce scratch | ring barriers | exp table
-__host__ __device__ constexpr int fs_smem_bytes(int nline, int lw, int ns, int pw)
+__host__ __device__ constexpr int fs_smem_bytes(int nline, int lw, int ns, int ng, int pw)
 {
-    return (kRingStages * ring_stage_doubles(nline, lw, ns, pw) + (ns > 0 ? 2 * ns * kRedRow : 0)) * 8 +
+    return (kRingStages * ring_stage_doubles(nline, lw, ns, ng, pw) + (ns > 0 ? 2 * ns * kRedRow : 0)) * 8 +
            (kRingStages * 8 + 15) / 16 * 16 + 128 * 16;
 }
 
@@ -128,15 +202,16 @@ struct MegaParams {
 
 // Warp reduce-scatter through shared memory, split in two so that the second half can run one depth step later
 // (its latency then overlaps the next step's arithmetic): reduce_store puts the lane's M values into the per-warp
-// scratch -- M rows of kRedRow = 34 doubles, lane l of a row at l + (l >> 4) -- and reduce_load sums them: afterwards
+// scratch -- M rows of kRedRow = 36 doubles, lane l of a row at l + 2 (l >> 4) -- and reduce_load sums them: afterwards
 // the G = red_group(M) lanes e * G .. e * G + G - 1 hold the total over the 32 lanes of value e.  Fixed order ->
 // deterministic.  Bank-conflict free in both phases: a store instruction writes 16 consecutive doubles per half-warp;
-// in a load instruction the 16 lanes of a half-warp read row e (stride 34 = 2 mod 16 eight-byte banks) at
-// part * (32 / G) + (that >> 4) + i, and 2 e + (part-dependent offset) takes 16 distinct values mod 16.
+// the loads are 128-bit (a lane's segment starts on a 16-byte boundary: the pad after lane 15 is TWO doubles), served
+// a quarter-warp at a time, and the 8 lanes of a quarter -- rows e = stride 18 sixteen-byte banks = 2 mod 8, segment
+// starts {0, 4, 9, 13}, {0, 9} ... -- fall into 8 distinct banks.
 template <int M>
 __device__ __forceinline__ void reduce_store(const double (&v)[M], int lane, double *red)
 {
-    double *dst = red + lane + (lane >> 4);
+    double *dst = red + lane + 2 * (lane >> 4);
 #pragma unroll
     for (int q = 0; q < M; ++q) dst[q * kRedRow] = v[q];
 }
@@ -144,22 +219,20 @@ template <int M>
 __device__ __forceinline__ double reduce_load(int lane, const double *red)
 {
     constexpr int G = red_group(M);   // lanes that share one value after the reduction
-    constexpr int SEG = 32 / G;       // source lanes each of them sums
+    constexpr int SEG = 32 / G;       // source lanes each of them sums (2, 4, 8 or 16)
     int e = lane / G;
     const int part = lane % G;
     if (e > M - 1) e = M - 1;         // lanes beyond M * G idle (their result is not used)
     const int l0 = part * SEG;
-    const double *row = red + e * kRedRow + l0 + (l0 >> 4);   // SEG <= 16: a segment never straddles the pad
+    const double2 *row = reinterpret_cast<const double2 *>(red + e * kRedRow + l0 + 2 * (l0 >> 4));   // SEG <= 16: no straddling
     double acc = 0.0, acc1 = 0.0;   // two interleaved partial sums halve the dependent-add chain
 #pragma unroll
-    for (int i = 0; i < SEG; ++i) {
-        const double x = row[i];
-        if (i & 1)
-            acc1 = (i == 1) ? x : acc1 + x;
-        else
-            acc = (i == 0) ? x : acc + x;
+    for (int i = 0; i < SEG / 2; ++i) {
+        const double2 x = row[i];
+        acc = (i == 0) ? x.x : acc + x.x;
+        acc1 = (i == 0) ? x.y : acc1 + x.y;
     }
-    if (SEG > 1) acc = acc + acc1;
+    acc = acc + acc1;
 #pragma unroll
     for (int off = G / 2; off > 0; off >>= 1) acc = acc + __shfl_xor_sync(0xffffffffu, acc, off);
     return acc;
@@ -211,7 +284,10 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
     constexpr int NLINE = spec_line_index(S, S.nslot);
     constexpr int VB = NLINE * kVRow;                // one direction's Vij rows
     constexpr int JW = rec_jw(LW);                   // J-dagger field (whole sectors)
-    constexpr int SF = rec_fields(LW, NS);           // all per-wavelength fields
+    constexpr int NGR = spec_ngroup(S);              // continuum groups (their U sums follow the slot fields)
+    constexpr int NGA = NGR > 0 ? NGR : 1;
+    constexpr FastPlan PL = make_fast_plan(S);
+    constexpr int SF = rec_fields(LW, NS, NGR);      // all per-wavelength fields
     constexpr int REC = 2 * VB + SF;                 // record stride (one depth point)
     constexpr int ST1 = VB + SF;                     // what one depth step of this direction reads: one contiguous piece
     constexpr int VOFF = DIR ? SF : 0;               // ... inside which the Vij rows sit here
@@ -321,16 +397,19 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
     double ca[NSA], cb[NSA], cw[NSA];   // continuum slots: alpha, 2hc/lambda^3, wlamu
 #pragma unroll
     for (int tt = 0; tt < NS; ++tt) {
+        // The cross-section goes with the record field the lane reads (Vji = g_ij * alpha of wavelength la0 + lsC):
+        // an idle lane (ls >= Lw) thus repeats the tile's last wavelength -- a physical opacity -- with zero weights.
         const SlotR &s = T.s[tt];
-        const int lt = laC - s.Nblue;
-        const bool act = valid && lt >= 0 && lt < s.Nlam;
+        const int laD = T.la0 + lsC;
+        const int lt = laD - s.Nblue;
+        const bool act = laD < Nspect && lt >= 0 && lt < s.Nlam;
         ca[tt] = 0.0;
         cb[tt] = 0.0;
         cw[tt] = 0.0;
         if (!S.kind[tt] && act) {
             ca[tt] = __ldg(p.alpha + s.toff + lt);
             cb[tt] = __ldg(p.twohc + s.toff + lt);
-            cw[tt] = (__ldg(p.wlacont + s.toff + lt) * hw) * fourPi;
+            if (valid) cw[tt] = (__ldg(p.wlacont + s.toff + lt) * hw) * fourPi;
         }
     }
     // segmented sum of J over the mu lanes of a wavelength: lane mu adds the partial sum of lane mu + off when that
@@ -399,8 +478,8 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
                 const double ld = sv[ST1 + line_index(tt) * kVRow];
                 chiTot += A::nmad(nj, T.s[tt].cA * ld, ni * ld);
             } else {
-                const double ld = sf[ST1 + (3 + tt) * LW];
-                chiTot += A::nmad(nj, ld * ca[tt], ni * ca[tt]);
+                const double ld = sf[ST1 + (3 + tt) * LW];       // Vji = g_ij * alpha
+                chiTot += A::nmad(nj, ld, ni * ca[tt]);
             }
         }
         chiProbe = chiTot + sf[ST1];

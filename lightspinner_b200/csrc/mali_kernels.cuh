@@ -122,9 +122,8 @@ __global__ void __launch_bounds__(128) fs_gamma_kernel(const FsParams p)
                     Uji = sd.c1 * Vji;
                 } else {
                     const double a = act ? __ldg(p.alpha + sd.toff + ltC) : 0.0;
-                    const double g = act ? __ldg(rec + sd.fOff + lsC) : 0.0;
                     Vij = a;
-                    Vji = g * Vij;
+                    Vji = act ? __ldg(rec + sd.fOff + lsC) : 0.0;      // the record holds g_ij * alpha (rh_method.py:285)
                     Uji = __ldg(p.twohc + sd.toff + ltC) * Vji;
                 }
                 const double ni = npop[(size_t)sd.rowI * N + k], nj = npop[(size_t)sd.rowJ * N + k];
@@ -190,9 +189,8 @@ __global__ void __launch_bounds__(128) fs_gamma_kernel(const FsParams p)
                             wla = act ? __ldg(rec + sd.fOff + lsC) : 0.0;
                         } else {
                             const double a = act ? __ldg(p.alpha + sd.toff + ltC) : 0.0;
-                            const double g = act ? __ldg(rec + sd.fOff + lsC) : 0.0;
                             Vij = a;
-                            Vji = g * Vij;
+                            Vji = act ? __ldg(rec + sd.fOff + lsC) : 0.0;
                             Uji = __ldg(p.twohc + sd.toff + ltC) * Vji;
                             wla = act ? __ldg(p.wlacont + sd.toff + ltC) : 0.0;
                         }
@@ -407,7 +405,7 @@ __global__ void uv_hook_kernel(const FsParams p, int col, SlotDesc sd, int recOf
         uji = sd.c1 * vji;
     } else {
         vij = p.alpha[sd.toff + lt];
-        vji = rec[sd.fOff + ls] * vij;
+        vji = rec[sd.fOff + ls];            // g_ij * alpha, one IEEE multiply folded in at upload
         uji = p.twohc[sd.toff + lt] * vji;
     }
     Uji[k] = uji;
@@ -433,7 +431,7 @@ struct PackChunk {
 };
 
 __global__ void pack_tiles_kernel(const PackChunk *chunks, const PackTile *tiles, const PackSlot *slots,
-                                  const double *wlambda, int N, int Nrays, int Nspect, int Lw, const double *staging,
+                                  const double *wlambda, const double *alpha, int N, int Nrays, int Nspect, int Lw, const double *staging,
                                   int64_t hpStride, int64_t hpBgChi, int64_t hpBgEta, int64_t hpBgSca, double *colconst,
                                   int64_t colStride, int64_t offTab, int col0, int skipPhi)
 {
@@ -479,8 +477,8 @@ __global__ void pack_tiles_kernel(const PackChunk *chunks, const PackTile *tiles
                     if (la < Nspect && lt >= 0 && lt < ps.Nlam) {
                         if (ps.isLine) {  // wla = wlambda(lt) * wphi[k] / HC   (rh_method.py:451)
                             if (!skipPhi) v = wlambda[ps.toff + lt] * src[ps.wphiOff + k] / kHC;
-                        } else if (skipPhi < 2)     // (2: setup_gij_kernel forms the continua's g_ij on the device)
-                            v = src[ps.srcOff + (size_t)lt * N + k];
+                        } else if (skipPhi < 2)     // (2: setup_gij_kernel forms the continua's fields on the device)
+                            v = src[ps.srcOff + (size_t)lt * N + k] * alpha[ps.toff + lt];   // Vji = g_ij * alpha, rh_method.py:285
                     }
                 }
             }
@@ -675,15 +673,16 @@ __global__ void setup_levels_kernel(const AtomLevels A, int N, const double *T, 
     vBroad[((size_t)c * A.Natom + a) * N + k] = sqrt(A.vTherm[a] * t + vt * vt);
 }
 
-// g_ij of the continua (rh_method.py:453-454): nStar_i / nStar_j * exp(-(hc/k) / lambda / T), written into the slot
-// fields of the tile records.  One block row per (continuum, column); threads run over (wavelength, depth).
+// g_ij of the continua (rh_method.py:453-454): nStar_i / nStar_j * exp(-(hc/k) / lambda / T), written -- times the
+// cross-section alpha, i.e. as Vji of rh_method.py:285 -- into the slot fields of the tile records.  One block row per (continuum, column); threads run over (wavelength, depth).
 struct GijCont {
     int32_t rowI, rowJ, Nblue, Nlam, tile0, tab0;   // level rows in nStar; wavelength range; first tile; first GijTile
+    int32_t toff, pad;                               // the continuum's entries of the per-wavelength tables (alpha)
 };
 struct GijTile {
     int32_t f, stride;    // depth-0 offset of the continuum's field in that tile's records; record stride
 };
-__global__ void setup_gij_kernel(const GijCont *conts, const GijTile *gt, const double *wavelength, int N, int Lw,
+__global__ void setup_gij_kernel(const GijCont *conts, const GijTile *gt, const double *wavelength, const double *alpha, int N, int Lw,
                                  int sumNlevel, const double *T, const double *nStar, double *colconst, int64_t colStride,
                                  int64_t offTab, int col0)
 {
@@ -699,7 +698,44 @@ __global__ void setup_gij_kernel(const GijCont *conts, const GijTile *gt, const 
         const GijTile g = gt[ct.tab0 + ti - ct.tile0];
         const double v = ns[(size_t)ct.rowI * N + k] / ns[(size_t)ct.rowJ * N + k] *
                          exp(-hc_k / wavelength[la] / T[(size_t)c * N + k]);
-        tab[g.f + (size_t)k * g.stride + ls] = v;
+        tab[g.f + (size_t)k * g.stride + ls] = v * alpha[ct.toff + lt];     // the field holds Vji = g_ij * alpha (:285)
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------
+// The continuum groups' fields (mali_fs_spec.cuh, spec_group_*): for every group of bound-free transitions of a tile
+// that share their upper level, sum_t Uji_t(lambda, k) with Uji = 2hc/lambda^3 * Vji exactly as uv forms it
+// (rh_method.py:284-286; the slots' fields hold Vji = g_ij * alpha), summed in slot order -- the population-independent part of that level's U and of the group's
+// emissivity.  Runs whenever the g_ij fields of a column are (re)written; one thread per (depth, wavelength of the tile).
+__global__ void cont_group_kernel(const TileDesc *tiles, const SlotDesc *slots, const int32_t *groupTiles,
+                                  const double *twohc, int N, int Nspect, int Lw, double *colconst, int64_t colStride,
+                                  int64_t offTab, int col0)
+{
+    const TileDesc td = tiles[groupTiles[blockIdx.y]];
+    double *tab = colconst + (size_t)(col0 + blockIdx.z) * colStride + offTab + td.recOff;
+    const SlotDesc *sl = slots + td.slot0;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < N * Lw; idx += gridDim.x * blockDim.x) {
+        const int k = idx / Lw, ls = idx - k * Lw;
+        const int la = td.la0 + ls;
+        double *rec = tab + (size_t)k * td.stride;
+        int g = 0;
+        for (int q = 0; q < td.nslot; ++q) {
+            if (sl[q].isLine) continue;
+            bool first = true;
+            for (int u = 0; u < q; ++u)
+                if (!sl[u].isLine && sl[u].lsJ == sl[q].lsJ) first = false;
+            if (!first) continue;
+            double sum = 0.0;
+            for (int u = q; u < td.nslot; ++u) {
+                if (sl[u].isLine || sl[u].lsJ != sl[q].lsJ) continue;
+                const int lt = la - sl[u].Nblue;
+                if (la < Nspect && lt >= 0 && lt < sl[u].Nlam) {
+                    sum = sum + twohc[sl[u].toff + lt] * rec[sl[u].fOff + ls];
+                }
+            }
+            rec[td.bgOff + (3 + td.nslot + g) * Lw + ls] = sum;
+            ++g;
+        }
     }
 }
 

@@ -11,7 +11,9 @@
 //     [ fields: J-dagger[Lw rounded up to 4]: the mean intensity of the previous iteration, rewritten by
 //               j_finish_kernel (the only part of a record that changes between iterations; zero after upload)
 //               bg chi[Lw] | bg eta[Lw] | bg sca[Lw]
-//               per slot: wla[Lw] (lines, rh_method.py:451) or g_ij[Lw] (continua, :453-454)     (padded to 4 doubles) ]
+//               per slot: wla[Lw] (lines, rh_method.py:451) or Vji = g_ij * alpha [Lw] (continua, :453-454, :285)
+//               per continuum group (the tile's bound-free transitions with one upper level): sum_t Uji_t [Lw], formed
+//               from the g_ij fields by cont_group_kernel whenever those are (re)written       (padded to 4 doubles) ]
 //     [ Vij rows of direction 1 (up sweep) ]
 // The fields sit BETWEEN the two directions' rows, so what one sweep direction needs at a depth -- [rows 0 | fields]
 // or [fields | rows 1] -- is one contiguous piece: one TMA bulk copy per depth step, and a sweep walks its tile's
@@ -45,7 +47,7 @@ struct SlotDesc {
     int32_t lsI, lsJ;    // level-slot of the lower / upper level inside the tile
     int32_t toff;        // offset of this transition in the per-wavelength tables (alpha, twohc, wlacont)
     int32_t flags;       // bit 0 / 1: this slot is the first of its tile to touch level-slot lsI / lsJ
-    int32_t fOff;        // record offset of the slot's per-wavelength field: wla[Lw] (lines) or g_ij[Lw] (continua)
+    int32_t fOff;        // record offset of the slot's per-wavelength field: wla[Lw] (lines) or g_ij * alpha [Lw] (continua)
     int32_t vOff;        // lines: record offset of the direction-0 Vij row (direction 1: + TileDesc::vDir); else -1
     int32_t pad;
     double c0, c1, c2;   // lines: hc/4pi*Bij (folded into the Vij table at upload), Aji/Bji, Bji/Bij  (rh_method.py:279-281,450)
@@ -61,7 +63,8 @@ struct TileDesc {
     int32_t bgOff;     // record offset of bg chi[Lw] (eta, sca follow at +Lw, +2Lw)
     int32_t vDir;      // distance between the direction-0 and direction-1 Vij rows (line rows + fields)
     int32_t stride;    // record size = distance between the tile's records of consecutive depth points
-    int32_t pad0, pad1, pad2;
+    int32_t ngroup;    // continuum groups of the tile: their fields sum_t Uji_t [Lw] follow the slots' fields
+    int32_t pad1, pad2;
 };
 
 constexpr int kVRow = 32;  // doubles per Vij row of a record (Lw * Nrays <= 32 lanes, zero padded)

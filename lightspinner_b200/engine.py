@@ -102,10 +102,15 @@ class MaliEngine:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def _staging_bufs(self):
+    def _staging_bufs(self, per_column=None):
+        """Device staging of `chunk` host-pack blocks and a pinned host buffer of `chunk * per_column` doubles
+        (default: whole blocks).  The upload paths that send only a prefix of each block pin only that much:
+        page-locking gigabytes takes a good fraction of a second."""
         if self._staging is None:
             self._staging = torch.empty(self.chunk * self.lay.hostpack, dtype=torch.float64, device=self.device)
-            self._pinned = torch.empty(self.chunk * self.lay.hostpack, dtype=torch.float64, pin_memory=True)
+        need = self.chunk * int(self.lay.hostpack if per_column is None else per_column)
+        if self._pinned is None or self._pinned.numel() < need:
+            self._pinned = torch.empty(need, dtype=torch.float64, pin_memory=True)
         return self._staging, self._pinned
 
     def hostpack_size(self):
@@ -130,8 +135,8 @@ class MaliEngine:
         rh_method.py:198-243 -> mali_compute_phi) from each problem's damping parameters `aDamp` [Ntrans, Nspace],
         Doppler widths `vBroad` [Natom, Nspace] and `vlos` [Nspace]: only the blocks without phi / wphi (about 40 %
         of the bytes) cross PCIe.  Profiles agree with the reference's to ~1e-13 (the accuracy of scipy's wofz)."""
-        staging, pinned = self._staging_bufs()
         hpp = int(self.lay.hp_phi)
+        staging, pinned = self._staging_bufs(hpp)
         pin_np = pinned.numpy()
         N = self.mt.Nspace
         for c0 in range(0, len(problems), self.chunk):
@@ -164,8 +169,8 @@ class MaliEngine:
         lines' damping parameters aDamp; LTE populations, collisional rates, Doppler widths, the continua's g_ij
         (mali_setup_columns) and the Voigt profiles (mali_compute_phi) are computed on the GPU.  start_from_lte=False
         keeps the populations given in problem['n'] (a warm start, response_fn.py:33).  Needs set_atoms()."""
-        staging, pinned = self._staging_bufs()
         hpc = int(self.lay.hp_C)
+        staging, pinned = self._staging_bufs(hpc)
         pin_np = pinned.numpy()
         N = self.mt.Nspace
         self.nStar = getattr(self, 'nStar', None)
@@ -210,8 +215,8 @@ class MaliEngine:
         opacities (mali_background), LTE populations, collisional rates, Doppler widths, the continua's g_ij
         (mali_setup_columns) and the Voigt profiles (mali_compute_phi) are all formed on the GPU.
         Needs set_eos() and set_atoms()."""
-        staging, pinned = self._staging_bufs()
         hpb = int(self.lay.hp_bg_chi)
+        staging, pinned = self._staging_bufs(hpb)
         pin_np = pinned.numpy()
         N = self.mt.Nspace
         if getattr(self, 'nStar', None) is None:
@@ -251,7 +256,7 @@ class MaliEngine:
         """Asynchronous form of upload_device_phi: `host_prefix_pinned` holds [ncol][lay.hp_phi] doubles (pinned),
         aDamp / vBroad / vlos are device tensors [ncol][Ntrans|Natom|1][Nspace]."""
         if staging is None:
-            staging, _ = self._staging_bufs()
+            staging, _ = self._staging_bufs(0)
         if ncol * self.lay.hostpack > staging.numel():
             raise ValueError('staging buffer too small for %d columns' % ncol)
         with torch.cuda.device(self.device):
@@ -265,7 +270,7 @@ class MaliEngine:
     def upload_packed(self, host_pinned, col0, ncol, staging=None):
         """H2D copy of `ncol` host-pack blocks (a pinned torch tensor) + device re-layout; asynchronous."""
         if staging is None:
-            staging, _ = self._staging_bufs()
+            staging, _ = self._staging_bufs(0)
         if ncol * self.lay.hostpack > staging.numel():
             raise ValueError('staging buffer too small for %d columns' % ncol)
         with torch.cuda.device(self.device):
