@@ -270,6 +270,9 @@ def main():
     ap.add_argument('--e2e-steps', type=int, default=0, help='timed steps of the e2e paths (default: min(steps, 3))')
     ap.add_argument('--first-chunk', type=int, default=0,
                     help='e2e path: size of a smaller first chunk (shortens the exposed first host->device copy)')
+    ap.add_argument('--sched', default='',
+                    help='explicit e2e upload schedule: comma-separated chunk sizes (the last one repeats); overrides '
+                         '--chunk / --first-chunk')
     ap.add_argument('--workload', default='columns', choices=['columns', 'lambda_shard'],
                     help='columns: the headline column-sharded batch; lambda_shard: BASELINE config 5 experiment, one '
                          'stress column wavelength-sharded over the GPUs with a Gamma all-reduce per iteration')
@@ -327,18 +330,28 @@ def main():
     ncol, iters = args.ncol, args.iters
     N, S, R = int(base['Nspace']), int(base['Nspect']), int(base['Nrays'])
     units_per_col_iter = S * R * N
+    sched_sizes = [int(x) for x in args.sched.split(',') if x] if args.sched else None
+    if sched_sizes:
+        args.chunk = max(sched_sizes)
     eng = MaliEngine(base, ncol, device=local, max_upload_chunk=args.chunk)
     lay, mt = eng.lay, eng.mt
     hp = int(lay.hostpack)
     chunk = min(args.chunk, ncol)
     # e2e schedule: [(first column, count)]; an optional small first chunk, then `chunk`-sized ones
     sched, c0 = [], 0
-    if 0 < args.first_chunk < chunk and args.first_chunk < ncol:
+    if sched_sizes:        # growing chunks: only the first (small) upload is exposed, every later one hides behind a solve
+        for i, n in enumerate(sched_sizes[:-1]):
+            if c0 + n < ncol:
+                sched.append((c0, n))
+                c0 += n
+        chunk = min(sched_sizes[-1], ncol)
+    elif 0 < args.first_chunk < chunk and args.first_chunk < ncol:
         sched.append((0, args.first_chunk))
         c0 = args.first_chunk
     while c0 < ncol:
         sched.append((c0, min(chunk, ncol - c0)))
         c0 += chunk
+    chunk = max(n for _, n in sched)     # what the staging buffers are sized by
     col_global0 = rank * ncol        # this rank's slice of the global batch
 
     # ---- build the resident batch: base host pack -> device, jitter on the device, re-layout
@@ -429,7 +442,12 @@ def main():
                 'frac': achieved / peak, 'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': alg_bytes, 'mean_launch_ms': fs_ms_mean, 'launches_timed': fs_n,
                 'share_of_step': fs_ms / ms if ms > 0 else None, 'arith': arith_default,
-                'note': 'fp64 CUDA-core work binds before HBM on this path (SURVEY.md 7.3-2); see DESIGN.md'}
+                'binding_unit': 'L1 data pipe (shared-memory / shuffle wavefronts): 91-93 % of peak in the two large '
+                                'kernel classes, dispatch ports 85-90 % (ncu --set full, profiles/r02_v18_fs_kernel_ncu_summary.txt; '
+                                'from that capture, not measured in this run)',
+                'note': 'neither HBM nor the fp64 pipe binds this path: the per-depth warp-wide Gamma sums saturate the '
+                        "SM's L1 data pipe first (DESIGN.md section 4); fp64 CUDA-core work would bind next, well "
+                        'before HBM (SURVEY.md 7.3-2)'}
     try:    # the roof that actually binds: unfused fp64 on the CUDA cores, peak measured live
         from lightspinner_b200.engine import fp64_peak
         pk = fp64_peak(local)

@@ -437,7 +437,15 @@ __device__ __forceinline__ void fs_body(const FsCommon &p, const TileR<NSP> &T, 
             if (writer) __stcg(gp, tot);
         }
         double sum = xP;
-        if constexpr (NR <= 6) {   // few angles: pull every other lane's term (no masking; only the leader's sum is used)
+        if constexpr (FAST && NR >= 4 && NR <= 6) {
+            // contracted mode: a fixed tree over the wavelength's lanes, (x0 + x1) + (x2 + x3) [+ x4 | + (x4 + x5)] -- three
+            // shuffle rounds instead of NR - 1 (no masking: only the leader's sum is used, and its sources are its own
+            // wavelength's lanes)
+            const double s1 = xP + __shfl_down_sync(0xffffffffu, xP, 1);
+            sum = s1 + __shfl_down_sync(0xffffffffu, s1, 2);
+            if constexpr (NR == 5) sum += __shfl_down_sync(0xffffffffu, xP, 4);
+            if constexpr (NR == 6) sum += __shfl_down_sync(0xffffffffu, s1, 4);
+        } else if constexpr (NR <= 6) {   // few angles: pull every other lane's term (no masking; only the leader's sum is used)
 #pragma unroll
             for (int m = 1; m < NR; ++m) sum += __shfl_down_sync(0xffffffffu, xP, m);
         } else {                   // many angles: a masked tree

@@ -524,6 +524,7 @@ __global__ void compute_phi_kernel(const PhiLine *lines, const PhiTile *ptile, c
     const bool lane_on = ls < Lw;
     const double sqrtPi = sqrt(kPi);
     const double rnorm = 1.0 / (sqrtPi * vb);
+    const VoigtPre vp = voigt_pre(ad);             // the damping-only part of the Voigt evaluation, once per (line, depth)
     const double vd = lane_on ? muz[mu] * vl / vb : 0.0;                                        // :223
     const double wm = lane_on ? wmu[mu] : 0.0;
     double wPhi = 0.0;
@@ -533,8 +534,8 @@ __global__ void compute_phi_kernel(const PhiLine *lines, const PhiTile *ptile, c
         double p0 = 0.0, p1 = 0.0;
         if (on) {
             const double v = (wavelength[la] - ln.lambda0) * kCLight / (vb * ln.lambda0);      // :225
-            p0 = voigt_H(ad, v - vd) * rnorm;                                                   // :229-231
-            p1 = voigt_H(ad, v + vd) * rnorm;
+            p0 = voigt_H_pre(vp, v - vd) * rnorm;                                               // :229-231
+            p1 = voigt_H_pre(vp, v + vd) * rnorm;
             wPhi += (p0 + p1) * ((wlambda[ln.toff + lt] * 0.5) * wm);                           // :227, :233
         }
         const PhiTile pt = ptile[ln.tab0 + j];

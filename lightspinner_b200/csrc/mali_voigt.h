@@ -58,10 +58,35 @@ MALI_VOIGT_HD double voigt_rcp(double d)
 #endif
 }
 
-MALI_VOIGT_HD double voigt_H(double a, double v)
+// What depends on the damping parameter alone (one value per line and depth point: the callers evaluate H for many
+// frequencies with the same a): a^2, whether the pole's residue is needed at all, and exp(2 pi a / h).
+struct VoigtPre {
+    double y, y2, E;
+    bool res;
+};
+MALI_VOIGT_HD VoigtPre voigt_pre(double a)
 {
     constexpr double h = 0.5, pi = 3.141592653589793;
-    const double x = fabs(v), y = a, y2 = y * y;
+    VoigtPre P;
+    P.y = a;
+    P.y2 = a * a;
+    P.res = a < pi / h;
+    P.E = P.res ? exp(2.0 * pi * a / h) : 0.0;
+    return P;
+}
+
+// 1 / A + 1 / B with one reciprocal: (A + B) / (A B).  A, B = (v -+ t)^2 + a^2 lie in [1/64, 1e3] on the trapezoid
+// branch (the grid is chosen so that no node is closer than h / 4 to v), so the product cannot leave the normal range.
+MALI_VOIGT_HD double voigt_pair(double dm, double dp, double y2)
+{
+    const double A = fma(dm, dm, y2), B = fma(dp, dp, y2);
+    return (A + B) * voigt_rcp(A * B);
+}
+
+MALI_VOIGT_HD double voigt_H_pre(const VoigtPre &P, double v)
+{
+    constexpr double h = 0.5, pi = 3.141592653589793;
+    const double x = fabs(v), y = P.y, y2 = P.y2;
     if (fma(x, x, y2) > 256.0) {
         // |z| > 16 (a third of a line's wavelength points): asymptotic series of w(z) = i / (sqrt(pi) z) *
         // sum_k (2k-1)!! / (2 z^2)^k, 8 terms (the next one is < 5e-16), complex Horner in u = 1 / (2 z^2)
@@ -83,38 +108,42 @@ MALI_VOIGT_HD double voigt_H(double a, double v)
     const double fl = floor(r);
     const double frac = r - fl;
     const bool half = frac < 0.25 || frac > 0.75;        // v is near an integer node -> use the half-integer grid
-    // centre the sum on the node nearest to ... the weights only depend on |n|, the nodes on n: walk both signs
+    // the weights only depend on |n|, the nodes on n: the two signs of a node share one reciprocal (voigt_pair)
     double s = 0.0;
     if (!half) {
-        {
-            const double d = x;
-            s = voigt_weight_int(0) * voigt_rcp(fma(d, d, y2));
-        }
+        s = voigt_weight_int(0) * voigt_rcp(fma(x, x, y2));
 #pragma unroll
         for (int n = 1; n <= kVoigtTerms; ++n) {
-            const double t = n * h, dm = x - t, dp = x + t;
-            s += voigt_weight_int(n) * (voigt_rcp(fma(dm, dm, y2)) + voigt_rcp(fma(dp, dp, y2)));
+            const double t = n * h;
+            s += voigt_weight_int(n) * voigt_pair(x - t, x + t, y2);
         }
     } else {
 #pragma unroll
         for (int n = 0; n <= kVoigtTerms; ++n) {
-            const double t = (n + 0.5) * h, dm = x - t, dp = x + t;
-            s += voigt_weight_half(n) * (voigt_rcp(fma(dm, dm, y2)) + voigt_rcp(fma(dp, dp, y2)));
+            const double t = (n + 0.5) * h;
+            s += voigt_weight_half(n) * voigt_pair(x - t, x + t, y2);
         }
     }
     s *= y;
-    // residue of the pole at t = x + i y (inside the strip of analyticity the rule needs only when y < pi / h)
-    if (y < pi / h && x < 27.0) {
+    // residue of the pole at t = x + i y (inside the strip of analyticity the rule needs only when y < pi / h).  Its
+    // size is at most sqrt(2) exp(y^2 - x^2) -- the grid choice keeps |1 -+ exp(-2 pi i z / h)| >= sqrt(2) -- against
+    // H >= ~ y / (sqrt(pi) (x^2 + y^2)): below 1e-17 of H once x^2 - y^2 > 70 for every a >= 1e-10
+    if (P.res && x * x - y2 < 70.0) {
         const double A = exp(y2 - x * x);                 // |exp(-z^2)|
         double st, ct, sp, cp;
         sincos(2.0 * x * y, &st, &ct);                    // exp(-z^2) = A (ct - i st)
-        sincos(2.0 * pi * frac, &sp, &cp);                // exp(-2 pi i z / h) = E (cp - i sp), x / h = fl + frac
-        const double E = exp(2.0 * pi * y / h);
+#ifdef __CUDA_ARCH__
+        sincospi(2.0 * frac, &sp, &cp);                   // exp(-2 pi i z / h) = E (cp - i sp), x / h = fl + frac
+#else
+        sincos(2.0 * pi * frac, &sp, &cp);
+#endif
         const double sg = half ? 1.0 : -1.0;
-        const double dr = 1.0 + sg * E * cp, di = -sg * E * sp;
+        const double dr = 1.0 + sg * P.E * cp, di = -sg * P.E * sp;
         s += 2.0 * A * (ct * dr - st * di) / (dr * dr + di * di);
     }
     return s;
 }
+
+MALI_VOIGT_HD double voigt_H(double a, double v) { return voigt_H_pre(voigt_pre(a), v); }
 
 }  // namespace mali

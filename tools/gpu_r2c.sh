@@ -3,7 +3,7 @@
 # ncu launch list with DRAM bytes (roofline.traffic), and one --set full capture of the formal-solution kernels
 mkdir -p gpurun_out
 tag=${1:-v18}
-python -m pytest tests -m gpu -x -q 2>&1 | tail -25 > gpurun_out/${tag}_pytest.log
+python -m pytest tests -m gpu -q 2>&1 | tail -40 > gpurun_out/${tag}_pytest.log
 tail -4 gpurun_out/${tag}_pytest.log
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${tag}_bench_reference.json 2> gpurun_out/${tag}_bench_reference.err
@@ -26,4 +26,16 @@ ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum 
     --log-file gpurun_out/${tag}_launches_traffic.csv $CMD > gpurun_out/${tag}_traffic_ncu.log 2>&1
 python tools/traffic_from_launches.py gpurun_out/${tag}_launches_traffic.csv gpurun_out/${tag}_traffic.json | tail -3
 bash tools/gpu_ncu_fs.sh ${tag} | tail -3
+# launch list of the e2e path (upload kernels: re-layout, line profiles) on a 512-column chunk
+CMDE="python bench.py --ncol 512 --iters 1 --steps 1 --warmup 1 --no-cpu --e2e-steps 1"
+$CMDE > gpurun_out/${tag}_e2e_plain.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${tag}_e2e_launches.csv $CMDE > gpurun_out/${tag}_e2e_ncu.log 2>&1
+python - <<PY
+import csv, collections
+tot = collections.Counter(); cnt = collections.Counter()
+for r in csv.DictReader(l for l in open('gpurun_out/${tag}_e2e_launches.csv') if l.startswith('"')):
+    v = float(r['Metric Value'].replace(',', '')); u = r['Metric Unit']
+    tot[r['Kernel Name'][:60]] += v * {'ns': 1e-6, 'us': 1e-3, 'ms': 1.0}.get(u, 1.0); cnt[r['Kernel Name'][:60]] += 1
+for k, v in tot.most_common(14): print('E2E-LAUNCHES %-60s n=%4d total %.3f ms' % (k, cnt[k], v))
+PY
 python tools/gpu_latency.py > gpurun_out/${tag}_latency.json 2> gpurun_out/${tag}_latency.err; tail -c 800 gpurun_out/${tag}_latency.json

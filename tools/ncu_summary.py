@@ -14,7 +14,12 @@ keys = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__
         'lts__t_sector_hit_rate.pct', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
         'smsp__thread_inst_executed_per_inst_executed.ratio', 'launch__occupancy_limit_registers',
         'launch__occupancy_limit_shared_mem', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
-        'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'smsp__inst_executed_pipe_lsu.sum']
+        'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'smsp__inst_executed_pipe_lsu.sum',
+        # the unit that bounds the formal-solution kernels: the L1 data pipe (one 128-byte wavefront per cycle and SM;
+        # LDS / STS / SHFL and global accesses all pass through it)
+        'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum', 'l1tex__data_pipe_lsu_wavefronts_mem_shared_op_st.sum',
+        'l1tex__throughput.avg.pct_of_peak_sustained_elapsed', 'sm__inst_executed_pipe_lsu.sum']
 for vals in rows[2:]:
     for i, h in enumerate(hdr):
         if h in keys:
