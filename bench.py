@@ -219,7 +219,8 @@ def run_lambda_shard(args):
     rank = int(os.environ.get('RANK', '0'))
     json_fd = None
     if world > 1:
-        os.environ.setdefault('NCCL_DEBUG', 'INFO')
+        if os.environ.get('NCCL_DEBUG', '').upper() not in ('INFO', 'TRACE'):
+            os.environ['NCCL_DEBUG'] = 'INFO'      # (the GPU boxes preset WARN: a round-2 run logged no rank lines)
         sys.stdout.flush()
         json_fd = os.dup(1)
         os.dup2(2, 1)
@@ -273,6 +274,8 @@ def main():
     ap.add_argument('--sched', default='',
                     help='explicit e2e upload schedule: comma-separated chunk sizes (the last one repeats); overrides '
                          '--chunk / --first-chunk')
+    ap.add_argument('--split', type=int, default=0,
+                    help='experiment: also time the resident solve issued as K column ranges on K streams')
     ap.add_argument('--workload', default='columns', choices=['columns', 'lambda_shard'],
                     help='columns: the headline column-sharded batch; lambda_shard: BASELINE config 5 experiment, one '
                          'stress column wavelength-sharded over the GPUs with a Gamma all-reduce per iteration')
@@ -306,9 +309,10 @@ def main():
     dev = torch.device('cuda', local)
     json_fd = None
     if world > 1:
-        # NCCL's own log (rank / channel lines: NCCL_DEBUG=INFO unless the launcher says otherwise) is written to the
+        # NCCL's own log (rank / channel lines: NCCL_DEBUG=INFO unless the launcher asks for INFO / TRACE itself) is written to the
         # process's stdout by NCCL; point fd 1 at stderr for everything but the one JSON line, which goes to the real one
-        os.environ.setdefault('NCCL_DEBUG', 'INFO')
+        if os.environ.get('NCCL_DEBUG', '').upper() not in ('INFO', 'TRACE'):
+            os.environ['NCCL_DEBUG'] = 'INFO'      # (the GPU boxes preset WARN: a round-2 run logged no rank lines)
         sys.stdout.flush()
         json_fd = os.dup(1)
         os.dup2(2, 1)
@@ -400,6 +404,48 @@ def main():
     finite = bool(torch.isfinite(eng.t_pops).all().item() and torch.isfinite(eng.t_I).all().item())
     total_units = world * ncol * units_per_col_iter * iters * args.steps
     value = total_units / (ms * 1e-3)
+
+    # ---- experiment (--split K): the same resident solve issued as K column ranges on K streams, so that one range's
+    # DRAM-bound finish kernels (gamma_finish, j_finish, statistical equilibrium: 13 % of an iteration, SMs mostly idle)
+    # can run under another range's formal solution; compared with the single-range solve replayed the same way (both as
+    # CUDA graphs, the per-launch profiling events off)
+    split_side = None
+    if args.split > 1:
+        try:
+            sts = [torch.cuda.Stream(dev) for _ in range(args.split)]
+            per = (ncol + args.split - 1) // args.split
+
+            def solve_split():
+                cur = torch.cuda.current_stream(dev)
+                for i, st_ in enumerate(sts):
+                    c0_, nc_ = i * per, min(per, ncol - i * per)
+                    if nc_ <= 0:
+                        continue
+                    st_.wait_stream(cur)
+                    with torch.cuda.stream(st_):
+                        eng.iterate_async(iters, tolJ=-1.0, col0=c0_, ncol=nc_)
+                for st_ in sts:
+                    cur.wait_stream(st_)
+
+            def timed(fn):
+                for _ in range(max(2, args.warmup)):
+                    fn()
+                barrier()
+                e0.record()
+                for _ in range(args.steps):
+                    fn()
+                e1.record()
+                barrier()
+                return max_over_ranks(e0.elapsed_time(e1)) / args.steps
+
+            ms_one = timed(solve_resident)
+            ms_spl = timed(solve_split)
+            split_side = {'ranges': args.split, 'ms_per_step_single_range': ms_one, 'ms_per_step_split': ms_spl,
+                          'value_single_range': world * ncol * units_per_col_iter * iters / (ms_one * 1e-3),
+                          'value_split': world * ncol * units_per_col_iter * iters / (ms_spl * 1e-3),
+                          'finite': bool(torch.isfinite(eng.t_pops).all().item())}
+        except Exception as ex:
+            split_side = {'error': repr(ex)}
 
     # ---- the same resident solve with the reference's rounding (MALI_ARITH_EXACT): a side number next to the
     # headline, which runs the library's default arithmetic (contracted; both modes are parity-tested)
@@ -925,6 +971,8 @@ def main():
                 'response_function_from_thermodynamic_state': rf_thermo, 'config4_from_thermodynamic_state': c4,
                 'results_finite': finite,
                 'arith': arith_default, 'exact_arith': exact_side}
+        if split_side is not None:
+            line['split_streams_experiment'] = split_side
         if json_fd is not None:
             sys.stdout.flush()
             os.write(json_fd, (json.dumps(line) + '\n').encode())
