@@ -173,7 +173,7 @@ struct mali_model {
     int64_t off_jpart = 0, off_part = 0, upOff = 0;
     int smemClass[3] = {0, 0, 0};   // shared-memory bytes per warp of the three specialised kernels
     std::vector<CopyJob> cjobs;
-    int packChunks = 0;
+    int packChunks = 0, packChunksFields = 0;   // all re-layout chunks; the leading ones that touch record fields
     // device copies
     TileDesc *d_tiles = nullptr;
     SlotDesc *d_slots = nullptr;
@@ -364,7 +364,7 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
     std::vector<int32_t> gijTile0(d->Ntrans, -1);
     std::vector<int32_t> phiTile0(d->Ntrans, -1);
     std::vector<PackSlot> pslots;
-    std::vector<PackChunk> pchunks;
+    std::vector<PackChunk> pchunks, pchunksRows;   // chunks touching the fields; chunks of Vij rows only
     int partRow = 0;
     int64_t rowOff = 0, rowSum = 0;
     for (int ti = 0; ti < m->ntile; ++ti) {
@@ -449,7 +449,13 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
                 if (phiTile0[s.t] < 0) phiTile0[s.t] = ti;
             }
         }
-        for (int e0 = 0; e0 < pt.recSize; e0 += 32) pchunks.push_back(PackChunk{ti, e0});
+        // chunks that hold nothing but Vij rows go to the back of the list: the uploads that leave the line profiles to
+        // compute_phi_kernel launch only the front part (two thirds of the blocks would return at once otherwise, and
+        // the re-layout is bound by the block launch rate, not by bandwidth)
+        for (int e0 = 0; e0 < pt.recSize; e0 += 32) {
+            const bool rowsOnly = (e0 + 32 <= pt.vb) || (e0 >= pt.vb + pt.sf);
+            (rowsOnly ? pchunksRows : pchunks).push_back(PackChunk{ti, e0});
+        }
         ptiles.push_back(pt);
         td.recOff = pt.recOff;
         td.bgOff = vb + jw;
@@ -468,6 +474,8 @@ int mali_model_create(const mali_model_desc *d, int device, mali_model **out)
     }
     m->nPartRows = partRow;
     m->rowStride = rowSum;      // doubles of the table per depth point (all tiles)
+    m->packChunksFields = (int)pchunks.size();
+    pchunks.insert(pchunks.end(), pchunksRows.begin(), pchunksRows.end());
     m->packChunks = (int)pchunks.size();
     std::vector<int32_t> trPartOff(d->Ntrans + 1, 0), trPartRows;
     for (int t = 0; t < d->Ntrans; ++t) {
@@ -812,8 +820,9 @@ static int upload_columns(const mali_model *m, const mali_buffers *b, int32_t co
                                  cudaMemcpyHostToDevice, st));
         }
     }
-    if (m->packChunks > 0) {
-        dim3 grid(m->packChunks, (m->N + 31) / 32, ncol), block(32, 8);
+    const int nPackChunks = nophi ? m->packChunksFields : m->packChunks;
+    if (nPackChunks > 0) {
+        dim3 grid(nPackChunks, (m->N + 31) / 32, ncol), block(32, 8);
         pack_tiles_kernel<<<grid, block, 0, st>>>(m->d_pchunks, m->d_ptiles, m->d_pslots, m->d_wlambda, m->d_alpha, m->N, m->Nrays,
                                                   m->Nspect, m->Lw, staging_dev, L.hostpack, L.hp_bg_chi, L.hp_bg_eta,
                                                   L.hp_bg_sca, b->colconst, L.colconst, m->off_tab, col0, mode);

@@ -108,21 +108,18 @@ MALI_VOIGT_HD double voigt_H_pre(const VoigtPre &P, double v)
     const double fl = floor(r);
     const double frac = r - fl;
     const bool half = frac < 0.25 || frac > 0.75;        // v is near an integer node -> use the half-integer grid
-    // the weights only depend on |n|, the nodes on n: the two signs of a node share one reciprocal (voigt_pair)
+    // One loop serves both grids -- nodes t_n = (n + off) h with off = 0 or 1/2, weights selected per lane -- so that a
+    // warp whose lanes sit on different grids (they do: neighbouring frequencies alternate) does not run two 13-term
+    // sums one after the other.  The two signs of a node share one reciprocal (voigt_pair); the integer grid's node 0
+    // is its own mirror image, hence half its weight.
     double s = 0.0;
-    if (!half) {
-        s = voigt_weight_int(0) * voigt_rcp(fma(x, x, y2));
+    const double off = half ? 0.5 * h : 0.0;
 #pragma unroll
-        for (int n = 1; n <= kVoigtTerms; ++n) {
-            const double t = n * h;
-            s += voigt_weight_int(n) * voigt_pair(x - t, x + t, y2);
-        }
-    } else {
-#pragma unroll
-        for (int n = 0; n <= kVoigtTerms; ++n) {
-            const double t = (n + 0.5) * h;
-            s += voigt_weight_half(n) * voigt_pair(x - t, x + t, y2);
-        }
+    for (int n = 0; n <= kVoigtTerms; ++n) {
+        const double t = n * h + off;
+        const double wi = (n == 0 ? 0.5 : 1.0) * voigt_weight_int(n);
+        const double w = half ? voigt_weight_half(n) : wi;
+        s += w * voigt_pair(x - t, x + t, y2);
     }
     s *= y;
     // residue of the pole at t = x + i y (inside the strip of analyticity the rule needs only when y < pi / h).  Its
@@ -131,7 +128,26 @@ MALI_VOIGT_HD double voigt_H_pre(const VoigtPre &P, double v)
     if (P.res && x * x - y2 < 70.0) {
         const double A = exp(y2 - x * x);                 // |exp(-z^2)|
         double st, ct, sp, cp;
-        sincos(2.0 * x * y, &st, &ct);                    // exp(-z^2) = A (ct - i st)
+        const double th = 2.0 * x * y;                    // exp(-z^2) = A (ct - i st)
+        if (th < 0.25) {
+            // chromospheric damping parameters (a ~ 1e-4 .. 1e-2) keep this angle small: Taylor series to t^13 / t^12
+            // (next terms < 1e-19), a fifth of the cost of the library's sincos
+            const double u = th * th;
+            double ps = fma(u, 1.0 / 6227020800.0, -1.0 / 39916800.0);
+            ps = fma(u, ps, 1.0 / 362880.0);
+            ps = fma(u, ps, -1.0 / 5040.0);
+            ps = fma(u, ps, 1.0 / 120.0);
+            ps = fma(u, ps, -1.0 / 6.0);
+            st = fma(th * u, ps, th);
+            double pc = fma(u, 1.0 / 479001600.0, -1.0 / 3628800.0);
+            pc = fma(u, pc, 1.0 / 40320.0);
+            pc = fma(u, pc, -1.0 / 720.0);
+            pc = fma(u, pc, 1.0 / 24.0);
+            pc = fma(u, pc, -0.5);
+            ct = fma(u, pc, 1.0);
+        } else {
+            sincos(th, &st, &ct);
+        }
 #ifdef __CUDA_ARCH__
         sincospi(2.0 * frac, &sp, &cp);                   // exp(-2 pi i z / h) = E (cp - i sp), x / h = fl + frac
 #else
@@ -139,7 +155,7 @@ MALI_VOIGT_HD double voigt_H_pre(const VoigtPre &P, double v)
 #endif
         const double sg = half ? 1.0 : -1.0;
         const double dr = 1.0 + sg * P.E * cp, di = -sg * P.E * sp;
-        s += 2.0 * A * (ct * dr - st * di) / (dr * dr + di * di);
+        s += 2.0 * A * (ct * dr - st * di) * voigt_rcp(dr * dr + di * di);     // |den|^2 >= 2 (see above)
     }
     return s;
 }
