@@ -227,9 +227,11 @@ __global__ void __launch_bounds__(128) fs_gamma_kernel(const FsParams p)
 struct TileJ {
     int32_t off, stride;   // J-dagger field of the tile's depth-0 record; record stride
 };
-__global__ void j_finish_kernel(double *J, int64_t JStride, const double *scratch, int64_t scratchStride,
-                                int64_t offJpart, int64_t upOff, double *colconst, int64_t colStride, int64_t offTab,
-                                const TileJ *tileJ, int Nspect, int Lw,
+// (memory-latency bound: 32 registers per thread keep all 64 warps of an SM resident)
+__global__ void __launch_bounds__(256, 8)
+j_finish_kernel(double *__restrict__ J, int64_t JStride, const double *__restrict__ scratch, int64_t scratchStride,
+                                int64_t offJpart, int64_t upOff, double *__restrict__ colconst, int64_t colStride, int64_t offTab,
+                                const TileJ *__restrict__ tileJ, int Nspect, int Lw,
                                 unsigned long long *dJbits, const int32_t *done, int col0)
 {
     const int col = col0 + blockIdx.y;
