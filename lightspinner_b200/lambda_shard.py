@@ -19,15 +19,42 @@ import torch.distributed as dist
 from .tables import ModelTables, transition_offsets
 
 
-def lambda_ranges(Nspect, world, align=1):
-    """[(lo, hi)] per rank: contiguous, covering [0, Nspect), boundaries on multiples of `align` (a tile width)."""
+def lambda_ranges(Nspect, world, align=1, cost=None):
+    """[(lo, hi)] per rank: contiguous, covering [0, Nspect), boundaries on multiples of `align` (a tile width).
+    cost: optional per-wavelength work estimate; the boundaries then equalise the ranks' summed cost instead of their
+    wavelength counts (the formal solution of a wavelength costs about 1.1 + its number of active transitions, SURVEY.md
+    8d -- with equal counts the rank holding the line cores was measured 1.5x slower than the mean, and the others
+    spent that time waiting in the exchange)."""
     nblk = (Nspect + align - 1) // align
     out = []
+    if cost is None:
+        for r in range(world):
+            b0 = (nblk * r) // world
+            b1 = (nblk * (r + 1)) // world
+            out.append((min(b0 * align, Nspect), min(b1 * align, Nspect)))
+        return out
+    c = np.zeros(nblk * align)
+    c[:Nspect] = np.asarray(cost, dtype=np.float64)[:Nspect]
+    cum = np.concatenate([[0.0], np.cumsum(c.reshape(nblk, align).sum(axis=1))])      # cost of the first b blocks
+    b_prev = 0
     for r in range(world):
-        b0 = (nblk * r) // world
-        b1 = (nblk * (r + 1)) // world
-        out.append((min(b0 * align, Nspect), min(b1 * align, Nspect)))
+        if r == world - 1:
+            b1 = nblk
+        else:
+            b1 = int(np.searchsorted(cum, cum[-1] * (r + 1) / world))
+            b1 = min(max(b1, b_prev + 1), nblk - (world - 1 - r))     # at least one block for every rank
+        out.append((min(b_prev * align, Nspect), min(b1 * align, Nspect)))
+        b_prev = b1
     return out
+
+
+def wavelength_cost(p):
+    """Work estimate per wavelength of problem `p`: 1.1 + number of transitions active there (31 + 28 A)."""
+    trans = np.asarray(p['trans'], dtype=np.int64).reshape(-1, 6)
+    cost = np.full(int(p['Nspect']), 1.1)
+    for (_, _, _, _, Nblue, Nlam) in trans:
+        cost[int(Nblue):int(Nblue + Nlam)] += 1.0
+    return cost
 
 
 def lambda_shard_problem(p, lo, hi, keep_C):
@@ -78,6 +105,31 @@ def lambda_shard_problem(p, lo, hi, keep_C):
     return q
 
 
+class GammaExchange:
+    """The path's only exchange as ONE collective: every rank contributes [Gamma | dJ] (147 KB for the stress column);
+    after the all-gather each rank adds the contributions in ascending rank order and takes the maximum of the dJ's --
+    a fixed order, so every rank holds the same bits (the replicated statistical equilibrium stays in lockstep) and the
+    result does not depend on the library's reduction tree.  One latency-bound call instead of two (sum, max)."""
+
+    def __init__(self, gamma, dJ, group=None):
+        self.gamma, self.dJ, self.group = gamma.view(-1), dJ.view(-1)[:1], group
+        self.world = dist.get_world_size(group)
+        n = self.gamma.numel()
+        self.send = torch.empty(n + 1, dtype=gamma.dtype, device=gamma.device)
+        self.recv = torch.empty(self.world * (n + 1), dtype=gamma.dtype, device=gamma.device)
+
+    def __call__(self):
+        n = self.gamma.numel()
+        self.send[:n].copy_(self.gamma)
+        self.send[n:].copy_(self.dJ)
+        dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
+        R = self.recv.view(self.world, n + 1)
+        torch.add(R[0, :n], R[1, :n], out=self.gamma)
+        for r in range(2, self.world):
+            self.gamma.add_(R[r, :n])
+        torch.amax(R[:, n:], dim=0, out=self.dJ)
+
+
 class LambdaShardedColumn:
     """One column, wavelength-sharded over the ranks of `group` (one process per GPU, NCCL over NVLink)."""
 
@@ -87,18 +139,17 @@ class LambdaShardedColumn:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         Lw = max(1, 32 // int(p['Nrays']))
-        self.ranges = lambda_ranges(int(p['Nspect']), self.world, align=Lw)
+        self.ranges = lambda_ranges(int(p['Nspect']), self.world, align=Lw, cost=wavelength_cost(p))
         self.lo, self.hi = self.ranges[self.rank]
         self.sub = lambda_shard_problem(p, self.lo, self.hi, keep_C=(self.rank == 0))
         self.eng = MaliEngine(self.sub, 1, device=device, specialize=(p if specialize else False))
         self.eng.upload([self.sub])
+        self.exchange = GammaExchange(self.eng.t_Gamma, self.eng.t_dJ, group) if self.world > 1 else (lambda: None)
 
     def formal_sol_gamma_matrices(self):
         """FS on this rank's wavelengths, then the only exchange of the path: Gamma summed, dJ maximised."""
         self.eng.formal_sol_gamma_async()
-        if self.world > 1:
-            dist.all_reduce(self.eng.t_Gamma, op=dist.ReduceOp.SUM, group=self.group)
-            dist.all_reduce(self.eng.t_dJ, op=dist.ReduceOp.MAX, group=self.group)
+        self.exchange()
         return float(self.eng.t_dJ[0].item())
 
     def stat_equil(self):

@@ -61,12 +61,15 @@ def _worker(rank, world, port, q):
     lo, hi = lambda_ranges(int(p['Nspect']), world, 6)[rank]
     oc = O.OracleContext(lambda_shard_problem(p, lo, hi, keep_C=(rank == 0)))
     hist = []
-    for it in range(1, 7):           # the loop of test.py with the exchange of lambda_shard.LambdaShardedColumn
-        dJ = torch.tensor([oc.formal_sol_gamma_matrices()], dtype=torch.float64)
-        G = torch.from_numpy(np.ascontiguousarray(oc.Gamma))
-        dist.all_reduce(G, op=dist.ReduceOp.SUM)
-        dist.all_reduce(dJ, op=dist.ReduceOp.MAX)
-        oc.Gamma[...] = G.numpy()
+    from lightspinner_b200.lambda_shard import GammaExchange
+    G = torch.zeros(oc.Gamma.size, dtype=torch.float64)
+    dJ = torch.zeros(1, dtype=torch.float64)
+    exchange = GammaExchange(G, dJ)      # the exchange of lambda_shard.LambdaShardedColumn itself (gloo here)
+    for it in range(1, 7):           # the loop of test.py
+        dJ[0] = oc.formal_sol_gamma_matrices()
+        G.copy_(torch.from_numpy(np.ascontiguousarray(oc.Gamma)).view(-1))
+        exchange()
+        oc.Gamma[...] = G.numpy().reshape(oc.Gamma.shape)
         dP = oc.stat_equil(use_scipy=False) if it > 3 else None
         hist.append((float(dJ), dP))
     q.put((rank, oc.n.copy(), hist))
