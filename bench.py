@@ -211,7 +211,8 @@ def reference_numpy_side_number():
 
 def run_lambda_shard(args):
     """BASELINE config 5 (an experiment, not the production path): one stress column -- 10x refined wavelength grid,
-    10-point quadrature, 512 depths -- split over the GPUs by wavelength; every iteration all-reduces Gamma over NCCL.
+    10-point quadrature, 512 depths -- split over the GPUs by wavelength (ranges balanced by work); every iteration exchanges Gamma (one NCCL all-gather of
+    [Gamma | dJ] + a fixed-order sum, lambda_shard.GammaExchange).
     A step is one MALI iteration of the column (strong scaling: the column is fixed)."""
     sys.path.insert(0, os.path.join(ROOT, 'tools'))
     import lambda_shard_experiment as ls
@@ -231,7 +232,7 @@ def run_lambda_shard(args):
                 'warmup': max(6, args.steps), 'ms_per_step': out['ms_per_iteration'], 'higher_is_better': True,
                 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
                 'config': {'workload': 'EXPERIMENT: wavelength-sharded single stress column (BASELINE config 5), Gamma '
-                                       'all-reduce over NCCL every iteration', 'Nspect': out['Nspect'], 'Nrays': out['Nrays'],
+                                       'exchange (one NCCL all-gather + fixed-order sum) every iteration', 'Nspect': out['Nspect'], 'Nrays': out['Nrays'],
                            'Nspace': out['Nspace'], 'parallelism': 'wavelengths sharded over %d GPU(s)' % world},
                 'lambda_shard': out, 'e2e': None, 'gpu_launches': None}
         if json_fd is not None:
