@@ -33,6 +33,31 @@ def test_lambda_ranges_cover_spectrum_on_tile_boundaries():
                     assert a1 == b0 and a0 <= a1 and a1 % align == 0
 
 
+def test_work_balanced_ranges():
+    """Ranges balanced by the per-wavelength work estimate: same covering / alignment rules, every rank gets at least one
+    tile, and on the config-5 fixture the heaviest rank carries less than with equal wavelength counts."""
+    from lightspinner_b200.lambda_shard import wavelength_cost
+    rng = np.random.default_rng(3)
+    for S in (7, 287, 2861):
+        cost = 1.1 + rng.integers(0, 9, S)
+        for world in (1, 2, 3, 8):
+            for align in (1, 3, 6):
+                if (S + align - 1) // align < world:
+                    continue
+                r = lambda_ranges(S, world, align, cost=cost)
+                assert len(r) == world and r[0][0] == 0 and r[-1][1] == S
+                for (a0, a1), (b0, b1) in zip(r[:-1], r[1:]):
+                    assert a1 == b0 and a0 < a1 and a1 % align == 0
+                assert r[-1][0] < r[-1][1]
+    p, _ = load_golden('stress_r10_d512')
+    cost = wavelength_cost(p)
+    S = int(p['Nspect'])
+    for world in (2, 4, 8):
+        heavy = max(cost[a:b].sum() for a, b in lambda_ranges(S, world, 3, cost=cost))
+        even = max(cost[a:b].sum() for a, b in lambda_ranges(S, world, 3))
+        assert heavy < even and heavy < 1.2 * cost.sum() / world
+
+
 @pytest.mark.parametrize('name,world', [('c1_falc_ca', 3), ('c2_falc_cah', 2)])
 def test_shards_reproduce_the_full_formal_solution(oracle, name, world):
     p, _ = load_golden(name)
